@@ -1,0 +1,166 @@
+"""Pins the CPU oracle (oracle/krylov_oracle.py) to the REAL reference: every fixture under
+tests/golden/ was produced by wilson-labs/cola itself (tests/golden/make_golden.py).  The oracle
+restates the same torch ops in the same order, so on CPU it must reproduce them essentially
+bit-for-bit; the tolerances below (1e-6 fp32 / 1e-12 fp64 relative) only absorb thread-count
+dependent BLAS blocking."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import krylov_oracle as ko
+from tests import problems as pb
+from tests.golden_cases import ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    den = 0.5 * (np.linalg.norm(a) + np.linalg.norm(b))
+    return 0.0 if den == 0 else float(np.linalg.norm(a - b) / den)
+
+
+def tol_of(dtype):
+    return 2e-6 if dtype == torch.float32 else 1e-12
+
+
+@pytest.mark.parametrize("name", MATMAT_PROBLEMS)
+def test_matmat(name, golden):
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    X = pb.randn_np((A.shape[1], 6), P["dtype"], 100)
+    g = golden("matmat_" + name)
+    assert rel(A.matmat(X), g["Y"]) < tol_of(P["dtype"])
+    assert rel(A @ X[:, 0].contiguous(), g["y"]) < tol_of(P["dtype"])
+
+
+@pytest.mark.parametrize("case", sorted(CG_CASES))
+def test_cg(case, golden):
+    name, tol, iters = CG_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    x, r, k, info = ko.cg(A, P["B"], tol=tol, max_iters=iters)
+    g = golden(case)
+    assert info["iterations"] == int(g["iterations"])
+    assert len(info["errors"]) == len(g["errors"])
+    t = tol_of(P["dtype"])
+    np.testing.assert_allclose(info["errors"], g["errors"], rtol=50 * t, atol=1e-30)
+    assert rel(x, g["x"]) < 50 * t
+
+
+def test_cg_x0(golden):
+    P = pb.problem("dense96_f32")
+    A = pb.to_oracle(P["spec"])
+    x0 = pb.randn_np(tuple(P["B"].shape), P["dtype"], 77)
+    x, r, k, info = ko.cg(A, P["B"], x0=x0, tol=1e-6, max_iters=500)
+    g = golden("cg_dense96_f32_x0")
+    assert info["iterations"] == int(g["iterations"])
+    assert rel(x, g["x"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", sorted(LANCZOS_CASES))
+def test_lanczos(case, golden):
+    name, m, tol, batched = LANCZOS_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    start = P["B"] if (batched or P["B"].dim() == 1) else P["B"][:, 0].contiguous()
+    Q, alpha, beta, info = ko.lanczos(A, start, m, tol)
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    assert info["iterations"] == int(g["iterations"])
+    assert rel(alpha, g["alpha"]) < 20 * t and rel(beta, g["beta"]) < 20 * t
+    Qn = Q.numpy()
+    if Qn.ndim == 2 and Qn.shape[0] > 1000:
+        Qn = Qn[::16]
+    assert rel(Qn, g["Q"]) < 1e3 * t
+    np.testing.assert_allclose(info["errors"], g["errors"], rtol=1e-3, atol=1e-12)
+
+
+def test_lanczos_early_termination(golden):
+    A = ko.DenseOp(torch.diag(torch.tensor([4., 2., 1.])))
+    Q, alpha, beta, info = ko.lanczos(A, torch.tensor([[1.0, 0.0, 0.0]]).T, 3, 1e-7)
+    g = golden("lanczos_case_early")
+    assert info["iterations"] == int(g["iterations"]) == 2
+    assert beta.shape == g["beta"].shape and alpha.shape == g["alpha"].shape
+    assert float(beta[0, 0]) == 4.0
+
+
+def test_lanczos_manual_known_answers():
+    """Hand-derived answers the reference's own tests pin (tests/algorithms/test_lanczos.py:282-300)."""
+    beta, alpha = [1., 3., 7.], [0.1, 1.0]
+    A = torch.tensor([[beta[2], 0, alpha[1]], [0, beta[0], alpha[0]], [alpha[1], alpha[0], beta[1]]])
+    Q, a, b, info = ko.lanczos(ko.DenseOp(A), torch.tensor([[0.0, 1.0, 0.]]).T, 3, 1e-7)
+    assert info["iterations"] - 1 == 3
+    assert rel(b[0], beta) < 1e-6 and rel(a[0], alpha) < 1e-6
+    beta, alpha = [1., 2., 4.], [0.1, 0.1]
+    A = torch.tensor([[beta[0], alpha[0], 0.], [alpha[0], beta[1], alpha[0]], [0., alpha[0], beta[2]]])
+    Q, a, b, info = ko.lanczos(ko.DenseOp(A), torch.tensor([[1.0, 0., 0.]]).T, 3, 1e-7)
+    assert info["iterations"] - 1 == 3
+    assert rel(b[0], beta) < 1e-6 and rel(a[0], alpha) < 1e-6
+
+
+def test_eig_default_start(golden):
+    P = pb.problem("graph2k_f64")
+    A = pb.to_oracle(P["spec"])
+    start = ko.keyed_randn(A.shape[0], dtype=A.dtype, key=ko.PRNGKey(42))
+    lam, V, info = ko.lanczos_eigs(A, start, 48, 1e-12)
+    g = golden("eig_graph2k_f64_default_start")
+    assert rel(lam[-6:], g["eigvals"]) < 1e-12
+    assert rel(np.abs(V[:, -6:].numpy()[::16]), np.abs(g["eigvecs"])) < 1e-8
+
+
+@pytest.mark.parametrize("case", sorted(ARNOLDI_CASES))
+def test_arnoldi(case, golden):
+    name, m, tol, batched = ARNOLDI_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    start = P["B"] if batched else P["B"][:, 0].contiguous()
+    Q, H, info = ko.arnoldi(A, start, m, tol)
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    assert info["iterations"] == int(g["iterations"])
+    assert rel(H, g["H"]) < 50 * t and rel(Q, g["Q"]) < 1e3 * t
+
+
+def test_arnoldi_eigs(golden):
+    P = pb.problem("nonsym48_f64")
+    A = pb.to_oracle(P["spec"])
+    lam, V, info = ko.arnoldi_eigs(A, P["B"][:, 0].contiguous(), 48, 1e-12)
+    mags = np.sort(np.abs(lam.numpy()))
+    assert rel(mags, golden("eig_arnoldi_nonsym48_f64")["eigvals_sorted_abs"]) < 1e-9
+
+
+@pytest.mark.parametrize("name,m,vtol", [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2),
+                                          ("lap24_f64", 40, 0.25)])
+def test_slq(name, m, vtol, golden):
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    g = golden("slq_" + name)
+    val = ko.slq(A, torch.log, max_iters=m, tol=1e-7, vtol=vtol, key=int(g["key"]))
+    assert abs(float(val) - float(g["logdet"])) <= 20 * tol_of(P["dtype"]) * abs(float(g["logdet"]))
+
+
+@pytest.mark.parametrize("name,m", [("kron884_diag_f32", 25), ("kron465_diag_f64", 30)])
+def test_log_matmat_and_hutch_logdet(name, m, golden):
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    Y, _ = ko.lanczos_unary_matmat(A, torch.log, P["B"], m, 1e-7)
+    t = tol_of(P["dtype"])
+    assert rel(Y, golden("logA_matmat_" + name)["Y"]) < 100 * t
+    g = golden("hutch_logdet_" + name)
+    mean, info = ko.hutchinson_diag(lambda Z: ko.lanczos_unary_matmat(A, torch.log, Z, m, 1e-7)[0], A.shape[0],
+                                    A.dtype, tol=2e-2, max_iters=3, key=int(g["key"]))
+    assert rel(mean, g["diag"]) < 100 * t
+    assert abs(float(mean.sum()) - float(g["logdet"])) <= 100 * t * abs(float(g["logdet"]))
+
+
+def test_hutch_rademacher(golden):
+    P = pb.problem("dense96_f64")
+    A = pb.to_oracle(P["spec"])
+    mean, info = ko.hutchinson_diag(A.matmat, 96, A.dtype, tol=5e-2, max_iters=4, rand="rademacher", key=ko.PRNGKey(7))
+    assert rel(mean, golden("hutch_diag_dense96_f64")["diag"]) < 1e-12
+
+
+def test_rng_key_chain():
+    """SHA-256 key chain (cola/backends/torch_fns.py:222-230): values computed by the reference."""
+    assert ko.PRNGKey(42) == ko.sha_key(42)
+    k = ko.PRNGKey(42)
+    assert 0 <= k < 2**32 - 1 and ko.next_key(k) != k
