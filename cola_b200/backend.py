@@ -1,0 +1,201 @@
+"""The "CUDA torch backend" of the Krylov path: a ctypes binding of libcola_b200.so (C ABI in
+include/cola_b200.h).  It plays the role cola/backends/torch_fns.py plays for the reference, but instead
+of ~110 eager array functions it exposes the handful of fused kernels the loops need.
+
+There is NO fallback: if the shared library is missing or an operand is not a contiguous CUDA tensor of
+a supported dtype, calls raise.  torch is used only for device memory and streams.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libcola_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cola_b200.h")
+
+_CTYPES = {
+    "int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
+    "void": None,
+}
+
+
+def parse_header(path=HEADER_PATH):
+    """Returns {name: (restype, [argtypes])} for every function declared in the C header, so the header stays
+    the single source of truth for the ABI."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    decls = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(cola_\w+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if "*" in ret:
+            restype = ctypes.c_char_p if "char" in ret else ctypes.c_void_p
+        else:
+            restype = _CTYPES[ret.replace("const", "").strip()]
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.c_void_p)
+                else:
+                    base = a.replace("const", "").split()[0]
+                    argtypes.append(_CTYPES[base])
+        decls[name] = (restype, argtypes)
+    return decls
+
+
+class CgCtl(ctypes.Structure):
+    """Mirror of cola_cg_ctl_t (device-resident; this host copy is only for reading it back)."""
+    _fields_ = [("it", ctypes.c_int32), ("done", ctypes.c_int32), ("max_iters", ctypes.c_int32), ("k", ctypes.c_int32)]
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m cola_b200.build` "
+                               "(cola_b200 has no CPU or eager-torch fallback)")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.decls = parse_header()
+        for name, (restype, argtypes) in self.decls.items():
+            fn = getattr(self.cdll, name)  # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = restype, argtypes
+
+    def call(self, name, *args):
+        rc = getattr(self.cdll, name)(*args)
+        if rc != 0:
+            msg = self.cdll.cola_last_error()
+            raise RuntimeError(f"{name} failed with status {rc}: {msg.decode() if msg else ''}")
+
+    def launch_count(self):
+        return int(self.cdll.cola_launch_count())
+
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = _Lib()
+    return _LIB
+
+
+SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def sfx(dtype):
+    try:
+        return SUFFIX[dtype]
+    except KeyError:
+        raise TypeError(f"cola_b200 supports float32/float64 operators on CUDA, got {dtype}") from None
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("cola_b200 is a CUDA-only path: got a CPU tensor (no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("cola_b200 kernels need contiguous operands")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def off_ptr(t, elem_offset):
+    """Pointer to element `elem_offset` of contiguous CUDA tensor t."""
+    if not (t.is_cuda and t.is_contiguous()):
+        raise RuntimeError("cola_b200 kernels need contiguous CUDA operands")
+    return ctypes.c_void_p(t.data_ptr() + elem_offset * t.element_size())
+
+
+def scalar(dtype, x):
+    return ctypes.c_float(x) if dtype == torch.float32 else ctypes.c_double(x)
+
+
+# ------------------------------------------------------------------------------------------------
+# thin tensor-level wrappers (one per C entry point family)
+# ------------------------------------------------------------------------------------------------
+def col_dots(X, Y, dots, gate=None):
+    n, k = X.shape
+    lib().call(f"cola_col_dots_{sfx(X.dtype)}", ptr(X), ptr(Y, X.dtype), n, k, k, ptr(dots, torch.float64), ptr(gate),
+               stream_ptr())
+
+
+def col_scale(X, Y, sq, take_sqrt, mode, a=1.0, gate=None):
+    n, k = X.shape
+    lib().call(f"cola_col_scale_{sfx(X.dtype)}", ptr(X), ptr(Y, X.dtype), n, k, k, ptr(sq, torch.float64),
+               int(take_sqrt), int(mode), scalar(X.dtype, a), ptr(gate), stream_ptr())
+
+
+def axpby(X, Y, a, b, gate=None):
+    n, k = X.shape
+    lib().call(f"cola_axpby_{sfx(X.dtype)}", ptr(X), ptr(Y, X.dtype), n, k, k, scalar(X.dtype, a), scalar(X.dtype, b),
+               ptr(gate), stream_ptr())
+
+
+def diag_matmat(X, Y, shift, diag, accumulate, dots=None, dots_row=None, gate=None):
+    n, k = X.shape
+    lib().call(f"cola_diag_matmat_{sfx(X.dtype)}", ptr(X), k, ptr(Y, X.dtype), k, n, k, scalar(X.dtype, shift),
+               ptr(diag, X.dtype) if diag is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
+               stream_ptr())
+
+
+def csr_spmm(rowptr, colidx, vals, shape, nnz, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False, dots=None,
+             dots_row=None, gate=None):
+    k = X.shape[1]
+    dt = vals.dtype
+    lib().call(f"cola_csr_spmm_{sfx(dt)}", ptr(rowptr, torch.int32), ptr(colidx, torch.int32), ptr(vals), shape[0],
+               shape[1], nnz, ptr(X, dt), k, k, ptr(Y, dt), k, scalar(dt, alpha), scalar(dt, shift),
+               ptr(diag, dt) if diag is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
+               stream_ptr())
+
+
+def mode_contract(M, d_out, d_in, pre, post, inp, out, alpha=1.0, shift=0.0, diag=None, epi_x=None, accumulate=False,
+                  dots=None, dots_row=None, gate=None):
+    """inp/out/diag/epi_x are ctypes pointers or tensors (tensors are converted)."""
+    dt = M.dtype
+
+    def p(x):
+        return x if (x is None or isinstance(x, ctypes.c_void_p)) else ptr(x, dt)
+
+    lib().call(f"cola_mode_contract_{sfx(dt)}", ptr(M), M.stride(0), d_out, d_in, pre, post, p(inp), p(out),
+               scalar(dt, alpha), scalar(dt, shift), p(diag), p(epi_x), int(accumulate), ptr(dots), ptr(dots_row),
+               ptr(gate), stream_ptr())
+
+
+def reorth_dots(V, j0, j1, W, C, gate=None):
+    """V (n_vec, n, b) contiguous, W (n, b), C (n_vec, b) float64."""
+    n, b = W.shape
+    lib().call(f"cola_reorth_dots_{sfx(W.dtype)}", ptr(V, W.dtype), n * b, j0, j1, ptr(W), n, b, ptr(C, torch.float64),
+               ptr(gate), stream_ptr())
+
+
+def reorth_update(V, j0, j1, W, C, sign=-1.0, wnorm2=None, gate=None):
+    n, b = W.shape
+    lib().call(f"cola_reorth_update_{sfx(W.dtype)}", ptr(V, W.dtype), n * b, j0, j1, ptr(W), n, b,
+               ptr(C, torch.float64), scalar(W.dtype, sign), ptr(wnorm2), ptr(gate), stream_ptr())
+
+
+def lanczos_three_term(W, Vi, Vim1, alpha_acc, beta_prev_sq, gate=None):
+    n, b = W.shape
+    lib().call(f"cola_lanczos_three_term_{sfx(W.dtype)}", ptr(W), ptr(Vi, W.dtype),
+               ptr(Vim1, W.dtype) if Vim1 is not None else None, n, b, ptr(alpha_acc, torch.float64),
+               ptr(beta_prev_sq) if beta_prev_sq is not None else None, ptr(gate), stream_ptr())
+
+
+def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
+    n, b = W.shape
+    lib().call(f"cola_mgs_link_{sfx(W.dtype)}", ptr(W), ptr(Qprev) if Qprev is not None else None,
+               ptr(hprev) if hprev is not None else None, ptr(Qcur) if Qcur is not None else None,
+               ptr(hcur) if hcur is not None else None, ptr(wnorm2) if wnorm2 is not None else None, n, b, ptr(gate),
+               stream_ptr())

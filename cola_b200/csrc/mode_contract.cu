@@ -1,0 +1,230 @@
+// Batched mode contraction  out[p,a,q] = alpha * sum_j M[a,j] in[p,j,q]  (+ fused operator epilogue).
+//
+// One primitive serves three reference operators without any of their moveaxis/reshape/concat copies:
+//   Dense._matmat      cola/ops/operators.py:26-28     pre = 1,            post = k
+//   Kronecker._matmat  cola/ops/operators.py:216-223   one call per factor (pre = prod earlier dims,
+//                                                      post = prod later dims * k)
+//   BlockDiag._matmat  cola/ops/operators.py:299-310   pre = multiplicity, post = k, one call per block
+//
+// This file is the exact-arithmetic SIMT path (fp32 and fp64, any shape).  Two kernels:
+//   mc_tile_kernel   64x64x16 shared-memory tiled GEMM per (p, a-tile, q-tile), 4x4 register micro-tiles;
+//   mc_thin_kernel   post <= 8 (GEMV-like: single RHS solves, Lanczos with one start vector): one warp per
+//                    output row, lanes stride over j so M is read coalesced exactly once.
+// The fp32 tensor-core path for large Kronecker factors lives in kron_tc.cu.
+#include "sweep.cuh"
+
+namespace cola {
+
+template <typename T>
+struct McArgs {
+  const T* M; int64_t ldm, d_out, d_in, pre, post;
+  const T* in; T* out;
+  T alpha, shift; const T* diag; const T* epi_x; int accumulate;
+  double* dots; const int32_t* dots_row; const int32_t* gate;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16, MC_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(MC_THREADS) mc_tile_kernel(McArgs<T> a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  __shared__ T As[BK][BM + 4];
+  __shared__ T Bs[BK][BN + 4];
+  __shared__ double red[MC_THREADS * 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;  // thread owns rows ty*4..+3, cols tx*4..+3 of the tile
+  const int64_t na = (a.d_out + BM - 1) / BM, nq = (a.post + BN - 1) / BN;
+  double dacc[4] = {0.0, 0.0, 0.0, 0.0};
+  const bool epi = (a.shift != (T)0) || a.diag || a.dots;
+
+  for (int64_t qt = blockIdx.y; qt < nq; qt += gridDim.y) {
+    const int64_t q0 = qt * BN;
+    for (int64_t t = blockIdx.x; t < a.pre * na; t += gridDim.x) {
+      const int64_t p = t / na, a0 = (t - p * na) * BM;
+      const T* inp = a.in + p * a.d_in * a.post;
+      T acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = (T)0;
+
+      for (int64_t k0 = 0; k0 < a.d_in; k0 += BK) {
+        // M tile (BM x BK), stored transposed; 1024 elements / 256 threads
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int idx = tid + e * MC_THREADS;
+          int kk = idx % BK, mm = idx / BK;
+          int64_t ga = a0 + mm, gk = k0 + kk;
+          As[kk][mm] = (ga < a.d_out && gk < a.d_in) ? a.M[ga * a.ldm + gk] : (T)0;
+        }
+        // in tile (BK x BN): q contiguous -> coalesced
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int idx = tid + e * MC_THREADS;
+          int nn = idx % BN, kk = idx / BN;
+          int64_t gk = k0 + kk, gq = q0 + nn;
+          Bs[kk][nn] = (gk < a.d_in && gq < a.post) ? inp[gk * a.post + gq] : (T)0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          T av[4], bv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        }
+        __syncthreads();
+      }
+      // epilogue on the flattened (pre*d_out, post) matrix
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t ga = a0 + ty * 4 + i;
+        if (ga >= a.d_out) continue;
+        const int64_t row = p * a.d_out + ga;
+        const T d = a.diag ? a.diag[row] : (T)0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t gq = q0 + tx * 4 + j;
+          if (gq >= a.post) continue;
+          const int64_t o = row * a.post + gq;
+          T tval = a.alpha * acc[i][j];
+          T xo = (T)0;
+          if (epi) {
+            xo = a.epi_x[o];
+            if (a.shift != (T)0) tval += a.shift * xo;
+            if (a.diag) tval += d * xo;
+          }
+          if (a.accumulate) tval += a.out[o];
+          a.out[o] = tval;
+          if (a.dots) dacc[j] += (double)xo * (double)tval;
+        }
+      }
+    }
+  }
+  if (a.dots) {  // host guarantees gridDim.y == nq here, so this thread's 4 columns are fixed
+    const int64_t q0 = (int64_t)blockIdx.y * BN;
+    double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.post : 0) + q0;
+    block_col_reduce<4>(red, dacc, true, tid, ty, tx, 16, 16, (int64_t)tx * 4, a.post - q0, -1, out);
+  }
+}
+
+constexpr int THIN_MAX = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(MC_THREADS) mc_thin_kernel(McArgs<T> a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  __shared__ double red[(MC_THREADS / 32) * THIN_MAX];
+  const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+  const int nwarps = MC_THREADS / 32;
+  const int post = (int)a.post;
+  const bool epi = (a.shift != (T)0) || a.diag || a.dots;
+  double dacc[THIN_MAX];
+#pragma unroll
+  for (int q = 0; q < THIN_MAX; ++q) dacc[q] = 0.0;
+  const int64_t total = a.pre * a.d_out;
+  for (int64_t row = (int64_t)blockIdx.x * nwarps + warp; row < total; row += (int64_t)gridDim.x * nwarps) {
+    const int64_t p = row / a.d_out, ga = row - p * a.d_out;
+    const T* inp = a.in + p * a.d_in * a.post;
+    const T* mrow = a.M + ga * a.ldm;
+    T acc[THIN_MAX];
+#pragma unroll
+    for (int q = 0; q < THIN_MAX; ++q) acc[q] = (T)0;
+    for (int64_t j = lane; j < a.d_in; j += 32) {
+      const T m = mrow[j];
+#pragma unroll
+      for (int q = 0; q < THIN_MAX; ++q)
+        if (q < post) acc[q] += m * inp[j * post + q];
+    }
+#pragma unroll
+    for (int q = 0; q < THIN_MAX; ++q) {
+      if (q < post) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+      }
+    }
+    if (lane == 0) {
+      const T d = a.diag ? a.diag[row] : (T)0;
+      for (int q = 0; q < post; ++q) {
+        const int64_t o = row * post + q;
+        T tval = a.alpha * acc[q];
+        T xo = (T)0;
+        if (epi) {
+          xo = a.epi_x[o];
+          if (a.shift != (T)0) tval += a.shift * xo;
+          if (a.diag) tval += d * xo;
+        }
+        if (a.accumulate) tval += a.out[o];
+        a.out[o] = tval;
+        dacc[q] += (double)xo * (double)tval;
+      }
+    }
+  }
+  if (a.dots) {
+    if (lane == 0)
+      for (int q = 0; q < post; ++q) red[warp * THIN_MAX + q] = dacc[q];
+    __syncthreads();
+    if (threadIdx.x < post) {
+      double s = 0.0;
+      for (int w = 0; w < nwarps; ++w) s += red[w * THIN_MAX + threadIdx.x];
+      double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.post : 0);
+      atomicAdd(out + threadIdx.x, s);
+    }
+  }
+}
+
+template <typename T>
+int mode_contract(const T* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t pre, int64_t post, const T* in,
+                  T* out, T alpha, T shift, const T* diag, const T* epi_x, int accumulate, double* dots,
+                  const int32_t* dots_row, const int32_t* gate, cudaStream_t st) {
+  COLA_REQUIRE(M && in && out, "mode_contract: null pointer");
+  COLA_REQUIRE(in != out, "mode_contract: in and out must not alias");
+  COLA_REQUIRE(ldm >= d_in, "mode_contract: ldm < d_in");
+  const bool epi = (shift != (T)0) || diag || dots;
+  COLA_REQUIRE(!epi || (epi_x && d_out == d_in), "mode_contract: shift/diag/dots need epi_x and a square factor");
+  if (pre <= 0 || post <= 0 || d_out <= 0) return COLA_OK;
+  McArgs<T> a{M, ldm, d_out, d_in, pre, post, in, out, alpha, shift, diag, epi_x, accumulate, dots, dots_row, gate};
+  if (post <= THIN_MAX) {
+    int64_t rows = pre * d_out;
+    int64_t grid = (rows + (MC_THREADS / 32) - 1) / (MC_THREADS / 32);
+    int64_t cap = (int64_t)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    mc_thin_kernel<T><<<(unsigned)grid, MC_THREADS, 0, st>>>(a);
+    return cuda_status("mode_contract(thin)");
+  }
+  const int64_t na = (d_out + BM - 1) / BM, nq = (post + BN - 1) / BN;
+  COLA_REQUIRE(!dots || nq <= 65535, "mode_contract: dots with post > 4M columns unsupported");
+  int64_t gy = nq < 65535 ? nq : 65535;
+  int64_t gx = pre * na;
+  int64_t want = ((int64_t)sm_count() * 4 + gy - 1) / gy;  // ~4 CTAs per SM in total
+  if (dots && gx > want) gx = want;                        // persistent over (p, a-tile): fixed columns per thread
+  if (gx > 2147483647LL) gx = 2147483647LL;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  mc_tile_kernel<T><<<grid, MC_THREADS, 0, st>>>(a);
+  return cuda_status("mode_contract(tile)");
+}
+
+}  // namespace cola
+
+using namespace cola;
+extern "C" {
+int cola_mode_contract_f32(const float* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t pre, int64_t post,
+                           const float* in, float* out, float alpha, float shift, const float* diag,
+                           const float* epi_x, int accumulate, double* dots, const int32_t* dots_row,
+                           const int32_t* gate, void* stream) {
+  return mode_contract<float>(M, ldm, d_out, d_in, pre, post, in, out, alpha, shift, diag, epi_x, accumulate, dots,
+                              dots_row, gate, reinterpret_cast<cudaStream_t>(stream));
+}
+int cola_mode_contract_f64(const double* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t pre, int64_t post,
+                           const double* in, double* out, double alpha, double shift, const double* diag,
+                           const double* epi_x, int accumulate, double* dots, const int32_t* dots_row,
+                           const int32_t* gate, void* stream) {
+  return mode_contract<double>(M, ldm, d_out, d_in, pre, post, in, out, alpha, shift, diag, epi_x, accumulate, dots,
+                               dots_row, gate, reinterpret_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,131 @@
+// Generic streaming sweep over an (n, k) row-major block with fused per-column reductions.
+//
+// All vector-update kernels of the Krylov loops (CG x/r/p updates, Lanczos three-term step, MGS links,
+// column dots / scalings) are instances of this one template: every element of every operand is read
+// exactly once with the widest aligned vector access, per-column partial sums live in registers (a thread
+// always owns the same columns), are tree-reduced across the block's rows in shared memory and leave the
+// SM as one fp64 atomicAdd per column per block.  HBM-bound by construction: bytes = sum of operand sizes.
+#pragma once
+#include "common.cuh"
+
+namespace cola {
+
+constexpr int kSweepThreads = 256;
+
+// Block-level reduction of per-thread column partials: thread (r,l) holds VEC partial sums for columns
+// c0..c0+VEC-1; partials of equal l are tree-summed over r in shared memory (r need not span a power of two)
+// and row 0 issues one fp64 atomicAdd per column.  `red` must hold blockDim.x*VEC doubles.
+template <int VEC>
+__device__ __forceinline__ void block_col_reduce(double* red, const double (&acc)[VEC], bool active, int tid, int r,
+                                                 int l, int lanes, int rows, int64_t c0, int64_t k, int64_t colmask,
+                                                 double* out) {
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[tid * VEC + v] = active ? acc[v] : 0.0;
+  __syncthreads();
+  int span = 1;
+  while (span < rows) span <<= 1;
+  for (int s = span >> 1; s > 0; s >>= 1) {
+    if (r < s && r + s < rows) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) red[(r * lanes + l) * VEC + v] += red[((r + s) * lanes + l) * VEC + v];
+    }
+    __syncthreads();
+  }
+  if (r == 0 && c0 < k) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) atomicAdd(out + ((c0 + v) & colmask), red[l * VEC + v]);
+  }
+}
+
+// Op concept:
+//   static constexpr int NACC;                       number of per-column reductions
+//   struct Regs;                                     registers holding one row-chunk of every operand
+//   __device__ bool enabled()                        false => whole kernel is a no-op (device-side gate)
+//   __device__ void setup(int64_t c0)                per-thread column scalars (alpha, beta, ...)
+//   __device__ void load(int64_t row, int64_t c0, Regs&)            issue the loads
+//   __device__ void finish(int64_t row, int64_t c0, Regs&, acc)     arithmetic, stores, partial sums
+//   __device__ double* out(int a)                    accumulator row for reduction a (k doubles) or nullptr
+// colmask: -1 normally; 0 when an (n,1) vector is viewed as (n/VEC, VEC) ("folded"): every lane then maps to
+// column 0 for per-column scalars and reductions.
+template <typename T, int VEC, typename Op>
+__global__ void __launch_bounds__(kSweepThreads)
+    sweep_kernel(int64_t n, int64_t k, int lanes, int rows_per_pass, int64_t colmask, Op op) {
+  constexpr int NACC = Op::NACC;
+  if (!op.enabled()) return;
+  const int tid = threadIdx.x;
+  const int r = tid / lanes, l = tid - r * lanes;
+  const int64_t c0 = (int64_t)l * VEC;
+  const bool active = (r < rows_per_pass) && (c0 < k);
+  double acc[NACC > 0 ? NACC : 1][VEC];
+#pragma unroll
+  for (int a = 0; a < (NACC > 0 ? NACC : 1); ++a)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[a][v] = 0.0;
+
+  if (active) {
+    op.setup(c0);
+    const int64_t stride = (int64_t)gridDim.x * rows_per_pass;
+    int64_t row = (int64_t)blockIdx.x * rows_per_pass + r;
+    // two rows in flight per thread: doubles the bytes outstanding per warp
+    for (; row + stride < n; row += 2 * stride) {
+      typename Op::Regs ra, rb;
+      op.load(row, c0, ra);
+      op.load(row + stride, c0, rb);
+      op.finish(row, c0, ra, acc);
+      op.finish(row + stride, c0, rb, acc);
+    }
+    if (row < n) {
+      typename Op::Regs ra;
+      op.load(row, c0, ra);
+      op.finish(row, c0, ra, acc);
+    }
+  }
+
+  if constexpr (NACC > 0) {
+    __shared__ double red[kSweepThreads * VEC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      double* out = op.out(a);
+      if (out == nullptr) continue;  // uniform across the grid
+      block_col_reduce<VEC>(red, acc[a], active, tid, r, l, lanes, rows_per_pass, c0, k, colmask, out);
+    }
+  }
+}
+
+// Host launcher: splits very wide blocks into column slabs of at most kSweepThreads*VEC columns so that
+// the kernel's "one column chunk per thread" invariant holds; `make(c_off)` builds the Op for a slab.
+template <typename T, int VEC, typename MakeOp>
+int launch_sweep(int64_t n, int64_t k, int64_t colmask, cudaStream_t st, MakeOp make, const char* name) {
+  if (n <= 0 || k <= 0) return COLA_OK;
+  const int64_t slab = (int64_t)kSweepThreads * VEC;
+  for (int64_t c = 0; c < k; c += slab) {
+    int64_t kk = (k - c < slab) ? (k - c) : slab;
+    RowMap m = row_map(kk, VEC, kSweepThreads);
+    int64_t tiles = (n + m.rows_per_pass - 1) / m.rows_per_pass;
+    int64_t tiles2 = (tiles + 1) / 2;
+    int64_t grid = (int64_t)sm_count() * 8;  // 8 x 256 threads = full occupancy, whole waves
+    if (grid > tiles2) grid = tiles2 > 0 ? tiles2 : 1;
+    auto op = make(c);
+    sweep_kernel<T, VEC, decltype(op)><<<(unsigned)grid, kSweepThreads, 0, st>>>(n, kk, m.lanes, m.rows_per_pass,
+                                                                                  colmask, op);
+    int rc = cuda_status(name);
+    if (rc) return rc;
+  }
+  return COLA_OK;
+}
+
+// dispatch on the vector width
+#define COLA_DISPATCH_VEC(T, vec, CALL)          \
+  do {                                           \
+    if constexpr (sizeof(T) == 4) {              \
+      if ((vec) == 4) { constexpr int VEC = 4; CALL; } \
+      else if ((vec) == 2) { constexpr int VEC = 2; CALL; } \
+      else { constexpr int VEC = 1; CALL; }      \
+    } else {                                     \
+      if ((vec) == 2) { constexpr int VEC = 2; CALL; } \
+      else { constexpr int VEC = 1; CALL; }      \
+    }                                            \
+  } while (0)
+
+}  // namespace cola

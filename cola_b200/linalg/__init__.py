@@ -1,0 +1,8 @@
+from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
+from .arnoldi import arnoldi, arnoldi_eigs, arnoldi_fact
+from .cg import CG, cg, run_batched_cg
+from .dispatch import (Arnoldi, Cholesky, Eigh, Exact, Lanczos, diag, eig, exact_diag, get_slice, inv, log, logdet,
+                       slogdet, solve, trace)
+from .lanczos import lanczos, lanczos_eigs, lanczos_fact
+from .stochastic import (Hutch, LanczosUnary, hutchinson_diag_estimate, slq_fwd, slq_per_probe,
+                         stochastic_lanczos_quad)

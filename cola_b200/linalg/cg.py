@@ -1,0 +1,124 @@
+"""Batched (multi-RHS) conjugate gradients on the fused sm_100a kernels.
+
+Same interface and semantics as the reference (cola/linalg/inverse/cg.py): `CG(tol, max_iters, pbar, x0, P)`,
+`cg(A, rhs, ...) -> (soln, info)`, `run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar)
+-> (x, r, k, info)` with `info = {'iterations', 'errors', 'iteration_time'}` as built by
+cola/utils/torch_tqdm.py:7-71.
+
+What is different underneath (see DESIGN.md "CG"):
+  * one iteration = 3 kernels + a 1-block scalar kernel instead of ~87 eager ATen calls
+      matmat(+shift/diag epilogue) with the p^T A p column dots fused      (cg.py:145, 157-158)
+      x += alpha p ; r -= alpha Ap ; gamma' = <r,r>                         (cg.py:147-150, 165-166)
+      p  = r + beta p                                                      (cg.py:151-153)
+  * alpha, beta, the has_converged mask, the iteration counter and the stopping rule live in a
+    device-resident control block; the host only polls it every `check_every` iterations, so the two
+    device->host syncs per iteration of torch_tqdm.py:42,88 are gone;
+  * the per-iteration residual norms are kept on the device (gamma trace) and `info['errors']` is rebuilt
+    from them once at the end.
+"""
+import time
+from dataclasses import dataclass
+from typing import Any
+
+import numpy as np
+import torch
+
+from .. import backend as be
+from ..ops import I_like, Identity, LinearOperator
+from .algorithm_base import Algorithm
+
+_small_value = 1e-40
+CHECK_EVERY = 16  # iterations enqueued between polls of the device-side stop flag
+
+
+@dataclass
+class CG(Algorithm):
+    """cola/linalg/inverse/cg.py:13-36"""
+    tol: float = 1e-6
+    max_iters: int = 1000
+    pbar: bool = False
+    x0: Any = None
+    P: Any = None
+
+    def __call__(self, A, b):
+        return cg(A, b, **self.__dict__)
+
+
+def cg(A: LinearOperator, rhs, x0=None, P=None, tol=1e-6, max_iters=5000, pbar=False):
+    """cola/linalg/inverse/cg.py:39-69"""
+    is_vector = len(rhs.shape) == 1
+    if x0 is None:
+        x0 = None  # zero initial guess: r0 = b exactly, the A @ x0 matmat is skipped
+    if is_vector:
+        rhs = rhs[..., None]
+        x0 = x0[..., None] if x0 is not None else None
+    if P is None:
+        P = I_like(A)
+    soln, *_, infodict = run_batched_cg(A, rhs, x0, max_iters, tol, P, pbar=pbar)
+    soln = soln.reshape(-1) if is_vector else soln
+    return soln, infodict
+
+
+def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
+    """cola/linalg/inverse/cg.py:94-119 on the device.  b (n,k) -> (x (n,k), r (n,k), k_iters, info)."""
+    if not isinstance(preconditioner, Identity):
+        raise NotImplementedError("cola_b200 CG runs with the identity preconditioner only "
+                                  "(Nystrom preconditioning is a 'next' row, DESIGN.md)")
+    if not b.is_cuda:
+        raise RuntimeError("cola_b200 is a CUDA-only path: right-hand side is on the CPU (no CPU fallback)")
+    dt = A.dtype
+    b = b.to(dt).contiguous()
+    n, k = b.shape
+    dev = b.device
+    max_iters = int(max_iters)
+    lib = be.lib()
+    sx = be.sfx(dt)
+    st = be.stream_ptr
+
+    # ---- setup: normalise RHS, residual, gamma0, tolerances (cg.py:96-101, 122-130)
+    mult_sq = torch.zeros(k, dtype=torch.float64, device=dev)
+    be.col_dots(b, b, mult_sq)
+    r = torch.empty_like(b)
+    be.col_scale(b, r, mult_sq, take_sqrt=True, mode=1)          # b / ||b|| (safe)
+    if x0 is None:
+        x = torch.zeros_like(b)
+    else:
+        x = x0.to(dt).contiguous().clone()
+        ax = torch.empty_like(b)
+        A.matmat_into(x, ax)
+        be.axpby(ax, r, -1.0, 1.0)                               # r0 = b - A x0
+        del ax
+    p = r.clone()
+    ap = torch.empty_like(b)
+    gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)
+    pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
+    be.col_dots(r, r, gamma[0])
+    tol_eff = torch.empty(k, dtype=dt, device=dev)
+    lib.call(f"cola_cg_tol_{sx}", be.ptr(gamma), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
+    ctl = torch.tensor([0, 0, max_iters, k], dtype=torch.int32, device=dev)
+    it_ptr, done_ptr = ctl[0:1], ctl[1:2]
+    lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 0, st())   # initial cond_fun
+
+    t0 = time.time()
+    it, done = 0, 0
+    while True:
+        c = ctl.cpu()
+        it, done = int(c[0]), int(c[1])
+        if done:
+            break
+        for _ in range(min(CHECK_EVERY, max_iters - it)):
+            A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)
+            lib.call(f"cola_cg_update_xr_{sx}", be.ptr(x), be.ptr(r), be.ptr(p), be.ptr(ap), n, k, k, be.ptr(ctl),
+                     be.ptr(gamma), be.ptr(pap), be.ptr(gamma), st())
+            lib.call(f"cola_cg_update_p_{sx}", be.ptr(r), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma), st())
+            lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
+    elapsed = time.time() - t0
+
+    # ---- info dict exactly as while_loop_winfo builds it (torch_tqdm.py:35-62): the tracked error is sampled
+    # before every cond evaluation (it+1 of them) and once more after the loop; the first two are dropped.
+    trace = torch.sqrt(gamma[:it + 1]).mean(dim=1).cpu().numpy()
+    samples = np.concatenate([trace, trace[-1:]])
+    info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
+    be.col_scale(x, x, mult_sq, take_sqrt=True, mode=0)          # x * ||b||  (cg.py:119)
+    be.col_scale(r, r, mult_sq, take_sqrt=True, mode=0)
+    return x, r, it, info

@@ -1,0 +1,253 @@
+"""The cola.linalg dispatch surface for the Krylov path: solve / inv / eig / logdet / slogdet / trace / diag with
+the reference's signatures (cola/linalg/inverse/inv.py, eig/eigs.py, logdet/logdet.py, trace/diag_trace.py,
+unary/unary.py:249-262).  The reference resolves these with plum multiple dispatch; here the same rules are
+plain isinstance chains (plum is not a dependency of this package).  Only rules that lead to the Krylov loops
+or to closed forms of the hot-path operators are restated; dense small-matrix algorithms (Cholesky/LU/Eigh) are
+torch library calls exactly as in the reference and are not part of the accelerated path."""
+from dataclasses import dataclass
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from .. import rng
+from ..ops import (PSD, BlockDiag, Dense, Diagonal, Identity, Kronecker, LinearOperator, Product, ScalarMul,
+                   SelfAdjoint, Unitary, lazify)
+from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
+from .arnoldi import arnoldi, arnoldi_eigs
+from .cg import CG
+from .lanczos import lanczos, lanczos_eigs
+from .stochastic import Hutch, LanczosUnary, hutchinson_diag_estimate
+
+
+@dataclass
+class Lanczos(Algorithm):
+    """cola/linalg/decompositions/decompositions.py:116-144"""
+    start_vector: Any = None
+    max_iters: int = 1_000
+    tol: float = 1e-6
+    pbar: bool = False
+    key: Optional[Any] = None
+
+    def __call__(self, A: LinearOperator):
+        return lanczos(A, **self.__dict__)
+
+
+@dataclass
+class Arnoldi(Algorithm):
+    """cola/linalg/decompositions/decompositions.py:60-88"""
+    start_vector: Any = None
+    max_iters: int = 1_000
+    tol: float = 1e-6
+    pbar: bool = False
+    key: Optional[Any] = None
+
+    def __call__(self, A: LinearOperator):
+        return arnoldi(A, **self.__dict__)
+
+
+@dataclass
+class Cholesky(Algorithm):
+    pass
+
+
+@dataclass
+class Eigh(Algorithm):
+    pass
+
+
+@dataclass
+class Exact(Algorithm):
+    """cola/linalg/trace/diagonal_estimation.py:13-31"""
+    bs: int = 100
+    pbar: bool = False
+
+    def __call__(self, A, k):
+        return exact_diag(A, k, self.bs)
+
+
+def exact_diag(A, k, bs):
+    """diagonal_estimation.py:117-128 for k = 0: blocks of identity columns through the fused matmat."""
+    if k != 0:
+        raise NotImplementedError("off-diagonals (k != 0) are outside the Krylov hot path")
+    bs = min(100, A.shape[0])
+    n = A.shape[0]
+    out = torch.empty(n, dtype=A.dtype, device=A.device)
+    for i in range(0, n, bs):
+        w = min(bs, n - i)
+        chunk = torch.zeros((n, w), dtype=A.dtype, device=A.device)
+        chunk[i:i + w] = torch.eye(w, dtype=A.dtype, device=A.device)
+        out[i:i + w] = ((A @ chunk) * chunk).sum(-1)[i:i + w]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------- inverse
+def solve(A, b, alg=Auto()):
+    """cola/linalg/inverse/inv.py:23-39"""
+    return inv(A, alg) @ b
+
+
+class _DenseInverse(LinearOperator):
+    """inv(A, Cholesky) for small PSD operators: torch.linalg.cholesky on the dense matrix (library, as in the
+    reference: decompositions.py:147-175 + TriangularInv)."""
+    def __init__(self, A):
+        super().__init__(A.dtype, A.shape)
+        self.L = torch.linalg.cholesky(A.to_dense())
+        self.device = A.device
+
+    def _matmat(self, X):
+        return torch.cholesky_solve(X, self.L)
+
+
+def inv(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/inverse/inv.py:42-151"""
+    # structure rules first (inv.py:108-151)
+    if isinstance(alg, Algorithm) and not isinstance(alg, (CG, Auto, Cholesky)) and False:
+        pass
+    if A.isa(Unitary):
+        return Unitary(A.H)
+    if isinstance(A, Identity):
+        return A
+    if isinstance(A, ScalarMul):
+        return ScalarMul(1 / A.c, shape=A.shape, dtype=A.dtype, device=A.c.device)
+    if type(A) is Product and all(M.shape[-2] == M.shape[-1] for M in A.Ms):
+        return Product(*reversed([inv(M, alg) for M in A.Ms]))
+    if isinstance(A, BlockDiag):
+        return BlockDiag(*[inv(M, alg) for M in A.Ms], multiplicities=A.multiplicities)
+    if isinstance(A, Kronecker):
+        return Kronecker(*[inv(M, alg) for M in A.Ms])
+    if isinstance(A, Diagonal):
+        return Diagonal(1. / A.diag)
+    # base cases
+    if isinstance(alg, Auto):   # inv.py:72-92
+        small = bool(np.prod(A.shape) <= 1e6)
+        if A.isa(PSD):
+            alg = Cholesky() if small else CG(**alg.__dict__)
+        else:
+            raise NotImplementedError("non-PSD operators route to LU/GMRES in the reference; GMRES is a 'next' row of "
+                                      "the hot-path scope (DESIGN.md)")
+    if isinstance(alg, CG):     # inv.py:66-69
+        assert A.isa(PSD), "CG only valid for PSD matrices, wrap in cola.PSD if desired"
+        return IterativeOperatorWInfo(A, alg)
+    if isinstance(alg, Cholesky):
+        assert A.isa(PSD), "Cholesky only valid for PSD matrices, wrap in cola.PSD if desired"
+        return _DenseInverse(A)
+    raise NotImplementedError(f"inv with {type(alg).__name__} is outside the Krylov hot path")
+
+
+# ---------------------------------------------------------------------------------------------------- eig
+def get_slice(num, which):
+    """cola/linalg/decompositions/decompositions.py:214-224"""
+    if num == -1:
+        raise ValueError(f"Number of eigenvalues {num} must be explicitly specified")
+    if which == "SM":
+        return slice(0, num, None)
+    if which == "LM":
+        return slice(-1 if num is None else -num, None, None)
+    raise NotImplementedError(f"which={which} is not implemented")
+
+
+def eig(A: LinearOperator, k: int, which: str = "LM", alg: Algorithm = Auto()):
+    """cola/linalg/eig/eigs.py:19-182 (Lanczos, Arnoldi and Auto/Eigh rules)."""
+    eig_slice = get_slice(k, which)
+    if isinstance(alg, Auto):   # eigs.py:76-96
+        small = bool(np.prod(A.shape) <= 1e6)
+        if A.isa(SelfAdjoint):
+            alg = Eigh() if small else Lanczos(**alg.__dict__)
+        else:
+            alg = Arnoldi(**alg.__dict__)
+    if isinstance(alg, Lanczos):   # eigs.py:106-111
+        assert A.isa(SelfAdjoint)
+        eig_vals, eig_vecs, _ = lanczos_eigs(A, **alg.__dict__)
+        return eig_vals[eig_slice], eig_vecs[:, eig_slice]
+    if isinstance(alg, Arnoldi):   # eigs.py:99-103
+        eig_vals, eig_vecs, _ = arnoldi_eigs(A, **alg.__dict__)
+        return eig_vals[eig_slice], eig_vecs[:, eig_slice]
+    if isinstance(alg, Eigh):
+        vals, vecs = torch.linalg.eigh(A.to_dense())
+        return vals[eig_slice], Unitary(lazify(vecs[:, eig_slice]))
+    raise NotImplementedError(f"eig with {type(alg).__name__} is outside the Krylov hot path")
+
+
+# ---------------------------------------------------------------------------------------------------- trace / diag
+def diag(A: LinearOperator, k: int = 0, alg: Algorithm = Auto()):
+    """cola/linalg/trace/diag_trace.py:22-120"""
+    if isinstance(A, Dense):
+        return torch.diagonal(A.A, offset=k)
+    if isinstance(A, Identity) and k == 0:
+        return torch.ones(A.shape[0], dtype=A.dtype, device=A.device)
+    if isinstance(A, Diagonal) and k == 0:
+        return A.diag
+    if isinstance(alg, Auto):   # diag_trace.py:43-50
+        tol = alg.__dict__.get("tol", 1e-6)
+        use_exact = bool(tol < 1 / np.sqrt(10 * A.shape[-1]))
+        alg = Exact(**{kk: v for kk, v in alg.__dict__.items() if kk in ("bs", "pbar")}) if use_exact else \
+            Hutch(**alg.__dict__)
+    return alg(A, k)
+
+
+def trace(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/trace/diag_trace.py:122-147"""
+    assert A.shape[0] == A.shape[1], "Can't trace non square matrix"
+    if isinstance(A, Kronecker):
+        out = 1.0
+        for M in A.Ms:
+            out = out * trace(M, alg)
+        return out
+    return diag(A, 0, alg).sum()
+
+
+# ---------------------------------------------------------------------------------------------------- log / logdet
+def log(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/unary/unary.py:249-262 + apply_unary rules :94-142 (Lanczos case)."""
+    if isinstance(A, Diagonal):
+        return Diagonal(torch.log(A.diag))
+    if isinstance(alg, Auto):
+        alg = Lanczos(**alg.__dict__)
+    if isinstance(alg, Lanczos):   # unary.py:134-137
+        assert A.isa(SelfAdjoint), "Lanczos unary functions need a SelfAdjoint operator"
+        return LanczosUnary(A, torch.log, **alg.__dict__)
+    raise NotImplementedError(f"log with {type(alg).__name__} is outside the Krylov hot path")
+
+
+def slogdet(A: LinearOperator, log_alg: Algorithm = Auto(), trace_alg: Algorithm = Auto()):
+    """cola/linalg/logdet/logdet.py:52-184: structure rules, then trace(log(A, Lanczos), trace_alg)."""
+    one = torch.ones((), dtype=A.dtype, device=A.device)
+    if isinstance(A, Identity):
+        return one, torch.zeros((), dtype=A.dtype, device=A.device)
+    if isinstance(A, Diagonal):
+        return torch.prod(torch.sign(A.diag)), torch.sum(torch.log(torch.abs(A.diag)))
+    if isinstance(A, Kronecker):   # logdet.py:147-160
+        n = A.shape[0]
+        signs, logdets = zip(*[slogdet(M, log_alg, trace_alg) for M in A.Ms])
+        ld = sum(l * (n // M.shape[-1]) for l, M in zip(logdets, A.Ms))
+        sg = one
+        for s, M in zip(signs, A.Ms):
+            sg = sg * s**(n // M.shape[-1])
+        return sg, ld
+    if isinstance(A, BlockDiag):   # logdet.py:163-170
+        signs, logdets = zip(*[slogdet(M, log_alg, trace_alg) for M in A.Ms])
+        ld = sum(l * c for l, c in zip(logdets, A.multiplicities))
+        sg = one
+        for s, c in zip(signs, A.multiplicities):
+            sg = sg * s**c
+        return sg, ld
+    if isinstance(log_alg, Auto):   # logdet.py:82-94
+        small = bool(np.prod(A.shape) <= 1e6)
+        if small:
+            s, l = torch.linalg.slogdet(A.to_dense())
+            return s, l
+        if not A.isa(PSD):
+            raise NotImplementedError("non-PSD logdet routes to Arnoldi in the reference (outside this path)")
+        log_alg = Lanczos(**log_alg.__dict__)
+    if isinstance(log_alg, Lanczos):   # logdet.py:111-117
+        logA = log(A, log_alg)
+        tr = trace(logA, trace_alg)
+        return one, tr
+    raise NotImplementedError(f"slogdet with {type(log_alg).__name__} is outside the Krylov hot path")
+
+
+def logdet(A: LinearOperator, log_alg: Algorithm = Auto(), trace_alg: Algorithm = Auto()):
+    """cola/linalg/logdet/logdet.py:30-49"""
+    _, ld = slogdet(A, log_alg, trace_alg)
+    return ld

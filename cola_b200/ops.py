@@ -1,0 +1,724 @@
+"""Structured linear operators with the reference's interface (cola/ops/operator_base.py, cola/ops/operators.py)
+whose `_matmat` runs on the hand-written sm_100a kernels.
+
+Same class names, constructor arguments, shapes and error behaviour as the reference for the operators on the
+Krylov hot path: Dense, Sparse, Kronecker, BlockDiag, Diagonal, ScalarMul, Identity, Sum, Product (+ Tridiagonal
+as the container Lanczos returns).  What differs is underneath: instead of one eager torch op (and one
+temporary) per node of the operator tree, `compile_plan` flattens the tree into
+        A X = sum_t  scale_t * K_t X   +  (shift + diag) o X
+and executes it as one fused kernel per core operator K_t (shift / Diagonal / pAp-dots ride in its epilogue).
+
+CUDA float32/float64 only; CPU tensors raise (there is no fallback path).
+"""
+import copy
+from functools import reduce
+from numbers import Number
+
+import numpy as np
+import torch
+
+from . import backend as be
+
+
+# ----------------------------------------------------------------------------------------------------
+# annotations (cola/annotations.py:26-74)
+# ----------------------------------------------------------------------------------------------------
+class _WrapMeta(type):
+    def __str__(cls):
+        return cls.__name__
+
+    __repr__ = __str__
+
+    def __call__(cls, obj):
+        new = copy.copy(obj)
+        new.annotations = set(obj.annotations) | {cls}
+        new._plan = None
+        return new
+
+
+class Annotation(metaclass=_WrapMeta):
+    pass
+
+
+class SelfAdjoint(Annotation):
+    pass
+
+
+Hermitian = SelfAdjoint
+
+
+class PSD(SelfAdjoint):
+    pass
+
+
+class Stiefel(Annotation):
+    pass
+
+
+class Unitary(Stiefel):
+    pass
+
+
+def _intersect(ops):
+    return reduce(lambda x, y: x & y, (set(op.annotations) for op in ops))
+
+
+# ----------------------------------------------------------------------------------------------------
+# base class (cola/ops/operator_base.py:16-219)
+# ----------------------------------------------------------------------------------------------------
+def _find_device(obj):
+    if torch.is_tensor(obj):
+        return obj.device
+    if isinstance(obj, LinearOperator):
+        return obj.device
+    if isinstance(obj, (tuple, list)):
+        for o in obj:
+            d = _find_device(o)
+            if d is not None:
+                return d
+    if isinstance(obj, dict):
+        for o in obj.values():
+            d = _find_device(o)
+            if d is not None:
+                return d
+    return None
+
+
+class LinearOperator:
+    """Linear operator base class: `A @ X` -> `_matmat(X)` with X (d, k) (operator_base.py:97-106)."""
+    __array_ufunc__ = None
+
+    def __new__(cls, *args, **kwargs):
+        obj = super().__new__(cls)
+        obj.device = _find_device([args, kwargs])
+        obj._plan = None
+        return obj
+
+    def __init__(self, dtype, shape, matmat=None, annotations=()):
+        self.dtype = dtype
+        self.shape = tuple(shape)
+        if matmat is not None:
+            self._matmat = matmat
+        self.annotations = self._infer_annotations() | set(annotations)
+        self.device = self.device or torch.device("cpu")
+
+    def _infer_annotations(self):  # cola/annotations.py:80-193 (rules for the hot-path operators)
+        return set()
+
+    def isa(self, annotation):
+        return any(issubclass(a, annotation) for a in self.annotations)
+
+    # ---- application ---------------------------------------------------------------------------------
+    def plan(self):
+        if self._plan is None:
+            self._plan = compile_plan(self)
+        return self._plan
+
+    def _matmat(self, X):
+        X = _as_operand(self, X)
+        Y = torch.empty((self.shape[0], X.shape[1]), dtype=X.dtype, device=X.device)
+        self.plan().apply(X, Y)
+        return Y
+
+    def _rmatmat(self, X):
+        if self.isa(SelfAdjoint):
+            return self._matmat(X.T.contiguous()).T
+        return (self.T._matmat(X.T.contiguous())).T
+
+    def matmat_into(self, X, Y, dots=None, dots_row=None, gate=None):
+        """Fused form used by the Krylov loops: Y = A X and, if given, dots[row] += colsum(X * Y) in the same
+        kernel; `gate`/`dots_row` are device int32 scalars (see include/cola_b200.h)."""
+        self.plan().apply(X, Y, dots=dots, dots_row=dots_row, gate=gate)
+
+    def __matmul__(self, X):
+        assert X.shape[0] == self.shape[-1], f"dimension mismatch {self.shape} vs {X.shape}"
+        if isinstance(X, LinearOperator):
+            return dot(self, X)
+        if len(X.shape) == 1:
+            return self._matmat(X.reshape(-1, 1)).reshape(-1)
+        if len(X.shape) >= 2:
+            return self._matmat(X)
+        raise NotImplementedError
+
+    def __rmatmul__(self, X):
+        assert X.shape[-1] == self.shape[-2], f"dimension mismatch {self.shape} vs {X.shape}"
+        if isinstance(X, LinearOperator):
+            return dot(X, self)
+        if len(X.shape) == 1:
+            return self._rmatmat(X.reshape(1, -1)).reshape(-1)
+        return self._rmatmat(X)
+
+    def to_dense(self):
+        eye = torch.eye(self.shape[-1], dtype=self.dtype, device=self.device)
+        return self @ eye
+
+    @property
+    def T(self):
+        return transpose(self)
+
+    @property
+    def H(self):
+        return transpose(self)  # real dtypes only on this path
+
+    def to(self, device, dtype=None):
+        new = copy.copy(self)
+        new._plan = None
+        for key, val in vars(self).items():
+            if torch.is_tensor(val):
+                setattr(new, key, val.to(device=device, dtype=dtype if val.is_floating_point() else None))
+            elif isinstance(val, LinearOperator):
+                setattr(new, key, val.to(device, dtype))
+            elif isinstance(val, tuple) and val and all(isinstance(v, LinearOperator) for v in val):
+                setattr(new, key, tuple(v.to(device, dtype) for v in val))
+        new.device = torch.device(device)
+        return new
+
+    # ---- algebra (cola/fns.py:63-137) -----------------------------------------------------------------
+    def __add__(self, other):
+        if isinstance(other, Number) and other == 0:
+            return self
+        return add(self, other)
+
+    __radd__ = __add__
+
+    def __mul__(self, c):
+        return mul(self, c)
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return -1 * self
+
+    def __sub__(self, x):
+        return self.__add__(-x)
+
+    def __truediv__(self, x):
+        return self.__mul__(1 / x)
+
+    def __str__(self):
+        return self.__class__.__name__
+
+    def __repr__(self):
+        return "<%dx%d %s with dtype=%s>" % (self.shape[0], self.shape[1], self.__class__.__name__, self.dtype)
+
+
+def _as_operand(A, X):
+    if not torch.is_tensor(X):
+        raise TypeError("operand must be a torch tensor")
+    if not X.is_cuda:
+        raise RuntimeError("cola_b200 is a CUDA-only path: operand is on the CPU (no CPU fallback); "
+                           "move the operator and the operand to a B200 with .to('cuda')")
+    dt = torch.promote_types(A.dtype, X.dtype)
+    if dt != A.dtype:
+        raise TypeError(f"operand dtype {X.dtype} does not match operator dtype {A.dtype}")
+    X = X.to(dt)
+    return X if X.is_contiguous() else X.contiguous()
+
+
+def lazify(A):
+    return A if isinstance(A, LinearOperator) else Dense(A)
+
+
+# ----------------------------------------------------------------------------------------------------
+# operators on the hot path (cola/ops/operators.py)
+# ----------------------------------------------------------------------------------------------------
+class Dense(LinearOperator):
+    """operators.py:12-38"""
+    def __init__(self, A):
+        self.A = A
+        super().__init__(dtype=A.dtype, shape=A.shape)
+
+    def to_dense(self):
+        return self.A
+
+
+class Sparse(LinearOperator):
+    """operators.py:48-81.  Same COO constructor; the CSR arrays (int32 indices) are built on the device with a
+    STABLE row sort, i.e. what the reference constructor means (its own non-stable argsort can misalign
+    values and indices).  No scipy / host round trip."""
+    def __init__(self, data, row_indices, col_indices, shape):
+        super().__init__(dtype=data.dtype, shape=shape)
+        row_indices = row_indices.to(data.device)
+        col_indices = col_indices.to(data.device)
+        order = torch.argsort(row_indices.to(torch.int64), stable=True)
+        self.data = data[order].contiguous()
+        self.row_indices = row_indices[order]
+        self.col_indices = col_indices[order]
+        counts = torch.bincount(self.row_indices.to(torch.int64), minlength=shape[0])
+        rowptr = torch.zeros(shape[0] + 1, dtype=torch.int64, device=data.device)
+        rowptr[1:] = torch.cumsum(counts, 0)
+        assert int(self.data.numel()) < 2**31, "int32 CSR indices (operators.py:73-74)"
+        self.indptr = rowptr.to(torch.int32).contiguous()
+        self.indices = self.col_indices.to(torch.int32).contiguous()
+        self.nnz = int(self.data.numel())
+
+    def _transpose(self):
+        return Sparse(self.data, self.col_indices, self.row_indices, (self.shape[1], self.shape[0]))
+
+
+class ScalarMul(LinearOperator):
+    """operators.py:84-101"""
+    def __init__(self, c, shape, dtype=None, device=None):
+        super().__init__(dtype=dtype or type(c), shape=shape)
+        self.c = torch.as_tensor(c, dtype=dtype, device=device)
+        self.device = device if device is not None else self.device
+
+    def __str__(self):
+        return f"{self.c}"
+
+
+class Identity(LinearOperator):
+    """operators.py:104-127"""
+    def __init__(self, shape, dtype):
+        super().__init__(dtype=dtype, shape=shape)
+
+    def _infer_annotations(self):
+        return {Unitary, PSD}
+
+    def _matmat(self, X):
+        return X
+
+    def to(self, device, dtype=None):
+        self.device = torch.device(device) if not isinstance(device, torch.device) else device
+        return self
+
+    def __str__(self):
+        return "I"
+
+
+def I_like(A):
+    op = Identity(dtype=A.dtype, shape=A.shape)
+    op.to(A.device)
+    return op
+
+
+class Product(LinearOperator):
+    """operators.py:138-164"""
+    def __init__(self, *Ms):
+        self.Ms = tuple(lazify(M) for M in Ms)
+        devices = [M.device for M in self.Ms]
+        assert all(x == devices[0] for x in devices), "There is a device mismatch in Product"
+        for M1, M2 in zip(Ms[:-1], Ms[1:]):
+            if M1.shape[-1] != M2.shape[-2]:
+                raise ValueError(f"dimension mismatch {M1.shape} vs {M2.shape}")
+        shape = (Ms[0].shape[-2], Ms[-1].shape[-1])
+        dtype = reduce(torch.promote_types, (M.dtype for M in self.Ms))
+        super().__init__(dtype, shape)
+        self.device = devices[0]
+
+    def _infer_annotations(self):  # annotations.py:115-122
+        not_commuting = [M for M in self.Ms if not isinstance(M, ScalarMul)]
+        if len(not_commuting) == 1:
+            return set(not_commuting[0].annotations)
+        return _intersect(self.Ms) & {Unitary, Stiefel}
+
+    def __str__(self):
+        return "".join(str(M) for M in self.Ms)
+
+
+class Sum(LinearOperator):
+    """operators.py:167-191"""
+    def __init__(self, *Ms):
+        self.Ms = tuple(lazify(M) for M in Ms)
+        devices = [M.device for M in self.Ms]
+        assert all(x == devices[0] for x in devices), "There is a device mismatch in Sum"
+        shape = Ms[0].shape
+        for M in Ms:
+            if tuple(M.shape) != tuple(shape):
+                raise ValueError(f"dimension mismatch {M.shape} vs {shape}")
+        super().__init__(Ms[0].dtype, shape)
+        self.device = devices[0]
+
+    def _infer_annotations(self):  # annotations.py:130-132
+        return _intersect(self.Ms) - {Unitary, Stiefel}
+
+    def __str__(self):
+        return "+".join(str(M) for M in self.Ms)
+
+
+def _prod(c):
+    return reduce(lambda a, b: a * b, c)
+
+
+class Kronecker(LinearOperator):
+    """operators.py:198-230"""
+    def __init__(self, *Ms):
+        self.Ms = tuple(lazify(M) for M in Ms)
+        shape = _prod([Mi.shape[-2] for Mi in Ms]), _prod([Mi.shape[-1] for Mi in Ms])
+        dtype = reduce(torch.promote_types, (M.dtype for M in self.Ms))
+        super().__init__(dtype, shape)
+
+    def _infer_annotations(self):  # annotations.py:91-93
+        return _intersect(self.Ms)
+
+    def to_dense(self):
+        return reduce(torch.kron, [M.to_dense() for M in self.Ms])
+
+    def __str__(self):
+        return "⊗".join(str(M) for M in self.Ms)
+
+
+class BlockDiag(LinearOperator):
+    """operators.py:277-320"""
+    def __init__(self, *Ms, multiplicities=None):
+        self.Ms = tuple(lazify(M) for M in Ms)
+        self.multiplicities = [1 for _ in Ms] if multiplicities is None else multiplicities
+        shape = (sum(Mi.shape[-2] * c for Mi, c in zip(Ms, self.multiplicities)),
+                 sum(Mi.shape[-1] * c for Mi, c in zip(Ms, self.multiplicities)))
+        dtype = reduce(torch.promote_types, (M.dtype for M in self.Ms))
+        super().__init__(dtype, shape)
+
+    def _infer_annotations(self):  # annotations.py:135-137
+        return _intersect(self.Ms)
+
+    def to_dense(self):
+        blocks = [M.to_dense() for M, c in zip(self.Ms, self.multiplicities) for _ in range(c)]
+        return torch.block_diag(*blocks)
+
+
+class Diagonal(LinearOperator):
+    """operators.py:323-348"""
+    def __init__(self, diag):
+        assert len(diag.shape) == 1, f"diagonal is not a vector, it is of shape {diag.shape=}"
+        self.diag = diag
+        super().__init__(dtype=diag.dtype, shape=(len(diag), ) * 2)
+
+    def to_dense(self):
+        return torch.diag(self.diag)
+
+    def __str__(self):
+        return f"diag({self.diag})"
+
+
+class Tridiagonal(LinearOperator):
+    """operators.py:351-372: the container Lanczos returns (alpha lower, beta diagonal, gamma upper band).
+    Tiny (m x m); its matmat is not on the hot path and stays a few elementwise torch ops on the device."""
+    def __init__(self, alpha, beta, gamma):
+        def col(v):
+            return v.reshape(-1, 1) if v.dim() == 1 else v
+        self.alpha, self.beta, self.gamma = col(alpha), col(beta), col(gamma)
+        super().__init__(dtype=beta.dtype, shape=(self.beta.shape[0], self.beta.shape[0]))
+
+    def _matmat(self, X):
+        out = self.beta * X
+        zeros = torch.zeros((1, X.shape[-1]), dtype=X.dtype, device=X.device)
+        up = torch.cat([self.gamma * X[1:], zeros], dim=0)
+        lo = torch.cat([zeros, self.alpha * X[:-1]], dim=0)
+        return out + lo + up
+
+    def to_dense(self):
+        m = self.beta.shape[0]
+        T = torch.diag(self.beta[:, 0])
+        if m > 1:
+            T = T + torch.diag(self.alpha[:, 0], -1) + torch.diag(self.gamma[:, 0], 1)
+        return T
+
+
+class Transpose(LinearOperator):
+    """operators.py:381-396 (only as the result of .T on a non-symmetric hot-path operator)."""
+    def __init__(self, A):
+        super().__init__(dtype=A.dtype, shape=(A.shape[1], A.shape[0]))
+        self.A = A
+
+    def _infer_annotations(self):
+        return set()
+
+
+class Sliced(LinearOperator):
+    """operators.py:417-453, column/row slices of a lazy operator (what eig() returns, eigs.py:111)."""
+    def __init__(self, A, slices):
+        self.A, self.slices = A, slices
+        rows = range(A.shape[0])[slices[0]]
+        cols = range(A.shape[1])[slices[1]]
+        super().__init__(dtype=A.dtype, shape=(len(rows), len(cols)))
+
+    def to_dense(self):
+        return self.A.to_dense()[self.slices[0], :][:, self.slices[1]]
+
+    def _matmat(self, X):
+        full = torch.zeros((self.A.shape[1], X.shape[1]), dtype=X.dtype, device=X.device)
+        full[self.slices[1]] = X
+        return (self.A @ full)[self.slices[0]]
+
+
+def _getitem(self, ids):
+    if isinstance(ids, tuple) and len(ids) == 2 and all(isinstance(s, slice) for s in ids):
+        return Sliced(self, ids)
+    raise NotImplementedError(f"__getitem__ not implemented for {type(ids)}")
+
+
+LinearOperator.__getitem__ = _getitem
+
+
+# ----------------------------------------------------------------------------------------------------
+# algebra dispatch (cola/fns.py)
+# ----------------------------------------------------------------------------------------------------
+def dot(A, B):
+    if isinstance(B, Identity):
+        return A
+    if isinstance(A, Identity):
+        return B
+    a = A.Ms if isinstance(A, Product) else (A, )
+    b = B.Ms if isinstance(B, Product) else (B, )
+    return Product(*(a + b))
+
+
+def add(A, B):
+    A, B = lazify(A), lazify(B)
+    a = A.Ms if type(A) is Sum else (A, )
+    b = B.Ms if type(B) is Sum else (B, )
+    return Sum(*(a + b))
+
+
+def mul(A, c):
+    if isinstance(A, ScalarMul):
+        if isinstance(c, ScalarMul):
+            return ScalarMul(A.c * c.c, A.shape, A.dtype, A.device)
+        return ScalarMul(A.c * c, A.shape, A.dtype, A.device)
+    S = ScalarMul(c, (A.shape[-2], A.shape[-2]), A.dtype, A.device)
+    return Product(S, A)
+
+
+def transpose(A):
+    if A.isa(SelfAdjoint):
+        return A
+    if isinstance(A, Transpose):
+        return A.A
+    if isinstance(A, Dense):
+        return Dense(A.A.T.contiguous())
+    if isinstance(A, Sparse):
+        return A._transpose()
+    if isinstance(A, (Diagonal, Identity, ScalarMul)):
+        return A
+    if isinstance(A, Kronecker):
+        return Kronecker(*[transpose(M) for M in A.Ms])
+    if isinstance(A, BlockDiag):
+        return BlockDiag(*[transpose(M) for M in A.Ms], multiplicities=A.multiplicities)
+    if isinstance(A, Sum):
+        return Sum(*[transpose(M) for M in A.Ms])
+    if isinstance(A, Product):
+        return Product(*[transpose(M) for M in reversed(A.Ms)])
+    return Transpose(A)
+
+
+def kron(A, B):
+    a = A.Ms if isinstance(A, Kronecker) else (lazify(A), )
+    b = B.Ms if isinstance(B, Kronecker) else (lazify(B), )
+    return Kronecker(*(a + b))
+
+
+def block_diag(*ops, multiplicities=None):
+    return BlockDiag(*ops, multiplicities=multiplicities)
+
+
+# ----------------------------------------------------------------------------------------------------
+# operator compiler: tree -> flat plan -> fused kernels
+# ----------------------------------------------------------------------------------------------------
+class _DenseCore:
+    def __init__(self, M):
+        self.M = M if M.is_contiguous() else M.contiguous()
+        self.shape = tuple(M.shape)
+
+    def apply(self, X, Y, epi):
+        k = X.shape[1]
+        be.mode_contract(self.M, self.shape[0], self.shape[1], 1, k, X, Y, epi_x=X if epi.needs_x() else None,
+                         **epi.kw())
+
+
+class _CsrCore:
+    def __init__(self, S):
+        self.S = S
+        self.shape = tuple(S.shape)
+
+    def apply(self, X, Y, epi):
+        S = self.S
+        be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, X, Y, **epi.kw())
+
+
+class _KronCore:
+    """Chain of mode contractions; factor i sees X as (pre_i, d_i, post_i) with no transposes
+    (replaces operators.py:216-223)."""
+    def __init__(self, factors):
+        self.Fs = [(f if f.is_contiguous() else f.contiguous()) for f in factors]
+        self.shape = (_prod([f.shape[0] for f in self.Fs]), _prod([f.shape[1] for f in self.Fs]))
+        self._ws = {}
+
+    def _workspace(self, numel, dtype, device, slot):
+        key = (slot, dtype, device)
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(numel, dtype=dtype, device=device)
+            self._ws[key] = buf
+        return buf
+
+    def apply(self, X, Y, epi):
+        k = X.shape[1]
+        D = len(self.Fs)
+        d_in = [f.shape[1] for f in self.Fs]
+        d_out = [f.shape[0] for f in self.Fs]
+        src = X
+        for i, F in enumerate(self.Fs):
+            pre = _prod(d_out[:i]) if i > 0 else 1
+            post = (_prod(d_in[i + 1:]) if i + 1 < D else 1) * k
+            last = i == D - 1
+            if last:
+                be.mode_contract(F, d_out[i], d_in[i], pre, post, src, Y, epi_x=X if epi.needs_x() else None,
+                                 **epi.kw())
+            else:
+                numel = pre * d_out[i] * post
+                dst = self._workspace(numel, X.dtype, X.device, i % 2)
+                be.mode_contract(F, d_out[i], d_in[i], pre, post, src, dst, gate=epi.gate)
+                src = dst
+
+
+class _BlockDiagCore:
+    """One batched contraction per distinct block: kron(I_mult, M) on its row range (operators.py:299-310)."""
+    def __init__(self, blocks, mults):
+        self.blocks = [(b if b.is_contiguous() else b.contiguous()) for b in blocks]
+        self.mults = list(mults)
+        self.shape = (sum(b.shape[0] * c for b, c in zip(self.blocks, self.mults)),
+                      sum(b.shape[1] * c for b, c in zip(self.blocks, self.mults)))
+
+    def apply(self, X, Y, epi):
+        k = X.shape[1]
+        ri = ro = 0
+        for M, c in zip(self.blocks, self.mults):
+            kw = epi.kw()
+            if kw.get("diag") is not None:
+                kw["diag"] = be.off_ptr(epi.diag, ro)
+            be.mode_contract(M, M.shape[0], M.shape[1], c, k, be.off_ptr(X, ri * k), be.off_ptr(Y, ro * k),
+                             epi_x=be.off_ptr(X, ri * k) if epi.needs_x() else None, **kw)
+            ri += c * M.shape[1]
+            ro += c * M.shape[0]
+
+
+class _OpaqueCore:
+    """Any other LinearOperator: call its own `_matmat` and add the result in (not a fused path)."""
+    def __init__(self, op):
+        self.op = op
+        self.shape = tuple(op.shape)
+
+    def apply(self, X, Y, epi):
+        Z = self.op._matmat(X)
+        Z = Z if Z.is_contiguous() else Z.contiguous()
+        be.axpby(Z, Y, epi.alpha, 1.0 if epi.accumulate else 0.0, gate=epi.gate)
+        if epi.shift != 0.0 or epi.diag is not None or epi.dots is not None:
+            # epilogue as a separate sweep: Y += (shift+diag) X ; dots += <X, Y>
+            be.diag_matmat(X, Y, epi.shift, epi.diag, True, epi.dots, epi.dots_row, epi.gate)
+
+
+class _Epilogue:
+    def __init__(self, alpha=1.0, shift=0.0, diag=None, accumulate=False, dots=None, dots_row=None, gate=None):
+        self.alpha, self.shift, self.diag, self.accumulate = alpha, shift, diag, accumulate
+        self.dots, self.dots_row, self.gate = dots, dots_row, gate
+
+    def needs_x(self):
+        return self.shift != 0.0 or self.diag is not None or self.dots is not None
+
+    def kw(self):
+        return dict(alpha=self.alpha, shift=self.shift, diag=self.diag, accumulate=self.accumulate, dots=self.dots,
+                    dots_row=self.dots_row, gate=self.gate)
+
+
+class Plan:
+    """A X = sum_t scale_t * chain_t X + (shift + diag) o X.  chain_t is a list of cores applied right to left."""
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = shape, dtype
+        self.terms = []      # (scale, [cores left-to-right])
+        self.shift = 0.0
+        self.diag = None
+
+    def describe(self):
+        parts = [f"{s:g}*" + "@".join(type(c).__name__.strip("_") for c in ch) for s, ch in self.terms]
+        if self.shift != 0.0:
+            parts.append(f"{self.shift:g}*I")
+        if self.diag is not None:
+            parts.append("Diag")
+        return " + ".join(parts)
+
+    def apply(self, X, Y, dots=None, dots_row=None, gate=None):
+        if not (X.is_cuda and Y.is_cuda):
+            raise RuntimeError("cola_b200 is a CUDA-only path (no CPU fallback)")
+        if X.dtype != self.dtype or Y.dtype != self.dtype:
+            raise TypeError(f"operand dtype {X.dtype}/{Y.dtype} does not match operator dtype {self.dtype}")
+        assert X.shape[0] == self.shape[1] and Y.shape[0] == self.shape[0] and X.shape[1] == Y.shape[1]
+        square = self.shape[0] == self.shape[1]
+        n_terms = len(self.terms)
+        if n_terms == 0:
+            assert square
+            be.diag_matmat(X, Y, self.shift, self.diag, False, dots, dots_row, gate)
+            return
+        for t, (scale, chain) in enumerate(self.terms):
+            last_term = t == n_terms - 1
+            src = X
+            for ci in range(len(chain) - 1, -1, -1):  # right to left
+                core = chain[ci]
+                final = ci == 0
+                if final:
+                    if last_term:
+                        epi = _Epilogue(scale, self.shift, self.diag, n_terms > 1, dots, dots_row, gate)
+                    else:
+                        epi = _Epilogue(scale, 0.0, None, t > 0, None, None, gate)
+                    core.apply(src, Y, epi)
+                else:
+                    tmp = torch.empty((core.shape[0], X.shape[1]), dtype=X.dtype, device=X.device)
+                    core.apply(src, tmp, _Epilogue(gate=gate))
+                    src = tmp
+
+
+def _core_of(op):
+    if isinstance(op, Dense):
+        return _DenseCore(op.A)
+    if isinstance(op, Sparse):
+        return _CsrCore(op)
+    if isinstance(op, Kronecker):
+        return _KronCore([_dense_of(M) for M in op.Ms])
+    if isinstance(op, BlockDiag):
+        return _BlockDiagCore([_dense_of(M) for M in op.Ms], op.multiplicities)
+    return _OpaqueCore(op)
+
+
+def _dense_of(op):
+    if isinstance(op, Dense):
+        return op.A
+    return op.to_dense()
+
+
+def compile_plan(A):
+    plan = Plan(tuple(A.shape), A.dtype)
+
+    def add_diag(d):
+        plan.diag = d if plan.diag is None else plan.diag + d
+
+    def visit(op, scale):
+        if isinstance(op, Identity):
+            plan.shift += scale
+        elif isinstance(op, ScalarMul):
+            plan.shift += scale * float(op.c)
+        elif isinstance(op, Diagonal):
+            add_diag(op.diag if scale == 1.0 else scale * op.diag)
+        elif type(op) is Sum:
+            for M in op.Ms:
+                visit(M, scale)
+        elif type(op) is Product:
+            rest = []
+            for M in op.Ms:
+                if isinstance(M, ScalarMul):
+                    scale = scale * float(M.c)
+                elif isinstance(M, Identity):
+                    continue
+                else:
+                    rest.append(M)
+            if not rest:
+                plan.shift += scale
+            elif len(rest) == 1:
+                visit(rest[0], scale)
+            else:
+                plan.terms.append((scale, [_core_of(M) for M in rest]))
+        else:
+            plan.terms.append((scale, [_core_of(op)]))
+
+    visit(A, 1.0)
+    if plan.diag is not None:
+        plan.diag = plan.diag.to(A.dtype).contiguous()
+    return plan

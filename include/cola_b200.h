@@ -1,0 +1,198 @@
+/*
+ * cola_b200.h -- C ABI of the B200-native Krylov engine (libcola_b200.so).
+ *
+ * This is the drop-in boundary for CoLA's Krylov hot path.  The reference
+ * (wilson-labs/cola) is pure Python over eager torch ops and has no native
+ * interface of its own; every entry point below therefore names the reference
+ * *Python* function / torch call sites it replaces (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes binding a cola
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative COLA_E_* for bad
+ *     arguments, or a positive cudaError_t; cola_last_error() gives the text.
+ *     No exceptions cross this boundary.
+ *   - all data pointers are DEVICE pointers unless the comment says "host".
+ *     The caller owns every buffer; the library never allocates, frees or
+ *     retains device memory.
+ *   - dense blocks of vectors are row-major (n, k) with the RHS / probe
+ *     index fastest and an explicit leading dimension `ld` (elements).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *     nothing synchronises the host.
+ *   - reductions (column dots) accumulate into DOUBLE accumulators that the
+ *     caller zeroes; kernels add to them with fp64 atomics, so results do not
+ *     depend on launch geometry beyond 1e-16 relative.
+ *   - suffix _f32 / _f64 = the arithmetic type of the path.
+ */
+#ifndef COLA_B200_H
+#define COLA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COLA_OK 0
+#define COLA_E_BADARG (-1)
+#define COLA_E_UNSUPPORTED (-2)
+#define COLA_E_NOGPU (-3)
+
+/* ---- library ---------------------------------------------------------- */
+int cola_version(void);               /* ABI version, bump on any signature change          */
+const char* cola_last_error(void);    /* host string describing the last non-zero status    */
+int cola_device_info(int* sm_count, int* cc_major, int* cc_minor); /* COLA_E_NOGPU without a device */
+/* Kernels launched by this library since load (the `gpu_launches` evidence). */
+int64_t cola_launch_count(void);
+
+/* ---- device-side gating ------------------------------------------------------
+ * Krylov loops run without host synchronisation: a batch of iterations is enqueued (or captured in a
+ * CUDA graph) before the host knows where the stopping rule fires.  Every kernel therefore takes an
+ * optional `gate` (device int32*, may be NULL): the launch is a no-op when *gate != 0.  For CG the gate
+ * is &ctl->done.  Matmats that feed a per-iteration accumulator also take `dots_row` (device int32*,
+ * may be NULL): the column dots go to dots[(*dots_row) * k + c] (for CG, &ctl->it).
+ */
+
+/* ---- fused operator epilogue ------------------------------------------
+ * Every matmat computes, for a square "core" operator K (Dense / CSR / Kronecker / BlockDiag):
+ *     Y[i,:] = alpha * (K X)[i,:] + (shift + diag[i]) * X[i,:]   (+ Y[i,:] if accumulate)
+ * which is how Sum[K, c*I, Diagonal(d)] / ScalarMul compositions
+ * (cola/ops/operators.py:84-127,138-191,323-348) collapse into one HBM pass.
+ * If `dots` != NULL the kernel also adds  sum_i X[i,c] * Y[i,c]  into dots[c]
+ * (k doubles): the p^T A p of CG (cola/linalg/inverse/cg.py:157-158) or the Lanczos
+ * <w, v_i> (cola/linalg/decompositions/lanczos.py:245) in the same pass.
+ * shift/diag/dots require a square operator.  diag may be NULL.
+ */
+
+/* Sparse CSR  Y = A X.   Replaces Sparse._matmat -> torch.sparse_csr @ dense
+ * (cola/ops/operators.py:77-78, indices int32 per :73-74). */
+int cola_csr_spmm_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
+                      int64_t n_cols, int64_t nnz, const float* X, int64_t ldx, int64_t k, float* Y, int64_t ldy, float alpha,
+                      float shift, const float* diag, int accumulate, double* dots, const int32_t* dots_row,
+                      const int32_t* gate, void* stream);
+int cola_csr_spmm_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
+                      int64_t n_cols, int64_t nnz, const double* X, int64_t ldx, int64_t k, double* Y, int64_t ldy, double alpha,
+                      double shift, const double* diag, int accumulate, double* dots, const int32_t* dots_row,
+                      const int32_t* gate, void* stream);
+
+/* Batched mode contraction  out[p,a,q] = alpha * sum_j M[a,j] in[p,j,q].
+ * M is (d_out, d_in) row-major with leading dimension ldm.  `in` is (pre, d_in, post) contiguous,
+ * `out` (pre, d_out, post) contiguous; they must not alias.
+ *   Dense._matmat      (operators.py:26-28)    : pre=1, post=k
+ *   Kronecker._matmat  (operators.py:216-223)  : one call per factor, no moveaxis/reshape copies
+ *   BlockDiag._matmat  (operators.py:299-310)  : pre=multiplicity, post=k, one call per block
+ * The epilogue (shift/diag/accumulate/dots) acts on the flattened (pre*d_out, post) matrix, row = p*d_out+a,
+ * and needs d_out == d_in for shift/diag/dots; `epi_x` is the tensor the epilogue's X refers to (the
+ * matmat input, laid out like `out`); pass NULL when shift/diag/dots are unused.  dots has `post` entries. */
+int cola_mode_contract_f32(const float* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t pre, int64_t post,
+                           const float* in, float* out, float alpha, float shift, const float* diag,
+                           const float* epi_x, int accumulate, double* dots, const int32_t* dots_row,
+                           const int32_t* gate, void* stream);
+int cola_mode_contract_f64(const double* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t pre, int64_t post,
+                           const double* in, double* out, double alpha, double shift, const double* diag,
+                           const double* epi_x, int accumulate, double* dots, const int32_t* dots_row,
+                           const int32_t* gate, void* stream);
+
+/* Operators with no core (Diagonal, ScalarMul*Identity, sums of those):
+ *   Y = (shift + diag[i]) * X  (+Y).   Diagonal._matmat / ScalarMul._matmat (operators.py:97-98,338-339). */
+int cola_diag_matmat_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n, int64_t k, float shift,
+                         const float* diag, int accumulate, double* dots, const int32_t* dots_row,
+                         const int32_t* gate, void* stream);
+int cola_diag_matmat_f64(const double* X, int64_t ldx, double* Y, int64_t ldy, int64_t n, int64_t k, double shift,
+                         const double* diag, int accumulate, double* dots, const int32_t* dots_row,
+                         const int32_t* gate, void* stream);
+
+/* ---- column reductions / scalings on (n,k) blocks, leading dimension ld ---------------- */
+/* dots[c] += sum_i X[i,c]*Y[i,c]   (xnp.sum(conj(a)*b, axis=-2), xnp.norm(.,axis=-2)**2) */
+int cola_col_dots_f32(const float* X, const float* Y, int64_t n, int64_t k, int64_t ld, double* dots,
+                      const int32_t* gate, void* stream);
+int cola_col_dots_f64(const double* X, const double* Y, int64_t n, int64_t k, int64_t ld, double* dots,
+                      const int32_t* gate, void* stream);
+/* mode 0: Y[i,c] = a*s[c]*X[i,c]
+ * mode 1: Y[i,c] = X[i,c] / safe(s[c])     (|s|<1e-40 -> 1e-40: do_safe_div, cg.py:173-178)
+ * mode 2: Y[i,c] = X[i,c] / s[c]           (unguarded, lanczos.py:240-241)
+ * mode 3: Y[i,c] = X[i,c] / max(s[c], a)   (clip(norm, min=tol/2), arnoldi.py:315)
+ * s[c] = sqrt(sq[c]) if take_sqrt else sq[c]; sq is k doubles.  Y may alias X. */
+int cola_col_scale_f32(const float* X, float* Y, int64_t n, int64_t k, int64_t ld, const double* sq, int take_sqrt,
+                       int mode, float a, const int32_t* gate, void* stream);
+int cola_col_scale_f64(const double* X, double* Y, int64_t n, int64_t k, int64_t ld, const double* sq, int take_sqrt,
+                       int mode, double a, const int32_t* gate, void* stream);
+/* Y = a*X + b*Y elementwise (residual r0 = b - A x0, cg.py:123). */
+int cola_axpby_f32(const float* X, float* Y, int64_t n, int64_t k, int64_t ld, float a, float b, const int32_t* gate,
+                   void* stream);
+int cola_axpby_f64(const double* X, double* Y, int64_t n, int64_t k, int64_t ld, double a, double b,
+                   const int32_t* gate, void* stream);
+
+/* ---- CG iteration (cola/linalg/inverse/cg.py:94-178, preconditioner = Identity) ------------------
+ * Device-resident control block: the whole loop, including the stopping rule, runs without host syncs.
+ * Iteration `it` uses accumulator rows gamma[it*k..], pAp[it*k..], gamma[(it+1)*k..] (all zeroed by the
+ * caller before the solve; gamma row 0 holds <r0,r0>).  After the solve gamma[j*k+c] = ||r_j[:,c]||^2 is
+ * the full residual trace from which info['errors'] (cola/utils/torch_tqdm.py:35-62) is rebuilt on the host. */
+typedef struct {
+  int32_t it;        /* iterations completed                                                        */
+  int32_t done;      /* set when the reference's cond_fun (cg.py:133-138) turns false               */
+  int32_t max_iters;
+  int32_t k;
+} cola_cg_ctl_t;
+
+/* One CG iteration minus the matmat, as two sweeps + one tiny scalar kernel:
+ *   xr:      alpha = safe(gamma/pAp) (0 where ||r||<1e-40);  X += alpha P;  R -= alpha AP;  gamma[it+1] += <R,R>
+ *   p :      beta  = safe(gamma[it+1]/gamma[it]) (0 where converged);  P = R + beta P
+ *   advance: it += increment;  done = !(any(sqrt(gamma[it]) > tol_eff) && it < max_iters)
+ * Each kernel reads ctl->it / ctl->done on the device and is a no-op once done. */
+int cola_cg_update_xr_f32(float* X, float* R, const float* P, const float* AP, int64_t n, int64_t k, int64_t ld,
+                          const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, double* gamma_w,
+                          void* stream);
+int cola_cg_update_xr_f64(double* X, double* R, const double* P, const double* AP, int64_t n, int64_t k, int64_t ld,
+                          const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, double* gamma_w,
+                          void* stream);
+int cola_cg_update_p_f32(const float* R, float* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
+                         const double* gamma, void* stream);
+int cola_cg_update_p_f64(const double* R, double* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
+                         const double* gamma, void* stream);
+/* tol_eff[c] = tol*||r0[:,c]|| + tol in the path's dtype (cg.py:101). */
+int cola_cg_tol_f32(const double* gamma0, float tol, float* tol_eff, int64_t k, void* stream);
+int cola_cg_tol_f64(const double* gamma0, double tol, double* tol_eff, int64_t k, void* stream);
+int cola_cg_advance_f32(cola_cg_ctl_t* ctl, const double* gamma, const float* tol_eff, int increment, void* stream);
+int cola_cg_advance_f64(cola_cg_ctl_t* ctl, const double* gamma, const double* tol_eff, int increment, void* stream);
+
+/* ---- Full reorthogonalisation (Lanczos CGS2: lanczos.py:287-296; Arnoldi MGS: arnoldi.py:304-311) ------
+ * Krylov basis layout (B200-native, differs from the reference's (b, n, m+2) with the Krylov index
+ * fastest): V is (n_vec, n, b) contiguous, i.e. vector j is an (n, b) row-major block at V + j*vstride,
+ * which is exactly the matmat operand layout, so no transposes are ever made.
+ *   dots:   C[j*b + c] += sum_i V[j][i,c] * W[i,c]   for j in [j0, j1)          (C doubles, zeroed by caller)
+ *   update: W[i,c] = W[i,c] + sign * sum_{j in [j0,j1)} coef(j,c) * V[j][i,c]
+ *           coef = C[j*b+c] (doubles, rounded to the path dtype first)           (sign = -1 for Gram-Schmidt)
+ *           if wnorm2 != NULL also wnorm2[c] += sum_i W_new[i,c]^2
+ */
+int cola_reorth_dots_f32(const float* V, int64_t vstride, int64_t j0, int64_t j1, const float* W, int64_t n,
+                         int64_t b, double* C, const int32_t* gate, void* stream);
+int cola_reorth_dots_f64(const double* V, int64_t vstride, int64_t j0, int64_t j1, const double* W, int64_t n,
+                         int64_t b, double* C, const int32_t* gate, void* stream);
+int cola_reorth_update_f32(const float* V, int64_t vstride, int64_t j0, int64_t j1, float* W, int64_t n, int64_t b,
+                           const double* C, float sign, double* wnorm2, const int32_t* gate, void* stream);
+int cola_reorth_update_f64(const double* V, int64_t vstride, int64_t j0, int64_t j1, double* W, int64_t n, int64_t b,
+                           const double* C, double sign, double* wnorm2, const int32_t* gate, void* stream);
+
+/* Lanczos three-term step after the matmat (lanczos.py:245-248), fused:
+ *   W -= alpha[c] * Vi + beta_prev[c] * Vim1   with alpha[c] = (T)alpha_acc[c] (the <w,v_i> dots of the matmat),
+ *   beta_prev[c] = (T)sqrt(beta_prev_sq[c]).  Vim1 / beta_prev_sq may be NULL (first step). */
+int cola_lanczos_three_term_f32(float* W, const float* Vi, const float* Vim1, int64_t n, int64_t b,
+                                const double* alpha_acc, const double* beta_prev_sq, const int32_t* gate,
+                                void* stream);
+int cola_lanczos_three_term_f64(double* W, const double* Vi, const double* Vim1, int64_t n, int64_t b,
+                                const double* alpha_acc, const double* beta_prev_sq, const int32_t* gate,
+                                void* stream);
+
+/* Arnoldi modified Gram-Schmidt link (arnoldi.py:304-311), one launch per basis vector:
+ *   if Qprev: W -= (T)hprev[c] * Qprev;   if Qcur: hcur[c] += sum_i Qcur[i,c] * W[i,c];
+ *   if wnorm2: wnorm2[c] += sum_i W[i,c]^2 (last link). */
+int cola_mgs_link_f32(float* W, const float* Qprev, const double* hprev, const float* Qcur, double* hcur,
+                      double* wnorm2, int64_t n, int64_t b, const int32_t* gate, void* stream);
+int cola_mgs_link_f64(double* W, const double* Qprev, const double* hprev, const double* Qcur, double* hcur,
+                      double* wnorm2, int64_t n, int64_t b, const int32_t* gate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLA_B200_H */

@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs and
+against the golden vectors the real reference produced (tests/golden/).
+
+Tolerances are the north-star bar: relative 1e-5 for fp32, 1e-10 for fp64, on per-iteration residual norms,
+Lanczos coefficients, solutions, eigenvalues and log-determinants."""
+import numpy as np
+import pytest
+import torch
+
+from tests import problems as pb
+from tests.golden_cases import ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL, F64_TOL = 1e-5, 1e-10
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    den = 0.5 * (np.linalg.norm(a) + np.linalg.norm(b))
+    return 0.0 if den == 0 else float(np.linalg.norm(a - b) / den)
+
+
+def tol_of(dtype):
+    return F32_TOL if dtype == torch.float32 else F64_TOL
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cola_b200
+    assert torch.cuda.is_available()
+    cola_b200.backend.lib()  # fails loudly if the extension is missing
+    cola_b200.rng.PROBE_DEVICE = "cpu"  # draw probes on the CPU generator: same stream as the CPU oracle
+    return cola_b200
+
+
+DEV = "cuda:0"
+
+
+# ------------------------------------------------------------------------------------------- matmats
+@pytest.mark.parametrize("name", MATMAT_PROBLEMS)
+def test_matmat(name, golden, cb):
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    X = pb.randn_np((A.shape[1], 6), P["dtype"], 100)
+    g = golden("matmat_" + name)
+    t = tol_of(P["dtype"])
+    assert rel(A @ X.to(DEV), g["Y"]) < t
+    assert rel(A @ X[:, 0].contiguous().to(DEV), g["y"]) < t
+    O = pb.to_oracle(P["spec"])
+    X2 = pb.randn_np((A.shape[1], 33), P["dtype"], 101)   # ragged RHS count: scalar-width path
+    assert rel(A @ X2.to(DEV), O.matmat(X2)) < t
+
+
+def test_matmat_fused_dots_and_gate(cb):
+    """The epilogue's column dots equal sum(X * (A X)) and a closed gate makes the launch a no-op."""
+    for name in ["lap24_f32", "kron884_diag_f32", "dense96_f64", "blockdiag_f32", "lap16_shift_f32"]:
+        P = pb.problem(name)
+        A = pb.to_b200(P["spec"], DEV, P["ann"])
+        X = pb.randn_np((A.shape[1], 8), P["dtype"], 5).to(DEV)
+        Y = torch.empty_like(X)
+        dots = torch.zeros((3, 8), dtype=torch.float64, device=DEV)
+        row = torch.tensor([2], dtype=torch.int32, device=DEV)
+        A.matmat_into(X, Y, dots=dots, dots_row=row)
+        ref = (X.double() * Y.double()).sum(0)
+        assert rel(dots[2], ref) < 1e-12 and float(dots[:2].abs().sum()) == 0.0
+        Y2 = torch.full_like(X, 7.0)
+        closed = torch.tensor([1], dtype=torch.int32, device=DEV)
+        A.matmat_into(X, Y2, dots=dots, dots_row=row, gate=closed)
+        assert bool((Y2 == 7.0).all()) and rel(dots[2], ref) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------- CG
+@pytest.mark.parametrize("case", sorted(CG_CASES))
+def test_cg_vs_oracle_and_golden(case, golden, cb):
+    from oracle import krylov_oracle as ko
+    name, tol, iters = CG_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    x, info = cb.linalg.CG(tol=tol, max_iters=iters)(A, P["B"].to(DEV))
+    xo, ro, ko_iters, info_o = ko.cg(pb.to_oracle(P["spec"]), P["B"], tol=tol, max_iters=iters)
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    # iteration counts: exact for fixed-length runs; convergence-limited runs may differ by rounding at the
+    # threshold crossing, compare the common window
+    n_common = min(len(info["errors"]), len(info_o["errors"]))
+    assert abs(info["iterations"] - info_o["iterations"]) <= 1
+    assert info_o["iterations"] == int(g["iterations"])
+    window = min(n_common, 100)
+    np.testing.assert_allclose(info["errors"][:window], info_o["errors"][:window], rtol=20 * t)
+    np.testing.assert_allclose(info["errors"][:window], g["errors"][:window], rtol=20 * t)
+    if tol > 1e-20:   # converged solves: compare solutions
+        assert rel(x, xo) < 50 * max(t, tol)
+        assert rel(x, g["x"]) < 50 * max(t, tol)
+    else:
+        assert rel(x, xo) < 1e3 * t
+
+
+def test_cg_first_iterations_tight(cb):
+    """Per-iteration residual norms over the first iterations at the strict north-star tolerance."""
+    from oracle import krylov_oracle as ko
+    for name, t in [("lap24_f32", F32_TOL), ("lap24_f64", F64_TOL), ("kron884_diag_f32", F32_TOL),
+                    ("kron465_diag_f64", F64_TOL)]:
+        P = pb.problem(name)
+        A = pb.to_b200(P["spec"], DEV, P["ann"])
+        x, info = cb.linalg.CG(tol=1e-30, max_iters=25)(A, P["B"].to(DEV))
+        xo, _, _, info_o = ko.cg(pb.to_oracle(P["spec"]), P["B"], tol=1e-30, max_iters=25)
+        assert info["iterations"] == info_o["iterations"] == 26
+        np.testing.assert_allclose(info["errors"], info_o["errors"], rtol=t)
+        assert rel(x, xo) < 10 * t
+
+
+def test_cg_vector_x0_and_solve_surface(golden, cb):
+    P = pb.problem("dense96_f32")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    x0 = pb.randn_np(tuple(P["B"].shape), P["dtype"], 77)
+    x, info = cb.linalg.CG(tol=1e-6, max_iters=500, x0=x0.to(DEV))(A, P["B"].to(DEV))
+    g = golden("cg_dense96_f32_x0")
+    assert abs(info["iterations"] - int(g["iterations"])) <= 1 and rel(x, g["x"]) < 1e-4
+    xs = cb.linalg.solve(A, P["B"].to(DEV), cb.linalg.CG(tol=1e-6, max_iters=500))
+    assert rel(xs, golden("solve_dense96_f32")["x"]) < 1e-4
+    Ainv = cb.linalg.inv(A, cb.linalg.CG(tol=1e-6, max_iters=500))
+    xv = Ainv @ P["B"][:, 0].contiguous().to(DEV)
+    assert xv.shape == (96, ) and "iterations" in Ainv.info and rel(xv, golden("solve_dense96_f32")["x"][:, 0]) < 1e-4
+
+
+def test_cg_edge_cases(cb):
+    P = pb.problem("dense96_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    # zero right-hand side: cond_fun false at k=0, no iterations, x = 0
+    x, info = cb.linalg.CG(tol=1e-8, max_iters=50)(A, torch.zeros(96, 2, dtype=torch.float64, device=DEV))
+    assert info["iterations"] == 1 and float(x.abs().sum()) == 0.0
+    # max_iters = 0
+    x, info = cb.linalg.CG(tol=1e-8, max_iters=0)(A, P["B"].to(DEV))
+    assert info["iterations"] == 1 and float(x.abs().sum()) == 0.0
+    # one converged column next to live ones keeps iterating until all meet the tolerance (any(), cg.py:136)
+    B = P["B"].clone()
+    B[:, 1] = 0.0
+    from oracle import krylov_oracle as ko
+    x, info = cb.linalg.CG(tol=1e-9, max_iters=300)(A, B.to(DEV))
+    xo, _, _, info_o = ko.cg(pb.to_oracle(P["spec"]), B, tol=1e-9, max_iters=300)
+    assert abs(info["iterations"] - info_o["iterations"]) <= 1 and rel(x, xo) < 1e-7
+    assert float(x[:, 1].abs().sum()) == 0.0
+
+
+def test_cg_full_size_properties(cb):
+    """BASELINE config 2 at a GPU-friendly slice of full size (1024^2 grid, 64 RHS, fp32): properties that
+    do not need the oracle: the true residual b - A x matches the recurrence residual and decreases."""
+    g = 1024
+    data, rows, cols, shape = pb.laplacian_2d_coo(g, torch.float32)
+    A = cb.PSD(cb.ops.Sparse(data.to(DEV), rows.to(DEV), cols.to(DEV), shape))
+    torch.manual_seed(0)
+    B = torch.randn(shape[0], 64, device=DEV)
+    x, info = cb.linalg.CG(tol=1e-30, max_iters=40)(A, B)
+    r_true = B - A @ x
+    rn = torch.linalg.norm(r_true, dim=0) / torch.linalg.norm(B, dim=0)
+    assert abs(float(rn.mean()) - info["errors"][-1]) < 1e-4 * info["errors"][-1] + 1e-6
+    assert info["errors"][-1] < info["errors"][0] and info["iterations"] == 41
+    # linearity: solving for 2B gives 2x (normalised system => same iterates)
+    x2, _ = cb.linalg.CG(tol=1e-30, max_iters=40)(A, 2 * B)
+    assert rel(x2, 2 * x) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- Lanczos
+@pytest.mark.parametrize("case", sorted(LANCZOS_CASES))
+def test_lanczos_vs_oracle_and_golden(case, golden, cb):
+    from oracle import krylov_oracle as ko
+    name, m, tol, batched = LANCZOS_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    start = P["B"] if (batched or P["B"].dim() == 1) else P["B"][:, 0].contiguous()
+    Q, T, info = cb.linalg.Lanczos(start_vector=start.to(DEV), max_iters=m, tol=tol)(A)
+    Qo, ao, bo, info_o = ko.lanczos(pb.to_oracle(P["spec"]), start, m, tol)
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    assert info["iterations"] == info_o["iterations"] == int(g["iterations"])
+    alpha, beta = T.alpha[..., 0], T.beta[..., 0]
+    assert tuple(alpha.shape) == tuple(g["alpha"].shape) and tuple(beta.shape) == tuple(g["beta"].shape)
+    # the first 12 coefficients at the strict bar; the whole run a little looser (Lanczos amplifies rounding)
+    w = 12
+    assert rel(alpha[..., :w], ao[..., :w]) < t and rel(beta[..., :w], bo[..., :w]) < t
+    assert rel(alpha[..., :w], g["alpha"][..., :w]) < t and rel(beta[..., :w], g["beta"][..., :w]) < t
+    assert rel(alpha, ao) < 100 * t and rel(beta, bo) < 100 * t
+    Qd = Q.to_dense()
+    assert tuple(Qd.shape) == tuple(Qo.shape)
+    Qn = Qd.cpu().numpy()
+    if Qn.ndim == 2 and Qn.shape[0] > 1000:
+        Qn = Qn[::16]
+    assert rel(Qn[..., :w], g["Q"][..., :w]) < 10 * t
+    # orthonormality of the basis (full reorthogonalisation does its job)
+    Qb = Qd if Qd.dim() == 3 else Qd[None]
+    G = Qb.transpose(1, 2).double() @ Qb.double()
+    eye = torch.eye(G.shape[-1], dtype=torch.float64, device=G.device)
+    assert float((G - eye).abs().max()) < (1e-4 if P["dtype"] == torch.float32 else 1e-10)
+
+
+def test_lanczos_known_answers_and_early_stop(golden, cb):
+    """Hand-derived cases the reference's own tests pin (tests/algorithms/test_lanczos.py:268-300)."""
+    L = cb.linalg
+    A = cb.SelfAdjoint(cb.ops.Dense(torch.diag(torch.tensor([4., 2., 1.])).to(DEV)))
+    Q, T, info = L.Lanczos(start_vector=torch.tensor([[1.0, 0.0, 0.0]]).T.to(DEV), max_iters=3, tol=1e-7)(A)
+    g = golden("lanczos_case_early")
+    assert info["iterations"] == int(g["iterations"]) == 2
+    assert tuple(T.beta[..., 0].shape) == tuple(g["beta"].shape) and float(T.beta[0, 0, 0]) == 4.0
+    assert tuple(T.alpha[..., 0].shape) == tuple(g["alpha"].shape)
+    beta, alpha = [1., 3., 7.], [0.1, 1.0]
+    M = torch.tensor([[beta[2], 0, alpha[1]], [0, beta[0], alpha[0]], [alpha[1], alpha[0], beta[1]]])
+    Q, T, info = L.Lanczos(start_vector=torch.tensor([[0.0, 1.0, 0.]]).T.to(DEV), max_iters=3, tol=1e-7)(
+        cb.SelfAdjoint(cb.ops.Dense(M.to(DEV))))
+    assert info["iterations"] - 1 == 3
+    assert rel(T.beta[0, :, 0], beta) < 1e-6 and rel(T.alpha[0, :, 0], alpha) < 1e-6
+
+
+def test_eig_lanczos_default_start(golden, cb):
+    P = pb.problem("graph2k_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    vals, vecs = cb.linalg.eig(A, 6, "LM", cb.linalg.Lanczos(max_iters=48, tol=1e-12))
+    g = golden("eig_graph2k_f64_default_start")
+    assert rel(vals, g["eigvals"]) < F64_TOL
+    V = vecs.to_dense()
+    assert tuple(V.shape) == (2048, 6)
+    assert rel(V.abs()[::16], np.abs(g["eigvecs"])) < 1e-7
+    # Ritz pairs satisfy A v = lambda v to the accuracy of the top of the spectrum
+    res = torch.linalg.norm(A @ V[:, -1].contiguous() - vals[-1] * V[:, -1]) / vals[-1]
+    assert float(res) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- Arnoldi
+@pytest.mark.parametrize("case", sorted(ARNOLDI_CASES))
+def test_arnoldi_vs_oracle_and_golden(case, golden, cb):
+    from oracle import krylov_oracle as ko
+    name, m, tol, batched = ARNOLDI_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    start = P["B"] if batched else P["B"][:, 0].contiguous()
+    Q, H, info = cb.linalg.Arnoldi(start_vector=start.to(DEV), max_iters=m, tol=tol)(A)
+    Qo, Ho, info_o = ko.arnoldi(pb.to_oracle(P["spec"]), start, m, tol)
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    assert info["iterations"] == info_o["iterations"] == int(g["iterations"])
+    Hd, Qd = H.to_dense(), Q.to_dense()
+    assert tuple(Hd.shape) == tuple(g["H"].shape) and tuple(Qd.shape) == tuple(g["Q"].shape)
+    assert rel(Hd, Ho) < 20 * t and rel(Hd, g["H"]) < 20 * t
+    assert rel(Qd, Qo) < 100 * t and rel(Qd, g["Q"]) < 100 * t
+
+
+def test_eig_arnoldi(golden, cb):
+    P = pb.problem("nonsym48_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    vals, vecs = cb.linalg.eig(A, 48, "LM", cb.linalg.Arnoldi(start_vector=P["B"][:, 0].contiguous().to(DEV),
+                                                                max_iters=48, tol=1e-12))
+    mags = np.sort(np.abs(vals.cpu().numpy()))
+    assert rel(mags, golden("eig_arnoldi_nonsym48_f64")["eigvals_sorted_abs"]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------- SLQ / Hutch
+@pytest.mark.parametrize("name,m,vtol", [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2),
+                                          ("lap24_f64", 40, 0.25)])
+def test_slq_logdet_identical_probes(name, m, vtol, golden, cb):
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    g = golden("slq_" + name)
+    val = cb.linalg.stochastic_lanczos_quad(A, torch.log, max_iters=m, tol=1e-7, vtol=vtol, key=int(g["key"]))
+    t = tol_of(P["dtype"])
+    assert abs(float(val) - float(g["logdet"])) <= 10 * t * abs(float(g["logdet"]))
+    # chunked probes give the same estimate (per-probe work is independent)
+    val2 = cb.linalg.stochastic_lanczos_quad(A, torch.log, max_iters=m, tol=1e-7, vtol=vtol, key=int(g["key"]),
+                                             probe_chunk_size=5)
+    assert abs(float(val2) - float(val)) <= 10 * t * abs(float(val))
+
+
+@pytest.mark.parametrize("name,m", [("kron884_diag_f32", 25), ("kron465_diag_f64", 30)])
+def test_log_matmat_and_hutch_logdet(name, m, golden, cb):
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    L = cb.linalg
+    t = tol_of(P["dtype"])
+    F = L.LanczosUnary(A, torch.log, max_iters=m, tol=1e-7)
+    assert rel(F @ P["B"].to(DEV), golden("logA_matmat_" + name)["Y"]) < 100 * t
+    g = golden("hutch_logdet_" + name)
+    val = L.logdet(A, L.Lanczos(max_iters=m, tol=1e-7), L.Hutch(tol=2e-2, max_iters=3, key=int(g["key"])))
+    assert abs(float(val) - float(g["logdet"])) <= 100 * t * abs(float(g["logdet"]))
+    dg = L.Hutch(tol=2e-2, max_iters=3, key=int(g["key"]))(L.LanczosUnary(A, torch.log, max_iters=m, tol=1e-7), 0)
+    assert rel(dg, g["diag"]) < 100 * t
+
+
+def test_hutch_rademacher_and_errors(golden, cb):
+    P = pb.problem("dense96_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    dg = cb.linalg.Hutch(tol=5e-2, max_iters=4, rand="rademacher", key=cb.rng.PRNGKey(7))(A, 0)
+    assert rel(dg, golden("hutch_diag_dense96_f64")["diag"]) < 1e-10
+    with pytest.raises(AssertionError, match="tolerance chosen too high"):
+        cb.linalg.Hutch(tol=1e-4)(A, 0)
+    ex = cb.linalg.diag(A, 0, cb.linalg.Exact())
+    assert rel(ex, torch.diagonal(P["spec"][1])) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------- kernels directly
+def test_reorth_kernels_shapes(cb):
+    """C = V^T W and W -= V C for ragged / wide / single-column probe blocks in both dtypes."""
+    be = cb.backend
+    for dt, t in [(torch.float32, 2e-6), (torch.float64, 1e-13)]:
+        for n, b, nv in [(1000, 1, 7), (777, 3, 5), (512, 8, 33), (300, 64, 40), (257, 100, 9), (129, 160, 4),
+                         (64, 256, 3)]:
+            torch.manual_seed(n + b)
+            V = torch.randn(nv, n, b, dtype=dt, device=DEV)
+            W = torch.randn(n, b, dtype=dt, device=DEV)
+            C = torch.zeros(nv, b, dtype=torch.float64, device=DEV)
+            be.reorth_dots(V, 1, nv, W, C)
+            ref = torch.einsum("jnb,nb->jb", V.double(), W.double())
+            assert float(C[0].abs().sum()) == 0.0
+            assert rel(C[1:], ref[1:]) < t, (dt, n, b, nv)
+            W2 = W.clone()
+            nrm = torch.zeros(b, dtype=torch.float64, device=DEV)
+            be.reorth_update(V, 1, nv, W2, C, sign=-1.0, wnorm2=nrm)
+            refW = W.double() - torch.einsum("jnb,jb->nb", V[1:].double(), C[1:].to(dt).double())
+            assert rel(W2, refW) < 10 * t, (dt, n, b, nv)
+            assert rel(nrm, (W2.double()**2).sum(0)) < 1e-12
+
+
+def test_vector_sweeps_fold_and_ragged(cb):
+    be = cb.backend
+    for dt in (torch.float32, torch.float64):
+        for n, k in [(1001, 1), (4096, 1), (333, 3), (200, 64), (50, 100), (17, 1500)]:
+            torch.manual_seed(n * k)
+            X = torch.randn(n, k, dtype=dt, device=DEV)
+            Y = torch.randn(n, k, dtype=dt, device=DEV)
+            d = torch.zeros(k, dtype=torch.float64, device=DEV)
+            be.col_dots(X, Y, d)
+            assert rel(d, (X.double() * Y.double()).sum(0)) < 1e-12
+            Z = Y.clone()
+            be.axpby(X, Z, 2.0, -3.0)
+            assert rel(Z, 2 * X - 3 * Y) < (1e-6 if dt == torch.float32 else 1e-14)
+            sq = (X.double()**2).sum(0)
+            O = torch.empty_like(X)
+            be.col_scale(X, O, sq, take_sqrt=True, mode=2)
+            assert rel(O, X / torch.sqrt(sq).to(dt)) < (1e-6 if dt == torch.float32 else 1e-14)
