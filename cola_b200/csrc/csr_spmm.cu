@@ -11,6 +11,8 @@
 //     neighbouring rows' segments hit in L1/L2;
 //   * Y is written once, streaming; per-column dot partials stay in registers for the whole kernel.
 // Algorithmic HBM bytes: nnz*(sizeof(T)+4) + 4(n+1) + 2*n*k*sizeof(T)   (SURVEY.md section 8d).
+#include <cstdlib>
+
 #include "sweep.cuh"
 
 namespace cola {
@@ -27,20 +29,33 @@ struct CsrArgs {
   double* dots; const int32_t* dots_row; int64_t k_full; const int32_t* gate;
   int lanes, groups, rows_per_tile, cap;
   int need_x;
+  int l2_prefetch, row_bytes;
 };
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kCsrThreads) csr_spmm_kernel(CsrArgs<T> a) {
+// One staged non-zero: element offset of its X row (col * ldx, computed ONCE per non-zero while staging
+// instead of once per lane in the inner loop) and its value.
+template <typename T>
+struct alignas(sizeof(T) == 4 ? 8 : 16) Nz {
+  uint32_t off;
+  T val;
+};
+
+// OFF32: every X row offset fits 32 bits (n_cols * ldx < 2^32), the common case; otherwise offsets are
+// recomputed in 64 bits from the column index.
+template <typename T, int VEC, bool EPI, bool DOTS, bool OFF32>
+__global__ void __launch_bounds__(kCsrThreads, 4) csr_spmm_kernel(CsrArgs<T> a) {
   if (a.gate != nullptr && *a.gate != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: vals[cap] | cols[cap] | rp[rows_per_tile+1] | red[256*VEC doubles]
-  T* s_vals = reinterpret_cast<T*>(smem_raw);
-  int32_t* s_cols = reinterpret_cast<int32_t*>(s_vals + a.cap);
-  int32_t* s_rp = s_cols + a.cap;
+  // layout: nz[cap] | rp[rows_per_tile+1] | red[256*VEC doubles]
+  Nz<T>* s_nz = reinterpret_cast<Nz<T>*>(smem_raw);
+  int32_t* s_rp = reinterpret_cast<int32_t*>(s_nz + a.cap);
   const int tid = threadIdx.x;
   const int g = tid / a.lanes, l = tid - g * a.lanes;
-  const int64_t c0 = (int64_t)l * VEC;
+  const int c0 = l * VEC;
   const bool col_ok = (g < a.groups) && (c0 < a.k);
+  const T* __restrict__ Xc = a.X + c0;
+  T* __restrict__ Yc = a.Y + c0;
+  const uint32_t ldx32 = (uint32_t)a.ldx;
 
   double dacc[VEC];
 #pragma unroll
@@ -58,8 +73,18 @@ __global__ void __launch_bounds__(kCsrThreads) csr_spmm_kernel(CsrArgs<T> a) {
     const bool staged = tile_nnz <= a.cap;
     if (staged) {
       for (int i = tid; i < tile_nnz; i += kCsrThreads) {
-        s_cols[i] = __ldcs(a.colidx + base + i);
-        s_vals[i] = __ldcs(a.vals + base + i);
+        Nz<T> e;
+        const uint32_t c = (uint32_t)__ldcs(a.colidx + base + i);
+        e.off = OFF32 ? c * ldx32 : c;
+        e.val = __ldcs(a.vals + base + i);
+        s_nz[i] = e;
+        if (a.l2_prefetch) {
+          // The gather below is latency-bound (ncu: long-scoreboard stalls, DRAM at 36 %).  Requesting every X row
+          // of the tile into L2 now -- one thread per non-zero, no registers held, all requests in flight at
+          // once -- turns the dependent loads of the row loop into L2 hits.
+          const char* xr = reinterpret_cast<const char*>(a.X + (size_t)c * (size_t)a.ldx);
+          for (int b = 0; b < a.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + b));
+        }
       }
     }
     __syncthreads();
@@ -73,51 +98,61 @@ __global__ void __launch_bounds__(kCsrThreads) csr_spmm_kernel(CsrArgs<T> a) {
       if (staged) {
 #pragma unroll 4
         for (int32_t j = s; j < e; ++j) {
-          const int64_t c = s_cols[j];
-          const T w = s_vals[j];
-          Vec<T, VEC> x = ldg<T, VEC>(a.X + c * a.ldx + c0);
+          const Nz<T> z = s_nz[j];
+          const Vec<T, VEC> x = ldg<T, VEC>(OFF32 ? (Xc + z.off) : (Xc + (uint64_t)z.off * (uint64_t)a.ldx));
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] += w * x.v[v];
+          for (int v = 0; v < VEC; ++v) acc[v] += z.val * x.v[v];
         }
-      } else {  // tile too heavy for the staging buffer: read the CSR arrays directly
-#pragma unroll 4
+      } else {  // tile too heavy for the staging buffer: read the CSR arrays directly (rare, kept small)
+#pragma unroll 1
         for (int32_t j = s; j < e; ++j) {
           const int64_t c = a.colidx[base + j];
           const T w = a.vals[base + j];
-          Vec<T, VEC> x = ldg<T, VEC>(a.X + c * a.ldx + c0);
+          Vec<T, VEC> x = ldg<T, VEC>(Xc + c * a.ldx);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) acc[v] += w * x.v[v];
         }
       }
-      Vec<T, VEC> y, xo;
-      if (a.need_x) xo = ldg<T, VEC>(a.X + row * a.ldx + c0);
-      const T d = a.diag ? a.diag[row] : (T)0;
-      Vec<T, VEC> yo;
-      if (a.accumulate) yo = ldg<T, VEC>(a.Y + row * a.ldy + c0);
+      Vec<T, VEC> y;
+      if constexpr (EPI) {
+        const Vec<T, VEC> xo = ldg<T, VEC>(Xc + row * a.ldx);   // own row: an L1 hit (it is one of the gathered rows)
+        const T d = a.diag ? a.diag[row] : (T)0;
+        Vec<T, VEC> yo;
+        if (a.accumulate) yo = ldg<T, VEC>(Yc + row * a.ldy);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        T t = a.alpha * acc[v];
-        if (a.shift != (T)0) t += a.shift * xo.v[v];
-        if (a.diag) t += d * xo.v[v];
-        if (a.accumulate) t += yo.v[v];
-        y.v[v] = t;
-        if (a.dots) dacc[v] += (double)xo.v[v] * (double)t;
+        for (int v = 0; v < VEC; ++v) {
+          T t = a.alpha * acc[v];
+          if (a.shift != (T)0) t += a.shift * xo.v[v];
+          if (a.diag) t += d * xo.v[v];
+          if (a.accumulate) t += yo.v[v];
+          y.v[v] = t;
+          if constexpr (DOTS) dacc[v] += (double)xo.v[v] * (double)t;
+        }
+      } else {
+        if (a.accumulate) {
+          Vec<T, VEC> yo = ldg<T, VEC>(Yc + row * a.ldy);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) y.v[v] = a.alpha * acc[v] + yo.v[v];
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) y.v[v] = a.alpha * acc[v];
+        }
       }
-      stg_stream<T, VEC>(a.Y + row * a.ldy + c0, y);
+      stg_stream<T, VEC>(Yc + row * a.ldy, y);
     }
   }
 
-  if (a.dots) {
+  if constexpr (DOTS) {
     double* red = reinterpret_cast<double*>(s_rp + a.rows_per_tile + 2);
     red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(red) + 7) & ~(uintptr_t)7);
     double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k_full : 0);
-    block_col_reduce<VEC>(red, dacc, col_ok, tid, g, l, a.lanes, a.groups, c0, a.k, -1, out);
+    block_col_reduce<VEC>(red, dacc, col_ok, tid, g, l, a.lanes, a.groups, (int64_t)c0, a.k, -1, out);
   }
 }
 
 template <typename T>
 int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_t n_rows, int64_t n_cols,
-             int64_t nnz, const T* X, int64_t ldx, int64_t k, T* Y, int64_t ldy, T alpha, T shift, const T* diag,
+             int64_t nnz, int64_t max_row_nnz, const T* X, int64_t ldx, int64_t k, T* Y, int64_t ldy, T alpha, T shift, const T* diag,
              int accumulate, double* dots, const int32_t* dots_row, const int32_t* gate, cudaStream_t st) {
   COLA_REQUIRE(rowptr && colidx && vals && X && Y, "csr_spmm: null pointer");
   COLA_REQUIRE(ldx >= k && ldy >= k, "csr_spmm: leading dimension < k");
@@ -136,29 +171,46 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     a.Y = Y + c; a.ldy = ldy; a.alpha = alpha; a.shift = shift; a.diag = diag; a.accumulate = accumulate;
     a.dots = dots ? dots + c : nullptr; a.dots_row = dots_row; a.k_full = k; a.gate = gate;
     a.need_x = epi ? 1 : 0;
+    static const bool no_pf = getenv("COLA_CSR_NO_PREFETCH") != nullptr;   // A/B knob
+    a.row_bytes = (int)(a.k * (int64_t)sizeof(T));
+    a.l2_prefetch = (!no_pf && a.row_bytes >= 32) ? 1 : 0;
     int64_t need = (a.k + vec - 1) / vec;
     a.lanes = (int)need;
     a.groups = kCsrThreads / a.lanes;
     // tile size: ~6 rows per group in flight, but keep the staged nnz range near half the buffer
     double avg = n_rows > 0 ? (double)nnz / (double)n_rows : 1.0;
     if (avg < 1.0) avg = 1.0;
-    const int cap_max = sizeof(T) == 4 ? 4096 : 2048;   // staging buffer stays under the 48 KB default
+    const int cap_max = 2048;   // staging buffer (8 or 16 B per non-zero) stays under the 48 KB default
     int rpg = (int)((cap_max / 2) / (avg * a.groups));
     if (rpg < 1) rpg = 1;
     if (rpg > 8) rpg = 8;
     a.rows_per_tile = a.groups * rpg;
     int64_t want = (int64_t)(2.0 * avg * a.rows_per_tile) + 64;   // 2x the mean tile, heavier tiles take the direct path
     a.cap = (int)(want < 512 ? 512 : (want > cap_max ? cap_max : want));
-    size_t smem = (size_t)a.cap * (sizeof(T) + 4) + (size_t)(a.rows_per_tile + 4) * 4 + 8 +
+    size_t smem = (size_t)a.cap * sizeof(Nz<T>) + (size_t)(a.rows_per_tile + 4) * 4 + 8 +
                   (dots ? (size_t)kCsrThreads * vec * sizeof(double) : 0);
     int64_t n_tiles = (n_rows + a.rows_per_tile - 1) / a.rows_per_tile;
+    const bool off32 = (double)n_cols * (double)ldx < 4294967296.0;
+#define COLA_CSR_LAUNCH(EPIV, DOTSV, OFFV)                                                                    \
+  do {                                                                                                        \
+    auto kern = csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV>;                                                \
+    int per_sm = 0;                                                                                           \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCsrThreads, smem);                          \
+    if (per_sm < 1) per_sm = 1;                                                                               \
+    int64_t grid = (int64_t)sm_count() * per_sm; /* persistent: whole waves of resident CTAs */               \
+    if (grid > n_tiles) grid = n_tiles;                                                                       \
+    kern<<<(unsigned)grid, kCsrThreads, smem, st>>>(a);                                                       \
+  } while (0)
     COLA_DISPATCH_VEC(T, vec, ({
-      int per_sm = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, csr_spmm_kernel<T, VEC>, kCsrThreads, smem);
-      if (per_sm < 1) per_sm = 1;
-      int64_t grid = (int64_t)sm_count() * per_sm;   // persistent: whole waves of resident CTAs
-      if (grid > n_tiles) grid = n_tiles;
-      csr_spmm_kernel<T, VEC><<<(unsigned)grid, kCsrThreads, smem, st>>>(a);
+      if (off32) {
+        if (dots) COLA_CSR_LAUNCH(true, true, true);
+        else if (epi) COLA_CSR_LAUNCH(true, false, true);
+        else COLA_CSR_LAUNCH(false, false, true);
+      } else {
+        if (dots) COLA_CSR_LAUNCH(true, true, false);
+        else if (epi) COLA_CSR_LAUNCH(true, false, false);
+        else COLA_CSR_LAUNCH(false, false, false);
+      }
     }));
     rc = cuda_status("csr_spmm");
   }
@@ -170,17 +222,19 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
 using namespace cola;
 extern "C" {
 int cola_csr_spmm_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, const float* X, int64_t ldx, int64_t k, float* Y, int64_t ldy,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const float* X, int64_t ldx, int64_t k, float* Y,
+                      int64_t ldy,
                       float alpha, float shift, const float* diag, int accumulate, double* dots,
                       const int32_t* dots_row, const int32_t* gate, void* stream) {
-  return csr_spmm<float>(rowptr, colidx, vals, n_rows, n_cols, nnz, X, ldx, k, Y, ldy, alpha, shift, diag, accumulate,
+  return csr_spmm<float>(rowptr, colidx, vals, n_rows, n_cols, nnz, max_row_nnz, X, ldx, k, Y, ldy, alpha, shift, diag, accumulate,
                          dots, dots_row, gate, reinterpret_cast<cudaStream_t>(stream));
 }
 int cola_csr_spmm_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, const double* X, int64_t ldx, int64_t k, double* Y, int64_t ldy,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const double* X, int64_t ldx, int64_t k, double* Y,
+                      int64_t ldy,
                       double alpha, double shift, const double* diag, int accumulate, double* dots,
                       const int32_t* dots_row, const int32_t* gate, void* stream) {
-  return csr_spmm<double>(rowptr, colidx, vals, n_rows, n_cols, nnz, X, ldx, k, Y, ldy, alpha, shift, diag,
+  return csr_spmm<double>(rowptr, colidx, vals, n_rows, n_cols, nnz, max_row_nnz, X, ldx, k, Y, ldy, alpha, shift, diag,
                           accumulate, dots, dots_row, gate, reinterpret_cast<cudaStream_t>(stream));
 }
 }

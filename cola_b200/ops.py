@@ -251,6 +251,7 @@ class Sparse(LinearOperator):
         self.indptr = rowptr.to(torch.int32).contiguous()
         self.indices = self.col_indices.to(torch.int32).contiguous()
         self.nnz = int(self.data.numel())
+        self.max_row_nnz = int(counts.max()) if counts.numel() > 0 else 0
 
     def _transpose(self):
         return Sparse(self.data, self.col_indices, self.row_indices, (self.shape[1], self.shape[0]))
@@ -532,7 +533,7 @@ class _CsrCore:
 
     def apply(self, X, Y, epi):
         S = self.S
-        be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, X, Y, **epi.kw())
+        be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, S.max_row_nnz, X, Y, **epi.kw())
 
 
 class _KronCore:

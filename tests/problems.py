@@ -133,6 +133,35 @@ def problem(name):
     raise KeyError(name)
 
 
+def upcast(spec):
+    """Same spec with every floating tensor promoted to float64 (oracle sensitivity probes)."""
+    if torch.is_tensor(spec):
+        return spec.double() if spec.is_floating_point() else spec
+    if isinstance(spec, (list, tuple)):
+        return type(spec)(upcast(v) for v in spec)
+    return spec
+
+
+def stable_window(name, tol, max_iters, rtol):
+    """Number of leading entries of info['errors'] over which the CG residual trace of problem `name` is
+    numerically well-posed at tolerance rtol: the oracle is re-run on a perturbed copy of the problem
+    (fp32 problems: in float64; fp64 problems: right-hand side perturbed by 1e-15 relative) and the window
+    ends where the two oracle traces stop agreeing to rtol/4.  Beyond it CG's own rounding sensitivity, not
+    the implementation, decides the digits (e.g. tiny block-diagonal systems after Krylov exhaustion)."""
+    from oracle import krylov_oracle as ko
+    P = problem(name)
+    _, _, _, base = ko.cg(to_oracle(P["spec"]), P["B"], tol=tol, max_iters=max_iters)
+    if P["dtype"] == torch.float32:
+        _, _, _, other = ko.cg(to_oracle(upcast(P["spec"])), P["B"].double(), tol=tol, max_iters=max_iters)
+    else:
+        noise = 1.0 + 1e-15 * t(rs(999).normal(size=tuple(P["B"].shape)), torch.float64)
+        _, _, _, other = ko.cg(to_oracle(P["spec"]), P["B"] * noise, tol=tol, max_iters=max_iters)
+    a, b = base["errors"], other["errors"]
+    m = min(len(a), len(b))
+    bad = np.nonzero(np.abs(a[:m] - b[:m]) > 0.25 * rtol * np.abs(b[:m]))[0]
+    return int(bad[0]) if len(bad) else m
+
+
 # ---------------------------------------------------------------------------- spec -> operators
 def to_oracle(spec):
     from oracle import krylov_oracle as ko
