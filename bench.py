@@ -76,7 +76,7 @@ class ClockSampler:
             return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", os.environ.get("COLA_BENCH_CLOCK_MS", "200"), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", os.environ.get("COLA_BENCH_CLOCK_MS", "500"), "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:

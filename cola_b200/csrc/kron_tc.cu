@@ -1,0 +1,459 @@
+// Kronecker matmat on the 5th-generation tensor cores (north_star item 3): a chain of batched mode-k
+// contractions  out[p, a, l, r] = sum_j F[a, j] * in[p, j, l, r]  with 64x64 fp32 factors, executed as
+// tcgen05.mma kind::tf32 with TMEM accumulators and TMA-staged tiles.  Replaces the moveaxis/reshape/GEMM/
+// moveaxis chain of Kronecker._matmat (cola/ops/operators.py:216-223).
+//
+// Formulation (per tile): D'[m, a] = sum_j A'[m, j] * B'[j, a]
+//   A' = the input tile: 128 "positions" m x K = 64 contraction indices j.  A position is (atom, r): an atom is
+//        a (p, l) pair, r one of 32 consecutive right-hand sides; in memory the 32 r of one (p, j, l) are
+//        contiguous (128 B), so one TMA box {32 r, 1 l, 64 j} (SWIZZLE_128B_ATOM_32B) IS one MN-major UMMA atom and a tile
+//        is just 4 such boxes (no transposes, no reshapes, whatever mode is being contracted).
+//   B' = F^T: K-major (F is row-major [a][j]), loaded once per CTA by TMA with the same 128B swizzle.
+//   D' = 128 TMEM lanes (positions) x 64 columns (a), fp32.
+// fp32-grade accuracy from tf32 tensor cores: 3xTF32 error compensation.  Every operand x is split on the CUDA
+// cores into hi = tf32(x) and lo = tf32(x - hi) (elementwise, in place in the swizzled tile, so the layout
+// never matters) and D' = A_lo B_hi + A_hi B_lo + A_hi B_hi  (24 MMAs of 128x64x8 per tile).
+// Roofline: the contraction itself is HBM-bound at d = 64 (48 flop/B < tf32 ridge): 64 KB of traffic per tile vs
+// 768 tensor-pipe cycles.  The host driver therefore runs all modes on one 32-column chunk of right-hand sides at
+// a time so the two intermediates (n*32 floats each) stay in the 126 MB L2, and only X in / Y out cross HBM.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over tiles): warp 0 TMA producer, warp 1 MMA issuer,
+// warp 2 TMEM allocator, warps 4-7 operand split, warps 8-11 epilogue (TMEM -> registers -> global, fused
+// alpha / shift / diag / pAp-dots on the last mode).
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace cola {
+
+constexpr int kTcThreads = 384;
+constexpr int kD = 64;                 // factor size handled by this path
+constexpr int kAtomBytes = 64 * 128;   // one TMA box: 64 rows (j) x 32 floats
+constexpr int kTileBytes = 4 * kAtomBytes;   // 32 KB: 128 positions x 64 j
+constexpr int kStages = 2;
+constexpr int kFacBytes = kD * kD * 4;       // 16 KB
+// shared memory map (all 1024-byte aligned for the 128B swizzle)
+constexpr int kOffFacHi = 0;
+constexpr int kOffFacLo = kOffFacHi + kFacBytes;
+constexpr int kOffStage = kOffFacLo + kFacBytes;                 // per stage: hi tile | lo tile
+constexpr int kOffBars = kOffStage + kStages * 2 * kTileBytes;
+constexpr int kSmemBytes = kOffBars + 256 + 1024;                // + alignment slack
+
+struct TcArgs {
+  float* out; const float* epi_x; const float* diag;
+  int64_t L, pre;           // in viewed as (pre, 64, L, row) with row = in_k floats
+  int64_t in_r0;            // first column of the 32-wide RHS chunk inside the source rows (TMA coordinate 0)
+  int64_t out_k, out_r0;    // row length of the destination and column offset of the chunk inside it
+  int64_t n_tiles;          // pre * L / 4
+  float alpha, shift; int accumulate; int last_mode;
+  double* dots; const int32_t* dots_row; const int32_t* gate;
+  int dbg;   // bring-up knob (COLA_KRON_DBG): 1 = skip split math, 2 = skip MMAs, 4 = skip epilogue stores
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor), version 1.
+// layout: 2 = SWIZZLE_128B (16-byte chunks ^ row%8), 1 = SWIZZLE_128B_BASE32B (32-byte chunks ^ row%4), the only
+// layout the tensor core accepts for MN-major 32-bit (tf32) operands (measured: every other MN-major tf32
+// layout silently yields zeros; scripts/umma_probe.cu).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor (InstrDescriptor): D=f32, A=B=tf32, A MN-major, B K-major, M=128, N=64
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((64u >> 3) << 17) |
+                            ((128u >> 4) << 24);
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+// elementwise 3xTF32 split of `bytes` of swizzled operand data: hi in place, lo into the twin buffer
+__device__ __forceinline__ void split_hi_lo(unsigned char* hi, unsigned char* lo, int bytes, int tid, int nthreads) {
+  for (int o = tid * 16; o < bytes; o += nthreads * 16) {
+    float4 v = *reinterpret_cast<float4*>(hi + o);
+    float4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    *reinterpret_cast<float4*>(hi + o) = h;
+    *reinterpret_cast<float4*>(lo + o) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+    kron_mode_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_fac,
+                        TcArgs a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  // barriers
+  const uint32_t bar_full0 = sbase + kOffBars;            // [stage] TMA landed
+  const uint32_t bar_ready0 = bar_full0 + 8 * kStages;     // [stage] split done (count 4: one per split warp)
+  const uint32_t bar_empty0 = bar_ready0 + 8 * kStages;    // [stage] MMAs that read the stage retired
+  const uint32_t bar_tfull0 = bar_empty0 + 8 * kStages;    // [acc]   accumulator complete
+  const uint32_t bar_tempty0 = bar_tfull0 + 8 * 2;         // [acc]   accumulator drained (count 4)
+  const uint32_t bar_fac = bar_tempty0 + 8 * 2;            // factor landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBars + 200);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_full0 + 8 * s, 1);
+      mbar_init(bar_ready0 + 8 * s, 4);
+      mbar_init(bar_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull0 + 8 * s, 1);
+      mbar_init(bar_tempty0 + 8 * s, 4);
+    }
+    mbar_init(bar_fac, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // factor: TMA (2 boxes of 32 k x 64 rows), then everybody splits it into hi/lo
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_fac, kFacBytes);
+    tma_load_2d(sbase + kOffFacHi, &map_fac, bar_fac, 0, 0);
+    tma_load_2d(sbase + kOffFacHi + kFacBytes / 2, &map_fac, bar_fac, 32, 0);
+  }
+  mbar_wait(bar_fac, 0);
+  split_hi_lo(smem + kOffFacHi, smem + kOffFacLo, kFacBytes, threadIdx.x, kTcThreads);
+  fence_async_smem();
+  __syncthreads();
+
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(bar_empty0 + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_full0 + 8 * s, kTileBytes);
+        const uint32_t dst = sbase + kOffStage + s * 2 * kTileBytes;
+        for (int at = 0; at < 4; ++at) {
+          const int64_t flat = t * 4 + at;
+          const int64_t p = flat / a.L, l = flat - p * a.L;
+          tma_load_3d(dst + at * kAtomBytes, &map_in, bar_full0 + 8 * s, (int)a.in_r0, (int)l, (int)(p * kD));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(bar_tempty0 + 8 * acc, aph ^ 1);
+        mbar_wait(bar_ready0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t a_hi = sbase + kOffStage + s * 2 * kTileBytes, a_lo = a_hi + kTileBytes;
+        const uint32_t b_hi = sbase + kOffFacHi, b_lo = sbase + kOffFacLo;
+        const uint32_t d = tmem_base + acc * kD;
+        uint32_t accum = 0;
+        if (!(a.dbg & 2))
+        // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t A0 = (term == 0) ? a_lo : a_hi;
+          const uint32_t B0 = (term == 1) ? b_lo : b_hi;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            // A': MN-major SW128_BASE32B: rows (j) of 128 B, K groups of 4 rows 512 B apart (SBO), 8 rows per
+            // MMA step (1024 B); the four 32-position atoms along MN are 8 KB apart (LBO)
+            const uint64_t ad = make_desc(A0 + kk * 1024, kAtomBytes, 512, kLayoutSw128Base32);
+            // B': K-major, two 32-float k-chunks of 8 KB; 32 B per K step inside a chunk; 8-row groups 1 KB apart
+            const uint64_t bd = make_desc(B0 + (kk / 4) * (kFacBytes / 2) + (kk % 4) * 32, 16, 1024, kLayoutSw128);
+            umma_tf32(d, ad, bd, kIdesc, accum);
+            accum = 1;
+          }
+        }
+        umma_commit(bar_empty0 + 8 * s);     // stage may be refilled once these MMAs retire
+        umma_commit(bar_tfull0 + 8 * acc);   // accumulator ready for the epilogue
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== operand split: raw fp32 tile -> hi (in place) + lo =====
+    const int tid = threadIdx.x - 128;
+    int it = 0;
+    for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
+      const int s = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      mbar_wait(bar_full0 + 8 * s, ph);
+      unsigned char* hi = smem + kOffStage + s * 2 * kTileBytes;
+      if (!(a.dbg & 1)) split_hi_lo(hi, hi + kTileBytes, kTileBytes, tid, 128);
+      fence_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_ready0 + 8 * s);
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp - 8;                 // TMEM lane quadrant == atom index within the tile
+    double dacc = 0.0;
+    int it = 0;
+    for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
+      const int acc = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      const int64_t flat = t * 4 + q;
+      const int64_t p = flat / a.L, l = flat - p * a.L;
+      // element (a, r) of this atom lives at base + a * row_stride + r
+      const int64_t row_stride = a.L * a.out_k;
+      const int64_t base = (p * kD * a.L + l) * a.out_k + a.out_r0 + lane;
+      mbar_wait(bar_tfull0 + 8 * acc, aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kD;
+      const float* __restrict__ xin = a.epi_x;
+      const float* __restrict__ dg = a.diag;
+      float* __restrict__ outp = a.out;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c * 16, v);
+        // operands of the fused epilogue are requested while the TMEM load is in flight (independent loads,
+        // all issued before the first use)
+        float xv[16], dv[16], ov[16];
+        if (a.last_mode) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int64_t o = base + (int64_t)(c * 16 + i) * row_stride;
+            xv[i] = xin ? xin[o] : 0.f;
+            dv[i] = dg ? dg[(p * kD + c * 16 + i) * a.L + l] : 0.f;
+            ov[i] = a.accumulate ? outp[o] : 0.f;
+          }
+        }
+        tmem_ld_wait();
+        if (c == 3) {   // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);
+        }
+        if (a.dbg & 4) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int64_t o = base + (int64_t)(c * 16 + i) * row_stride;
+          float y = a.alpha * __uint_as_float(v[i]);
+          if (a.last_mode) {
+            if (xin != nullptr) {
+              if (a.shift != 0.f) y += a.shift * xv[i];
+              if (dg != nullptr) y += dv[i] * xv[i];
+              if (a.dots != nullptr) dacc += (double)xv[i] * (double)y;
+            }
+            if (a.accumulate) y += ov[i];
+          }
+          outp[o] = y;
+        }
+      }
+    }
+    if (a.dots != nullptr) {
+      double* outp = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.out_k : 0);
+      atomicAdd(outp + a.out_r0 + lane, dacc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+static int make_map_in(CUtensorMap* m, const float* in, int64_t pre, int64_t L, int64_t k) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(COLA_E_UNSUPPORTED, "kron_tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)L, (cuuint64_t)(pre * kD)};
+  cuuint64_t strides[2] = {(cuuint64_t)(k * 4), (cuuint64_t)(L * k * 4)};
+  cuuint32_t box[3] = {32, 1, (cuuint32_t)kD};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)in, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(COLA_E_BADARG, "kron_tc: cuTensorMapEncodeTiled(in) failed");
+  return COLA_OK;
+}
+
+static int make_map_fac(CUtensorMap* m, const float* F, int64_t ldf) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(COLA_E_UNSUPPORTED, "kron_tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)kD};
+  cuuint64_t strides[1] = {(cuuint64_t)(ldf * 4)};
+  cuuint32_t box[2] = {32, (cuuint32_t)kD};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)F, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(COLA_E_BADARG, "kron_tc: cuTensorMapEncodeTiled(factor) failed");
+  return COLA_OK;
+}
+
+}  // namespace cola
+
+using namespace cola;
+
+extern "C" {
+
+int64_t cola_kron_tc_workspace_bytes(int64_t n, int64_t n_factors) {
+  return n_factors > 1 ? 2 * n * 32 * (int64_t)sizeof(float) : 0;
+}
+
+int cola_kron_tc_supported(int64_t n_factors, const int64_t* dims, int64_t k) {
+  if (n_factors < 1 || n_factors > 8 || k < 32 || k % 32 != 0) return 0;
+  int64_t n = 1;
+  for (int64_t i = 0; i < n_factors; ++i) {
+    if (dims[i] != kD) return 0;
+    n *= kD;
+  }
+  // tiles are groups of 4 atoms: pre*L must be a multiple of 4 for every mode, i.e. n/64 % 4 == 0
+  if (n_factors == 1) return 0;   // a single 64x64 dense factor: plain GEMM path
+  return ((n / kD) % 4 == 0) ? 1 : 0;
+}
+
+int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
+                            float* Y, int64_t k, float* workspace, float alpha, float shift, const float* diag,
+                            int accumulate, double* dots, const int32_t* dots_row, const int32_t* gate,
+                            void* stream) {
+  COLA_REQUIRE(factors && ldf && X && Y, "kron_tc: null pointer");
+  COLA_REQUIRE(n_factors >= 2 && n_factors <= 8, "kron_tc: 2..8 factors of 64x64");
+  COLA_REQUIRE(k >= 32 && k % 32 == 0, "kron_tc: k must be a multiple of 32");
+  COLA_REQUIRE(workspace, "kron_tc: workspace required (cola_kron_tc_workspace_bytes)");
+  COLA_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)workspace % 128 == 0),
+               "kron_tc: X/Y must be 16-byte and workspace 128-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t n = 1;
+  for (int64_t i = 0; i < n_factors; ++i) n *= kD;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kron_mode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    attr_set = true;
+  }
+  float* ws0 = workspace;
+  float* ws1 = workspace + n * 32;
+  CUtensorMap fac_maps[8];
+  for (int64_t i = 0; i < n_factors; ++i) {
+    COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
+    int rc = make_map_fac(&fac_maps[i], factors[i], ldf[i]);
+    if (rc) return rc;
+  }
+  const int grid_max = sm_count();
+  // One 32-column chunk of right-hand sides at a time through ALL modes: the two chunk-sized intermediates
+  // (n*32 floats = 33.5 MB for n = 64^3) ping-pong inside L2, only X (in) and Y (out) stream through HBM.
+  for (int64_t r0 = 0; r0 < k; r0 += 32) {
+    const float* src = X;
+    int64_t src_k = k, src_r0 = r0;       // the chunk inside X is strided (row length k); intermediates are dense (32)
+    for (int64_t i = 0; i < n_factors; ++i) {
+      const bool last = (i == n_factors - 1);
+      int64_t pre = 1, L = 1;
+      for (int64_t j = 0; j < i; ++j) pre *= kD;
+      for (int64_t j = i + 1; j < n_factors; ++j) L *= kD;
+      float* dst = last ? Y : ((i % 2 == 0) ? ws0 : ws1);
+      CUtensorMap map_in;
+      int rc = make_map_in(&map_in, src, pre, L, src_k);
+      if (rc) return rc;
+      TcArgs a;
+      a.out = dst; a.epi_x = nullptr; a.diag = nullptr; a.L = L; a.pre = pre;
+      a.in_r0 = src_r0; a.out_k = last ? k : 32; a.out_r0 = last ? r0 : 0;
+      a.n_tiles = pre * L / 4; a.alpha = last ? alpha : 1.f; a.shift = 0.f; a.accumulate = 0;
+      a.last_mode = last ? 1 : 0; a.dots = nullptr; a.dots_row = dots_row; a.gate = gate;
+      static const int dbg = getenv("COLA_KRON_DBG") ? atoi(getenv("COLA_KRON_DBG")) : 0;
+      a.dbg = dbg;
+      if (last) {
+        const bool epi = (shift != 0.f) || diag || dots;
+        a.epi_x = epi ? X : nullptr; a.diag = diag; a.shift = shift; a.accumulate = accumulate; a.dots = dots;
+      }
+      const int64_t grid = a.n_tiles < grid_max ? a.n_tiles : grid_max;
+      kron_mode_tc_kernel<<<(unsigned)grid, kTcThreads, kSmemBytes, st>>>(map_in, fac_maps[i], a);
+      rc = cuda_status("kron_mode_tc");
+      if (rc) return rc;
+      src = dst; src_k = a.out_k; src_r0 = a.out_r0;
+    }
+  }
+  return COLA_OK;
+}
+
+}  // extern "C"

@@ -11,6 +11,7 @@ and executes it as one fused kernel per core operator K_t (shift / Diagonal / pA
 CUDA float32/float64 only; CPU tensors raise (there is no fallback path).
 """
 import copy
+import ctypes
 from functools import reduce
 from numbers import Number
 
@@ -543,6 +544,7 @@ class _KronCore:
         self.Fs = [(f if f.is_contiguous() else f.contiguous()) for f in factors]
         self.shape = (_prod([f.shape[0] for f in self.Fs]), _prod([f.shape[1] for f in self.Fs]))
         self._ws = {}
+        self.use_tensor_cores = True   # set False to force the exact-fp32 SIMT contraction (A/B checks)
 
     def _workspace(self, numel, dtype, device, slot):
         key = (slot, dtype, device)
@@ -552,7 +554,30 @@ class _KronCore:
             self._ws[key] = buf
         return buf
 
+    def _tc_ok(self, X):
+        """fp32, every factor 64x64, k % 32 == 0: the tcgen05 / TMA path (csrc/kron_tc.cu)."""
+        if X.dtype != torch.float32 or len(self.Fs) < 2:
+            return False
+        if any(tuple(f.shape) != (64, 64) for f in self.Fs):
+            return False
+        dims = (ctypes.c_int64 * len(self.Fs))(*[64] * len(self.Fs))
+        return bool(be.lib().cdll.cola_kron_tc_supported(len(self.Fs), dims, X.shape[1]))
+
+    def _apply_tc(self, X, Y, epi):
+        D = len(self.Fs)
+        n, k = X.shape
+        ws_bytes = int(be.lib().cdll.cola_kron_tc_workspace_bytes(n, D))
+        ws = self._workspace(ws_bytes // 4, X.dtype, X.device, "tc")
+        facs = (ctypes.c_void_p * D)(*[f.data_ptr() for f in self.Fs])
+        ldf = (ctypes.c_int64 * D)(*[f.stride(0) for f in self.Fs])
+        be.lib().call("cola_kron_matmat_tc_f32", D, facs, ldf, be.ptr(X), be.ptr(Y), k, be.ptr(ws),
+                      ctypes.c_float(epi.alpha), ctypes.c_float(epi.shift),
+                      be.ptr(epi.diag) if epi.diag is not None else None, int(epi.accumulate), be.ptr(epi.dots),
+                      be.ptr(epi.dots_row), be.ptr(epi.gate), be.stream_ptr())
+
     def apply(self, X, Y, epi):
+        if self.use_tensor_cores and self._tc_ok(X):
+            return self._apply_tc(X, Y, epi)
         k = X.shape[1]
         D = len(self.Fs)
         d_in = [f.shape[1] for f in self.Fs]

@@ -318,6 +318,54 @@ def test_hutch_rademacher_and_errors(golden, cb):
     assert rel(ex, torch.diagonal(P["spec"][1])) < 1e-12
 
 
+# ------------------------------------------------------------------------------------------- tensor-core Kronecker
+def test_kronecker_tensor_core_path(cb):
+    """64x64 factors take the tcgen05 / TMA path (3xTF32): fp32-grade accuracy against an fp64 reference, the
+    fused epilogue (shift, diagonal, pAp dots), agreement with the exact SIMT contraction, and CG parity with the
+    CPU oracle on a BASELINE-config-3-shaped operator (scaled to two factors so the oracle stays fast)."""
+    from oracle import krylov_oracle as ko
+    torch.manual_seed(0)
+    for D, k in [(2, 32), (2, 96), (3, 64)]:
+        Fs = [pb.kron_factor(64, torch.float32, 40 + i) for i in range(D)]
+        n = 64**D
+        dg = pb.t(pb.rs(9).uniform(size=n) + 0.5, torch.float32)
+        K = cb.ops.Kronecker(*[cb.ops.Dense(F.to(DEV)) for F in Fs])
+        A = cb.PSD(K + 0.1 * cb.ops.I_like(K) + cb.ops.Diagonal(dg.to(DEV)))
+        core = A.plan().terms[0][1][0]
+        X = pb.randn_np((n, k), torch.float32, 3).to(DEV)
+        assert core._tc_ok(X)
+        Y = torch.empty_like(X)
+        dots = torch.zeros(k, dtype=torch.float64, device=DEV)
+        A.matmat_into(X, Y, dots=dots)
+        E = X.double().reshape(*([64] * D), k)
+        for i, F in enumerate(Fs):
+            E = torch.moveaxis(torch.tensordot(F.double().to(DEV), torch.moveaxis(E, i, 0), dims=1), 0, i)
+        ref = E.reshape(n, k) + (0.1 + dg.double().to(DEV))[:, None] * X.double()
+        assert rel(Y, ref) < 2e-6, (D, k, rel(Y, ref))
+        assert rel(dots, (X.double() * Y.double()).sum(0)) < 1e-12
+        core.use_tensor_cores = False
+        Y2 = torch.empty_like(X)
+        A.matmat_into(X, Y2)
+        core.use_tensor_cores = True
+        assert rel(Y, Y2) < 2e-6
+    # CG through the tensor-core matmat vs the CPU oracle
+    Fs = [pb.kron_factor(64, torch.float32, 50 + i) for i in range(2)]
+    B = pb.randn_np((4096, 32), torch.float32, 8)
+    K = cb.ops.Kronecker(*[cb.ops.Dense(F.to(DEV)) for F in Fs])
+    A = cb.PSD(K + 0.1 * cb.ops.I_like(K))
+    x, info = cb.linalg.CG(tol=1e-30, max_iters=30)(A, B.to(DEV))
+    Ao = ko.SumOp(ko.KroneckerOp(*[ko.DenseOp(F) for F in Fs]), ko.ScaledIdentityOp(0.1, 4096, torch.float32))
+    xo, _, _, info_o = ko.cg(Ao, B, tol=1e-30, max_iters=30)
+    A64 = ko.SumOp(ko.KroneckerOp(*[ko.DenseOp(F.double()) for F in Fs]), ko.ScaledIdentityOp(0.1, 4096, torch.float64))
+    _, _, _, info_64 = ko.cg(A64, B.double(), tol=1e-30, max_iters=30)
+    bad = np.nonzero(np.abs(info_o["errors"] - info_64["errors"]) > 0.25 * F32_TOL * info_64["errors"])[0]
+    window = int(bad[0]) if len(bad) else len(info_o["errors"])
+    assert window >= 5
+    np.testing.assert_allclose(info["errors"][:window], info_o["errors"][:window], rtol=F32_TOL)
+    assert info["iterations"] == info_o["iterations"] == 31
+    print(f"tensor-core CG: strict window {window} of {len(info_o['errors'])}")
+
+
 # ------------------------------------------------------------------------------------------- kernels directly
 def test_reorth_kernels_shapes(cb):
     """C = V^T W and W -= V C for ragged / wide / single-column probe blocks in both dtypes."""
