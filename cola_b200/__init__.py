@@ -9,8 +9,8 @@ Same names, arguments, return values and error behaviour as wilson-labs/cola for
 matmats).  All arithmetic runs in hand-written CUDA kernels loaded from cola_b200/csrc/libcola_b200.so through
 the C ABI in include/cola_b200.h; there is no CPU or eager-torch fallback.
 """
-from . import backend, linalg, ops, rng
+from . import backend, linalg, ops, rng, sharding
 from .ops import (PSD, Hermitian, LinearOperator, SelfAdjoint, Stiefel, Unitary, block_diag, kron, lazify)
 
-__all__ = ["backend", "linalg", "ops", "rng", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
+__all__ = ["backend", "linalg", "ops", "rng", "sharding", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
            "LinearOperator", "lazify", "kron", "block_diag"]

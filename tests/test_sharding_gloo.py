@@ -1,0 +1,72 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: column ranges, the single SLQ all-reduce and the
+per-block Hutchinson all-reduce.  The per-probe arithmetic is stubbed with the CPU oracle (the CUDA kernels cannot
+run here); what is under test is that the sharded estimate equals the unsharded one on identical probes."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cola_b200 as cb
+    from cola_b200.linalg import stochastic
+    from oracle import krylov_oracle as ko
+    from tests import problems as pb
+    cb.rng.PROBE_DEVICE = "cpu"
+    P = pb.problem("kron465_diag_f64")
+    Ao = pb.to_oracle(P["spec"])
+
+    class Stub:  # just enough of a LinearOperator for slq_fwd / Hutch host logic
+        shape, dtype, device = Ao.shape, Ao.dtype, torch.device("cpu")
+
+        def __matmul__(self, Z):
+            return ko.lanczos_unary_matmat(Ao, torch.log, Z, 20, 1e-12)[0]
+
+    stochastic.slq_per_probe = lambda A, f, Z, m, tol, pbar=False: ko.slq_per_probe(Ao, f, Z, m, tol)
+    key = cb.rng.PRNGKey(42)
+    num = max(int(1 / 0.2**2), 1)   # 24: same rounding as stochastic_lanczos_quad (slq.py:74)
+    val = stochastic.slq_fwd(Stub(), torch.log, num_samples=num, max_iters=20, tol=1e-12, pbar=False, key=key,
+                             probe_chunk_size=4, group=dist.group.WORLD)
+    ref = ko.slq(Ao, torch.log, max_iters=20, tol=1e-12, vtol=0.2, key=key)
+    dg, info = stochastic.hutchinson_diag_estimate(Stub(), 0, tol=2e-2, max_iters=2, key=key, group=dist.group.WORLD)
+    dref, iref = ko.hutchinson_diag(lambda Z: ko.lanczos_unary_matmat(Ao, torch.log, Z, 20, 1e-12)[0], Ao.shape[0],
+                                    Ao.dtype, tol=2e-2, max_iters=2, key=key)
+    lo, hi = cb.sharding.column_range(num, rank, world)
+    results[rank] = (float(val), float(ref), float((dg - dref).abs().max()), info["iterations"], iref["iterations"],
+                     lo, hi)
+    dist.destroy_process_group()
+
+
+def test_sharded_slq_and_hutch_match_unsharded():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(world, port, results), nprocs=world, join=True)
+    assert len(results) == world
+    spans = sorted((results[r][5], results[r][6]) for r in range(world))
+    assert spans[0][0] == 0 and spans[-1][1] == 24 and spans[0][1] == spans[1][0]
+    for r in range(world):
+        val, ref, derr, it, itref, _, _ = results[r]
+        assert abs(val - ref) <= 1e-10 * abs(ref)      # one all-reduce of (sum, count) == the mean over all probes
+        assert derr < 1e-10 and it == itref            # per-block all-reduce reproduces the global stopping rule
+    assert results[0][0] == results[1][0]
+
+
+def test_column_range_covers_everything():
+    from cola_b200.sharding import column_range
+    for total in (1, 7, 64, 100, 1024):
+        for world in (1, 2, 3, 8):
+            got = []
+            for r in range(world):
+                lo, hi = column_range(total, r, world)
+                got.extend(range(lo, hi))
+            assert got == list(range(total))
