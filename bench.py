@@ -142,11 +142,12 @@ def cg_kernel_breakdown(A, n, k, dev):
     out = {}
     out["csr_spmm+pAp"] = (time_kernel(lambda: A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)),
                            A.nnz * (s + 4) + 4 * (n + 1) + 2 * n * k * s)
-    out["cg_update_xr"] = (time_kernel(lambda: lib.call("cola_cg_update_xr_f32", be.ptr(x), be.ptr(r), be.ptr(p),
-                                                        be.ptr(ap), n, k, k, be.ptr(ctl), be.ptr(gamma), be.ptr(pap),
-                                                        be.ptr(gamma), be.stream_ptr())), 6 * n * k * s)
-    out["cg_update_p"] = (time_kernel(lambda: lib.call("cola_cg_update_p_f32", be.ptr(r), be.ptr(p), n, k, k,
-                                                       be.ptr(ctl), be.ptr(gamma), be.stream_ptr())), 3 * n * k * s)
+    out["cg_update_r"] = (time_kernel(lambda: lib.call("cola_cg_update_r_f32", be.ptr(r), be.ptr(ap), n, k, k,
+                                                       be.ptr(ctl), be.ptr(gamma), be.ptr(pap), be.ptr(gamma),
+                                                       be.stream_ptr())), 3 * n * k * s)
+    out["cg_update_xp"] = (time_kernel(lambda: lib.call("cola_cg_update_xp_f32", be.ptr(x), be.ptr(r), be.ptr(p), n, k,
+                                                        k, be.ptr(ctl), be.ptr(gamma), be.ptr(pap),
+                                                        be.stream_ptr())), 5 * n * k * s)
     return out
 
 

@@ -228,24 +228,81 @@ int diag_matmat(const T* X, int64_t ldx, T* Y, int64_t ldy, int64_t n, int64_t k
   return rc;
 }
 
-// ---- CG: X += alpha P; R -= alpha AP; gamma_next += <R,R>   (cg.py:141-150, 157-162) ---------------
+// ---- CG iteration minus the matmat, as two sweeps (10 vector passes per iteration with the matmat's 2,
+// instead of the 11 of the textbook split x/r-update + p-update: P is read once, by the sweep that needs the
+// old direction for BOTH x += alpha p and p = r + beta p).
+//   r-sweep : alpha = safe(gamma/pAp) (0 where ||r|| < 1e-40);  R -= alpha AP;  gamma[it+1] += <R,R>
+//   xp-sweep: beta = safe(gamma[it+1]/gamma[it]) (0 where converged);  X += alpha P;  P = R + beta P
+// (cg.py:141-170; alpha/beta/has_converged are recomputed per thread from the device-resident accumulators)
+template <typename T>
+__device__ __forceinline__ T cg_alpha(const double* gamma, const double* pAp, int64_t it, int64_t k_full, int64_t c) {
+  const T g = (T)gamma[it * k_full + c];
+  const T q = (T)pAp[it * k_full + c];
+  const bool conv = (T)sqrt(gamma[it * k_full + c]) < (T)1e-40;  // has_converged, cg.py:144
+  return conv ? (T)0 : safe_div<T>(g, q);
+}
+
 template <typename T, int VEC>
-struct CgXrOp {
+struct CgROp {
   static constexpr int NACC = 1;
-  struct Regs { Vec<T, VEC> x, r, p, ap; };
-  T* X; T* R; const T* P; const T* AP; int64_t ld; const cola_cg_ctl_t* ctl; const double* gamma; const double* pAp;
+  struct Regs { Vec<T, VEC> r, ap; };
+  T* R; const T* AP; int64_t ld; const cola_cg_ctl_t* ctl; const double* gamma; const double* pAp;
   double* gamma_w; int64_t k_full; int64_t colmask;
   T alpha[VEC];
   __device__ bool enabled() const { return ctl->done == 0; }
   __device__ void setup(int64_t c0) {
     const int64_t it = ctl->it;
 #pragma unroll
+    for (int v = 0; v < VEC; ++v) alpha[v] = cg_alpha<T>(gamma, pAp, it, k_full, (c0 + v) & colmask);
+  }
+  __device__ void load(int64_t row, int64_t c0, Regs& r) const {
+    const int64_t o = row * ld + c0;
+    r.r = ldg_stream<T, VEC>(R + o);
+    r.ap = ldg_stream<T, VEC>(AP + o);
+  }
+  __device__ void finish(int64_t row, int64_t c0, Regs& r, double (&acc)[1][VEC]) const {
+    Vec<T, VEC> rn;
+#pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      int64_t c = (c0 + v) & colmask;
-      T g = (T)gamma[it * k_full + c];
-      T q = (T)pAp[it * k_full + c];
-      bool conv = (T)sqrt(gamma[it * k_full + c]) < (T)1e-40;  // has_converged, cg.py:144
-      alpha[v] = conv ? (T)0 : safe_div<T>(g, q);
+      rn.v[v] = r.r.v[v] - alpha[v] * r.ap.v[v];
+      acc[0][v] += (double)rn.v[v] * (double)rn.v[v];
+    }
+    stg<T, VEC>(R + row * ld + c0, rn);
+  }
+  __device__ double* out(int) const { return gamma_w + ((int64_t)ctl->it + 1) * k_full; }
+};
+
+template <typename T>
+int cg_update_r(T* R, const T* AP, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl, const double* gamma,
+                const double* pAp, double* gamma_w, cudaStream_t st) {
+  COLA_REQUIRE(R && AP && ctl && gamma && pAp && gamma_w, "cg_update_r: null pointer");
+  Shape s = shape_of<T>(n, k, ld, R, AP);
+  int rc = COLA_OK;
+  COLA_DISPATCH_VEC(T, s.vec, (rc = launch_sweep<T, VEC>(s.n, s.k, s.colmask, st, [&](int64_t c) {
+    int64_t cc = c & s.colmask;
+    return CgROp<T, VEC>{R + c, AP + c, s.ld, ctl, gamma + cc, pAp + cc, gamma_w + cc, k, s.colmask, {}};
+  }, "cg_update_r")));
+  return rc;
+}
+
+template <typename T, int VEC>
+struct CgXpOp {
+  static constexpr int NACC = 0;
+  struct Regs { Vec<T, VEC> x, r, p; };
+  T* X; const T* R; T* P; int64_t ld; const cola_cg_ctl_t* ctl; const double* gamma; const double* pAp;
+  int64_t k_full; int64_t colmask;
+  T alpha[VEC], beta[VEC];
+  __device__ bool enabled() const { return ctl->done == 0; }
+  __device__ void setup(int64_t c0) {
+    const int64_t it = ctl->it;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const int64_t c = (c0 + v) & colmask;
+      alpha[v] = cg_alpha<T>(gamma, pAp, it, k_full, c);
+      const T g0 = (T)gamma[it * k_full + c];
+      const T g1 = (T)gamma[(it + 1) * k_full + c];
+      const bool conv = (T)sqrt(gamma[it * k_full + c]) < (T)1e-40;
+      beta[v] = conv ? (T)0 : safe_div<T>(g1, g0);
     }
   }
   __device__ void load(int64_t row, int64_t c0, Regs& r) const {
@@ -253,78 +310,31 @@ struct CgXrOp {
     r.x = ldg_stream<T, VEC>(X + o);
     r.r = ldg_stream<T, VEC>(R + o);
     r.p = ldg_stream<T, VEC>(P + o);
-    r.ap = ldg_stream<T, VEC>(AP + o);
   }
-  __device__ void finish(int64_t row, int64_t c0, Regs& r, double (&acc)[1][VEC]) const {
+  __device__ void finish(int64_t row, int64_t c0, Regs& r, double (&)[1][VEC]) const {
     const int64_t o = row * ld + c0;
-    Vec<T, VEC> xn, rn;
+    Vec<T, VEC> xn, pn;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       xn.v[v] = r.x.v[v] + alpha[v] * r.p.v[v];
-      rn.v[v] = r.r.v[v] - alpha[v] * r.ap.v[v];
-      acc[0][v] += (double)rn.v[v] * (double)rn.v[v];
+      pn.v[v] = r.r.v[v] + beta[v] * r.p.v[v];
     }
     stg_stream<T, VEC>(X + o, xn);
-    stg<T, VEC>(R + o, rn);  // R is re-read by the p-update right after: keep it cacheable
-  }
-  __device__ double* out(int) const { return gamma_w + ((int64_t)ctl->it + 1) * k_full; }
-};
-
-template <typename T>
-int cg_update_xr(T* X, T* R, const T* P, const T* AP, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
-                 const double* gamma, const double* pAp, double* gamma_w, cudaStream_t st) {
-  COLA_REQUIRE(X && R && P && AP && ctl && gamma && pAp && gamma_w, "cg_update_xr: null pointer");
-  Shape s = shape_of<T>(n, k, ld, X, R, P, AP);
-  int rc = COLA_OK;
-  COLA_DISPATCH_VEC(T, s.vec, (rc = launch_sweep<T, VEC>(s.n, s.k, s.colmask, st, [&](int64_t c) {
-    int64_t cc = c & s.colmask;
-    return CgXrOp<T, VEC>{X + c, R + c, P + c, AP + c, s.ld, ctl, gamma + cc, pAp + cc, gamma_w + cc, k, s.colmask, {}};
-  }, "cg_update_xr")));
-  return rc;
-}
-
-// ---- CG: P = R + beta P   (cg.py:151-153, 165-170) --------------------------------------------------
-template <typename T, int VEC>
-struct CgPOp {
-  static constexpr int NACC = 0;
-  struct Regs { Vec<T, VEC> r, p; };
-  const T* R; T* P; int64_t ld; const cola_cg_ctl_t* ctl; const double* gamma; int64_t k_full; int64_t colmask;
-  T beta[VEC];
-  __device__ bool enabled() const { return ctl->done == 0; }
-  __device__ void setup(int64_t c0) {
-    const int64_t it = ctl->it;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      int64_t c = (c0 + v) & colmask;
-      T g0 = (T)gamma[it * k_full + c];
-      T g1 = (T)gamma[(it + 1) * k_full + c];
-      bool conv = (T)sqrt(gamma[it * k_full + c]) < (T)1e-40;
-      beta[v] = conv ? (T)0 : safe_div<T>(g1, g0);
-    }
-  }
-  __device__ void load(int64_t row, int64_t c0, Regs& r) const {
-    const int64_t o = row * ld + c0;
-    r.r = ldg_stream<T, VEC>(R + o);
-    r.p = ldg_stream<T, VEC>(P + o);
-  }
-  __device__ void finish(int64_t row, int64_t c0, Regs& r, double (&)[1][VEC]) const {
-    Vec<T, VEC> pn;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) pn.v[v] = r.r.v[v] + beta[v] * r.p.v[v];
-    stg<T, VEC>(P + row * ld + c0, pn);
+    stg<T, VEC>(P + o, pn);   // P is gathered by the matmat right after: keep it cacheable
   }
   __device__ double* out(int) const { return nullptr; }
 };
 
 template <typename T>
-int cg_update_p(const T* R, T* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl, const double* gamma,
-                cudaStream_t st) {
-  COLA_REQUIRE(R && P && ctl && gamma, "cg_update_p: null pointer");
-  Shape s = shape_of<T>(n, k, ld, R, P);
+int cg_update_xp(T* X, const T* R, T* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
+                 const double* gamma, const double* pAp, cudaStream_t st) {
+  COLA_REQUIRE(X && R && P && ctl && gamma && pAp, "cg_update_xp: null pointer");
+  Shape s = shape_of<T>(n, k, ld, X, R, P);
   int rc = COLA_OK;
   COLA_DISPATCH_VEC(T, s.vec, (rc = launch_sweep<T, VEC>(s.n, s.k, s.colmask, st, [&](int64_t c) {
-    return CgPOp<T, VEC>{R + c, P + c, s.ld, ctl, gamma + (c & s.colmask), k, s.colmask, {}};
-  }, "cg_update_p")));
+    int64_t cc = c & s.colmask;
+    return CgXpOp<T, VEC>{X + c, R + c, P + c, s.ld, ctl, gamma + cc, pAp + cc, k, s.colmask, {}, {}};
+  }, "cg_update_xp")));
   return rc;
 }
 
@@ -504,14 +514,13 @@ int cola_device_info(int* sms, int* major, int* minor) {
                              const int32_t* gate, void* s) {                                                          \
     return diag_matmat<T>(X, ldx, Y, ldy, n, k, shift, diag, accumulate, dots, dots_row, gate, ST(s));                \
   }                                                                                                                   \
-  int cola_cg_update_xr_##SFX(T* X, T* R, const T* P, const T* AP, int64_t n, int64_t k, int64_t ld,                 \
-                              const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, double* gamma_w,      \
-                              void* s) {                                                                              \
-    return cg_update_xr<T>(X, R, P, AP, n, k, ld, ctl, gamma, pAp, gamma_w, ST(s));                                   \
+  int cola_cg_update_r_##SFX(T* R, const T* AP, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,          \
+                             const double* gamma, const double* pAp, double* gamma_w, void* s) {                      \
+    return cg_update_r<T>(R, AP, n, k, ld, ctl, gamma, pAp, gamma_w, ST(s));                                          \
   }                                                                                                                   \
-  int cola_cg_update_p_##SFX(const T* R, T* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,           \
-                             const double* gamma, void* s) {                                                          \
-    return cg_update_p<T>(R, P, n, k, ld, ctl, gamma, ST(s));                                                         \
+  int cola_cg_update_xp_##SFX(T* X, const T* R, T* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,    \
+                              const double* gamma, const double* pAp, void* s) {                                      \
+    return cg_update_xp<T>(X, R, P, n, k, ld, ctl, gamma, pAp, ST(s));                                                \
   }                                                                                                                   \
   int cola_cg_tol_##SFX(const double* gamma0, T tol, T* tol_eff, int64_t k, void* s) {                               \
     if (!gamma0 || !tol_eff) return fail(COLA_E_BADARG, "cg_tol: null pointer");                                      \

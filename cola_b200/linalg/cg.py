@@ -8,8 +8,8 @@ cola/utils/torch_tqdm.py:7-71.
 What is different underneath (see DESIGN.md "CG"):
   * one iteration = 3 kernels + a 1-block scalar kernel instead of ~87 eager ATen calls
       matmat(+shift/diag epilogue) with the p^T A p column dots fused      (cg.py:145, 157-158)
-      x += alpha p ; r -= alpha Ap ; gamma' = <r,r>                         (cg.py:147-150, 165-166)
-      p  = r + beta p                                                      (cg.py:151-153)
+      r -= alpha Ap ; gamma' = <r,r>                                        (cg.py:148-150, 165-166)
+      x += alpha p ; p = r + beta p   (p read once for both)                (cg.py:147, 151-153)
   * alpha, beta, the has_converged mask, the iteration counter and the stopping rule live in a
     device-resident control block; the host only polls it every `check_every` iterations, so the two
     device->host syncs per iteration of torch_tqdm.py:42,88 are gone;
@@ -108,9 +108,10 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
             break
         for _ in range(min(CHECK_EVERY, max_iters - it)):
             A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)
-            lib.call(f"cola_cg_update_xr_{sx}", be.ptr(x), be.ptr(r), be.ptr(p), be.ptr(ap), n, k, k, be.ptr(ctl),
-                     be.ptr(gamma), be.ptr(pap), be.ptr(gamma), st())
-            lib.call(f"cola_cg_update_p_{sx}", be.ptr(r), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma), st())
+            lib.call(f"cola_cg_update_r_{sx}", be.ptr(r), be.ptr(ap), n, k, k, be.ptr(ctl), be.ptr(gamma),
+                     be.ptr(pap), be.ptr(gamma), st())
+            lib.call(f"cola_cg_update_xp_{sx}", be.ptr(x), be.ptr(r), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma),
+                     be.ptr(pap), st())
             lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
     elapsed = time.time() - t0
 

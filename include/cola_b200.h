@@ -151,21 +151,20 @@ typedef struct {
   int32_t k;
 } cola_cg_ctl_t;
 
-/* One CG iteration minus the matmat, as two sweeps + one tiny scalar kernel:
- *   xr:      alpha = safe(gamma/pAp) (0 where ||r||<1e-40);  X += alpha P;  R -= alpha AP;  gamma[it+1] += <R,R>
- *   p :      beta  = safe(gamma[it+1]/gamma[it]) (0 where converged);  P = R + beta P
+/* One CG iteration minus the matmat, as two sweeps + one tiny scalar kernel (10 vector passes per iteration
+ * including the matmat's 2, instead of the 11 of the textbook x/r-update + p-update split):
+ *   r :      alpha = safe(gamma[it]/pAp[it]) (0 where ||r||<1e-40);  R -= alpha AP;  gamma[it+1] += <R,R>
+ *   xp:      beta  = safe(gamma[it+1]/gamma[it]) (0 where converged);  X += alpha P;  P = R + beta P
  *   advance: it += increment;  done = !(any(sqrt(gamma[it]) > tol_eff) && it < max_iters)
  * Each kernel reads ctl->it / ctl->done on the device and is a no-op once done. */
-int cola_cg_update_xr_f32(float* X, float* R, const float* P, const float* AP, int64_t n, int64_t k, int64_t ld,
-                          const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, double* gamma_w,
-                          void* stream);
-int cola_cg_update_xr_f64(double* X, double* R, const double* P, const double* AP, int64_t n, int64_t k, int64_t ld,
-                          const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, double* gamma_w,
-                          void* stream);
-int cola_cg_update_p_f32(const float* R, float* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
-                         const double* gamma, void* stream);
-int cola_cg_update_p_f64(const double* R, double* P, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
-                         const double* gamma, void* stream);
+int cola_cg_update_r_f32(float* R, const float* AP, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
+                         const double* gamma, const double* pAp, double* gamma_w, void* stream);
+int cola_cg_update_r_f64(double* R, const double* AP, int64_t n, int64_t k, int64_t ld, const cola_cg_ctl_t* ctl,
+                         const double* gamma, const double* pAp, double* gamma_w, void* stream);
+int cola_cg_update_xp_f32(float* X, const float* R, float* P, int64_t n, int64_t k, int64_t ld,
+                          const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, void* stream);
+int cola_cg_update_xp_f64(double* X, const double* R, double* P, int64_t n, int64_t k, int64_t ld,
+                          const cola_cg_ctl_t* ctl, const double* gamma, const double* pAp, void* stream);
 /* tol_eff[c] = tol*||r0[:,c]|| + tol in the path's dtype (cg.py:101). */
 int cola_cg_tol_f32(const double* gamma0, float tol, float* tol_eff, int64_t k, void* stream);
 int cola_cg_tol_f64(const double* gamma0, double tol, double* tol_eff, int64_t k, void* stream);

@@ -19,8 +19,8 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(cdll, name), f"{name} declared in include/cola_b200.h but not exported"
     L = be.lib()
     assert L.cdll.cola_version() >= 1
-    for family in ("csr_spmm", "mode_contract", "diag_matmat", "col_dots", "col_scale", "axpby", "cg_update_xr",
-                   "cg_update_p", "cg_tol", "cg_advance", "reorth_dots", "reorth_update", "lanczos_three_term",
+    for family in ("csr_spmm", "mode_contract", "diag_matmat", "col_dots", "col_scale", "axpby", "cg_update_r",
+                   "cg_update_xp", "cg_tol", "cg_advance", "reorth_dots", "reorth_update", "lanczos_three_term",
                    "mgs_link"):
         for sfx in ("f32", "f64"):
             assert f"cola_{family}_{sfx}" in decls
