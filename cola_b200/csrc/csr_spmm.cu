@@ -42,7 +42,11 @@ struct alignas(sizeof(T) == 4 ? 8 : 16) Nz {
 
 // OFF32: every X row offset fits 32 bits (n_cols * ldx < 2^32), the common case; otherwise offsets are
 // recomputed in 64 bits from the column index.
-template <typename T, int VEC, bool EPI, bool DOTS, bool OFF32>
+// NZL: threads that share one row AND one column chunk and split the row's non-zeros between them (their
+// partial sums are combined with warp shuffles).  NZL = 1 for wide RHS blocks (the row's k*sizeof(T) bytes already
+// fill a half warp); NZL = 8 for SpMV-like shapes (k <= 4), where a thread-per-row walk would expose one
+// memory round trip per non-zero.
+template <typename T, int VEC, bool EPI, bool DOTS, bool OFF32, int NZL>
 __global__ void __launch_bounds__(kCsrThreads, 4) csr_spmm_kernel(CsrArgs<T> a) {
   if (a.gate != nullptr && *a.gate != 0) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -50,12 +54,15 @@ __global__ void __launch_bounds__(kCsrThreads, 4) csr_spmm_kernel(CsrArgs<T> a) 
   Nz<T>* s_nz = reinterpret_cast<Nz<T>*>(smem_raw);
   int32_t* s_rp = reinterpret_cast<int32_t*>(s_nz + a.cap);
   const int tid = threadIdx.x;
-  const int g = tid / a.lanes, l = tid - g * a.lanes;
+  const int gw = a.lanes * NZL;                       // threads per row
+  const int g = tid / gw, rem = tid - g * gw;
+  const int z = rem / a.lanes, l = rem - z * a.lanes;  // non-zero lane, column lane
   const int c0 = l * VEC;
   const bool col_ok = (g < a.groups) && (c0 < a.k);
   const T* __restrict__ Xc = a.X + c0;
   T* __restrict__ Yc = a.Y + c0;
   const uint32_t ldx32 = (uint32_t)a.ldx;
+  const uint32_t gmask = NZL > 1 ? (gw >= 32 ? 0xffffffffu : (((1u << gw) - 1u) << ((tid & 31) & ~(gw - 1)))) : 0u;
 
   double dacc[VEC];
 #pragma unroll
@@ -97,21 +104,27 @@ __global__ void __launch_bounds__(kCsrThreads, 4) csr_spmm_kernel(CsrArgs<T> a) 
       for (int v = 0; v < VEC; ++v) acc[v] = (T)0;
       if (staged) {
 #pragma unroll 4
-        for (int32_t j = s; j < e; ++j) {
-          const Nz<T> z = s_nz[j];
-          const Vec<T, VEC> x = ldg<T, VEC>(OFF32 ? (Xc + z.off) : (Xc + (uint64_t)z.off * (uint64_t)a.ldx));
+        for (int32_t j = s + z; j < e; j += NZL) {
+          const Nz<T> nz = s_nz[j];
+          const Vec<T, VEC> x = ldg<T, VEC>(OFF32 ? (Xc + nz.off) : (Xc + (uint64_t)nz.off * (uint64_t)a.ldx));
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] += z.val * x.v[v];
+          for (int v = 0; v < VEC; ++v) acc[v] += nz.val * x.v[v];
         }
       } else {  // tile too heavy for the staging buffer: read the CSR arrays directly (rare, kept small)
 #pragma unroll 1
-        for (int32_t j = s; j < e; ++j) {
+        for (int32_t j = s + z; j < e; j += NZL) {
           const int64_t c = a.colidx[base + j];
           const T w = a.vals[base + j];
           Vec<T, VEC> x = ldg<T, VEC>(Xc + c * a.ldx);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) acc[v] += w * x.v[v];
         }
+      }
+      if constexpr (NZL > 1) {   // combine the non-zero lanes' partial sums (group-local shuffle mask)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          for (int o = a.lanes; o < gw; o <<= 1) acc[v] += __shfl_xor_sync(gmask, acc[v], o);
+        if (z != 0) continue;
       }
       Vec<T, VEC> y;
       if constexpr (EPI) {
@@ -146,7 +159,84 @@ __global__ void __launch_bounds__(kCsrThreads, 4) csr_spmm_kernel(CsrArgs<T> a) 
     double* red = reinterpret_cast<double*>(s_rp + a.rows_per_tile + 2);
     red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(red) + 7) & ~(uintptr_t)7);
     double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k_full : 0);
-    block_col_reduce<VEC>(red, dacc, col_ok, tid, g, l, a.lanes, a.groups, (int64_t)c0, a.k, -1, out);
+    // partials live in the z == 0 threads; reduce over (group, nz-lane) pairs as "rows" of width lanes
+    block_col_reduce<VEC>(red, dacc, col_ok && z == 0, tid, tid / a.lanes, l, a.lanes, kCsrThreads / a.lanes,
+                          (int64_t)c0, a.k, -1, out);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SpMV-like shapes (k <= 4: single-RHS CG, Lanczos with one start vector, cfg5): no shared-memory staging, no
+// block barriers.  SUB threads share a row: each reads a strided subset of the row's (colidx, val) pairs straight
+// from global memory (consecutive lanes -> consecutive non-zeros: coalesced), gathers X, and the partial sums are
+// combined with sub-warp shuffles.  With ~32 registers the SM holds 2048 threads = 256 independent rows in
+// flight, which is what hides the rowptr -> colidx -> X dependent-load chain.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int KMAX, int SUB, bool EPI, bool DOTS>
+__global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  const int tid = threadIdx.x;
+  const int sub = tid % SUB;
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + tid) / SUB;
+  const int64_t n_grp = (int64_t)gridDim.x * blockDim.x / SUB;
+  const uint32_t gmask = SUB >= 32 ? 0xffffffffu : (((1u << SUB) - 1u) << ((tid & 31) & ~(SUB - 1)));
+  const int k = (int)a.k;
+  double dacc[KMAX];
+#pragma unroll
+  for (int c = 0; c < KMAX; ++c) dacc[c] = 0.0;
+  for (int64_t row = grp; row < a.n_rows; row += n_grp) {
+    const int32_t s = a.rowptr[row], e = a.rowptr[row + 1];
+    T acc[KMAX];
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) acc[c] = (T)0;
+#pragma unroll 2
+    for (int32_t j = s + sub; j < e; j += SUB) {
+      const int64_t col = __ldcs(a.colidx + j);
+      const T w = __ldcs(a.vals + j);
+      const T* xr = a.X + col * a.ldx;
+#pragma unroll
+      for (int c = 0; c < KMAX; ++c)
+        if (c < k) acc[c] += w * xr[c];
+    }
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c)
+      for (int o = 1; o < SUB; o <<= 1) acc[c] += __shfl_xor_sync(gmask, acc[c], o);
+    if (sub == 0) {
+      const T d = (EPI && a.diag) ? a.diag[row] : (T)0;
+#pragma unroll
+      for (int c = 0; c < KMAX; ++c) {
+        if (c < k) {
+          T t = a.alpha * acc[c];
+          if constexpr (EPI) {
+            const T xo = a.X[row * a.ldx + c];
+            if (a.shift != (T)0) t += a.shift * xo;
+            if (a.diag) t += d * xo;
+            if (a.accumulate) t += a.Y[row * a.ldy + c];
+            if constexpr (DOTS) dacc[c] += (double)xo * (double)t;
+          } else if (a.accumulate) {
+            t += a.Y[row * a.ldy + c];
+          }
+          a.Y[row * a.ldy + c] = t;
+        }
+      }
+    }
+  }
+  if constexpr (DOTS) {
+    __shared__ double red[8][KMAX];
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+      double v = dacc[c];   // non-zero only in sub == 0 threads
+      v = warp_sum(v);
+      if (lane == 0) red[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < k) {
+      double v = 0.0;
+      for (int w = 0; w < 8; ++w) v += red[w][tid];
+      double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k_full : 0);
+      atomicAdd(out + tid, v);
+    }
   }
 }
 
@@ -176,11 +266,15 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     a.l2_prefetch = (!no_pf && a.row_bytes >= 32) ? 1 : 0;
     int64_t need = (a.k + vec - 1) / vec;
     a.lanes = (int)need;
-    a.groups = kCsrThreads / a.lanes;
+    // SpMV-like shapes: share a row between 8 (or 4 / 2) threads when the column lanes are a small power of two
+    int nzl = 1;
+    if (a.lanes <= 4 && (a.lanes & (a.lanes - 1)) == 0 && a.k == (int64_t)a.lanes * vec && nnz >= 2 * n_rows)
+      nzl = 8 / a.lanes >= 2 ? 8 / a.lanes : 1;
+    a.groups = kCsrThreads / (a.lanes * nzl);
     // tile size: ~6 rows per group in flight, but keep the staged nnz range near half the buffer
     double avg = n_rows > 0 ? (double)nnz / (double)n_rows : 1.0;
     if (avg < 1.0) avg = 1.0;
-    const int cap_max = 2048;   // staging buffer (8 or 16 B per non-zero) stays under the 48 KB default
+    const int cap_max = sizeof(T) == 4 ? 4096 : 3072;   // staging buffer: 32 KB (fp32) / 48 KB (fp64) of (offset, value)
     int rpg = (int)((cap_max / 2) / (avg * a.groups));
     if (rpg < 1) rpg = 1;
     if (rpg > 8) rpg = 8;
@@ -190,11 +284,33 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     size_t smem = (size_t)a.cap * sizeof(Nz<T>) + (size_t)(a.rows_per_tile + 4) * 4 + 8 +
                   (dots ? (size_t)kCsrThreads * vec * sizeof(double) : 0);
     int64_t n_tiles = (n_rows + a.rows_per_tile - 1) / a.rows_per_tile;
+    if (k <= 4) {   // SpMV-like: sub-warp-per-row kernel, no staging
+      a.k = k;
+      const double avg_nnz = n_rows > 0 ? (double)nnz / (double)n_rows : 1.0;
+      const int subw = avg_nnz >= 12 ? 8 : (avg_nnz >= 6 ? 4 : 2);
+      int64_t groups_needed = n_rows;
+      int64_t blocks = (groups_needed * subw + 255) / 256;
+      int64_t cap_blocks = (int64_t)sm_count() * 8;
+      if (blocks > cap_blocks) blocks = cap_blocks;
+#define COLA_SPMV_LAUNCH(SUBV)                                                                            \
+  do {                                                                                                    \
+    if (dots) csr_spmv_kernel<T, 4, SUBV, true, true><<<(unsigned)blocks, 256, 0, st>>>(a);               \
+    else if (epi) csr_spmv_kernel<T, 4, SUBV, true, false><<<(unsigned)blocks, 256, 0, st>>>(a);          \
+    else csr_spmv_kernel<T, 4, SUBV, false, false><<<(unsigned)blocks, 256, 0, st>>>(a);                  \
+  } while (0)
+      if (subw == 8) COLA_SPMV_LAUNCH(8); else if (subw == 4) COLA_SPMV_LAUNCH(4); else COLA_SPMV_LAUNCH(2);
+      rc = cuda_status("csr_spmv");
+      break;
+    }
     const bool off32 = (double)n_cols * (double)ldx < 4294967296.0;
 #define COLA_CSR_LAUNCH(EPIV, DOTSV, OFFV)                                                                    \
   do {                                                                                                        \
-    auto kern = csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV>;                                                \
+    auto kern = nzl == 8 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 8>                                      \
+              : nzl == 4 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 4>                                      \
+              : nzl == 2 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 2>                                      \
+                         : csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 1>;                                     \
     int per_sm = 0;                                                                                           \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCsrThreads, smem);                          \
     if (per_sm < 1) per_sm = 1;                                                                               \
     int64_t grid = (int64_t)sm_count() * per_sm; /* persistent: whole waves of resident CTAs */               \
