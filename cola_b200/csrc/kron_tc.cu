@@ -99,6 +99,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+template <int C>
+__device__ __forceinline__ void tmem_ld16_at(uint32_t taddr, uint32_t (&r)[32]) {   // columns C*16 .. C*16+15 of a 32-wide half row
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[C * 16 + 0]), "=r"(r[C * 16 + 1]), "=r"(r[C * 16 + 2]), "=r"(r[C * 16 + 3]), "=r"(r[C * 16 + 4]),
+        "=r"(r[C * 16 + 5]), "=r"(r[C * 16 + 6]), "=r"(r[C * 16 + 7]), "=r"(r[C * 16 + 8]), "=r"(r[C * 16 + 9]),
+        "=r"(r[C * 16 + 10]), "=r"(r[C * 16 + 11]), "=r"(r[C * 16 + 12]), "=r"(r[C * 16 + 13]), "=r"(r[C * 16 + 14]),
+        "=r"(r[C * 16 + 15])
+      : "r"(taddr + C * 16) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -330,6 +345,312 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
 }
 
+// =======================================================================================================
+// Fused persistent variant (2 <= D <= 3 factors): ONE launch per matmat.  One CTA per SM walks the phases
+// (chunk 0: mode 0, 1, .., D-1; chunk 1: ...) and meets the other CTAs at a device-wide barrier only where a
+// phase consumes what the previous one produced (mode i -> mode i+1 of the same chunk).  All D factors stay
+// resident in shared memory as hi/lo pairs; the TMA producer runs R tiles ahead in a ring of raw tiles, the split
+// warps turn one raw tile into the (single) hi/lo operand pair while the previous tile's accumulator drains
+// through 8 epilogue warps.  Compared with one launch per (chunk, mode) this removes 4*D-1 prologues (TMEM
+// allocation, barrier init, factor load + split) and keeps the TMA queue full across chunk boundaries.
+// =======================================================================================================
+constexpr int kFusedThreads = 512;          // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-11 split, 12-15 epilogue
+constexpr int kMaxFused = 3;
+constexpr int kRing = 4;                    // raw-tile ring depth: 128 KB of TMA loads in flight per SM
+constexpr int kSplitWarps = 8;
+struct FusedMaps {
+  CUtensorMap in[kMaxFused];    // source of mode i: X (3D over row length k) for i = 0, the dense chunk workspaces after
+  CUtensorMap fac[kMaxFused];
+};
+struct FusedArgs {
+  int D;
+  int cpc;                      // 32-column blocks per chunk: the intermediates hold 32*cpc columns per row
+  int64_t k, n_chunks;
+  float* ws0; float* ws1; float* Y; const float* X; const float* diag;
+  float alpha, shift; int accumulate;
+  double* dots; const int32_t* dots_row; const int32_t* gate;
+  unsigned int* sync_counter;   // zeroed by the host before the launch
+  int dbg;                      // bring-up knob (COLA_KRON_DBG): 1 skip split math, 2 skip MMAs, 4 skip stores, 8 skip grid barrier
+};
+// shared-memory map of the fused kernel (1024-byte aligned pieces)
+constexpr int kFOffFacHi = 0;                          // current mode's factor, hi | lo
+constexpr int kFOffFacLo = kFacBytes;
+constexpr int kFOffOpHi = 2 * kFacBytes;               // operand pair of the tile being multiplied
+constexpr int kFOffOpLo = kFOffOpHi + kTileBytes;
+constexpr int kFOffRaw = kFOffOpLo + kTileBytes;       // ring of raw tiles (a factor travels through it as a half-filled slot)
+constexpr int kFOffBars = kFOffRaw + kRing * kTileBytes;
+constexpr int kFusedSmem = kFOffBars + 256 + 1024;
+
+__device__ __forceinline__ void grid_arrive_and_wait(unsigned int* counter, unsigned int target) {
+  __threadfence();
+  atomicAdd(counter, 1u);
+  unsigned int v;
+  do {
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+  } while (v < target);
+}
+
+__device__ __forceinline__ void split_to(const unsigned char* raw, unsigned char* hi, unsigned char* lo, int bytes, int tid,
+                                         int nthreads) {
+  for (int o = tid * 16; o < bytes; o += nthreads * 16) {
+    const float4 v = *reinterpret_cast<const float4*>(raw + o);
+    float4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    *reinterpret_cast<float4*>(hi + o) = h;
+    *reinterpret_cast<float4*>(lo + o) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+    kron_fused_tc_kernel(const __grid_constant__ FusedMaps maps, FusedArgs a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int D = a.D;
+  const uint32_t bar_full0 = sbase + kFOffBars;            // [kRing] ring slot landed (tile or factor)
+  const uint32_t bar_rfree0 = bar_full0 + 8 * kRing;       // [kRing] ring slot consumed by the split warps (count 8)
+  const uint32_t bar_ready = bar_rfree0 + 8 * kRing;       // operand pair written (count 8)
+  const uint32_t bar_opfree = bar_ready + 8;               // MMAs reading the operand pair / factor retired
+  const uint32_t bar_tfull0 = bar_opfree + 8;              // [2] accumulator complete
+  const uint32_t bar_tempty0 = bar_tfull0 + 16;            // [2] accumulator drained (count 4)
+  const uint32_t bar_phase = bar_tempty0 + 16;             // epilogue warps finished a phase (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kFOffBars + 200);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRing; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_rfree0 + 8 * s, kSplitWarps); }
+    mbar_init(bar_ready, kSplitWarps);
+    mbar_init(bar_opfree, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull0 + 8 * s, 1); mbar_init(bar_tempty0 + 8 * s, 4); }
+    mbar_init(bar_phase, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int64_t n = 1;
+  for (int i = 0; i < D; ++i) n *= kD;
+  const int64_t n_pos_tiles = n / kD / 4;      // pre * L / 4 position tiles, the same for every mode (a power of two)
+  const int pos_sh = 6 * (D - 1) - 2;
+  const int64_t pos_mask = n_pos_tiles - 1;
+  const int64_t n_tiles = n_pos_tiles * a.cpc; // x column blocks of the chunk
+  const int n_phases = (int)a.n_chunks * D;
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0) {
+    // ===== TMA producer: per phase one factor slot, then the tiles =====
+    if (lane == 0) {
+      int rit = 0;   // ring items issued
+      unsigned int barriers_passed = 0;
+      for (int ph = 0; ph < n_phases; ++ph) {
+        const int chunk = ph / D, mode = ph - chunk * D;
+        const int lsh = 6 * (D - 1 - mode);           // L = 64^(D-1-mode): divisions become shifts
+        const int64_t lmask = ((int64_t)1 << lsh) - 1;
+        {  // the factor does not depend on other CTAs: request it before the phase barrier
+          const int s = rit % kRing;
+          mbar_wait(bar_rfree0 + 8 * s, ((rit / kRing) & 1) ^ 1);
+          mbar_expect_tx(bar_full0 + 8 * s, kFacBytes);
+          const uint32_t dst = sbase + kFOffRaw + s * kTileBytes;
+          tma_load_2d(dst, &maps.fac[mode], bar_full0 + 8 * s, 0, 0);
+          tma_load_2d(dst + kFacBytes / 2, &maps.fac[mode], bar_full0 + 8 * s, 32, 0);
+          ++rit;
+        }
+        if (ph > 0) mbar_wait(bar_phase, (ph - 1) & 1);   // every phase completion is consumed in order (parity tracking)
+        if (mode > 0) {
+          // this phase reads what every CTA wrote in the previous one: local epilogue done, then device-wide
+          ++barriers_passed;
+          if (!(a.dbg & 8)) grid_arrive_and_wait(a.sync_counter, barriers_passed * gridDim.x);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        const int in_base = (mode == 0) ? chunk * 32 * a.cpc : 0;
+        for (int64_t t = first; t < n_tiles; t += step, ++rit) {
+          const int64_t cc = t >> pos_sh, tp = t & pos_mask;   // column block inside the chunk, position tile
+          const int in_r0 = in_base + (int)cc * 32;
+          const int s = rit % kRing;
+          mbar_wait(bar_rfree0 + 8 * s, ((rit / kRing) & 1) ^ 1);
+          const int nat = (a.dbg & 16) ? 1 : 4;
+          mbar_expect_tx(bar_full0 + 8 * s, nat * kAtomBytes);
+          const uint32_t dst = sbase + kFOffRaw + s * kTileBytes;
+          for (int at = 0; at < nat; ++at) {
+            const int64_t flat = tp * 4 + at;
+            const int64_t p = flat >> lsh, l = flat & lmask;
+            tma_load_3d(dst + at * kAtomBytes, &maps.in[mode], bar_full0 + 8 * s, in_r0, (int)l, (int)(p * kD));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int it = 0;
+      // A': MN-major SW128_BASE32B: rows (j) of 128 B, K groups of 4 rows 512 B apart (SBO), 8 rows (1024 B) per
+      // MMA step, the four 32-position atoms 8 KB apart (LBO).  B': K-major SW128, two 32-float k-chunks of 8 KB,
+      // 32 B per K step inside a chunk, 8-row groups 1 KB apart.
+      const uint64_t ad_hi = make_desc(sbase + kFOffOpHi, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t ad_lo = make_desc(sbase + kFOffOpLo, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t bd_hi = make_desc(sbase + kFOffFacHi, 16, 1024, kLayoutSw128);
+      const uint64_t bd_lo = make_desc(sbase + kFOffFacLo, 16, 1024, kLayoutSw128);
+      for (int ph = 0; ph < n_phases; ++ph) {
+        for (int64_t t = first; t < n_tiles; t += step, ++it) {
+          const int acc = it & 1;
+          const uint32_t aph = (it >> 1) & 1;
+          mbar_wait(bar_tempty0 + 8 * acc, aph ^ 1);
+          mbar_wait(bar_ready, it & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * kD;
+          uint32_t accum = 0;
+          if (!(a.dbg & 2))
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {
+            // descriptors differ only in the 14-bit start-address field: one 64-bit add per MMA on the issuing thread
+            const uint64_t ad0 = (term == 0) ? ad_lo : ad_hi;
+            const uint64_t bd0 = (term == 1) ? bd_lo : bd_hi;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t ad = ad0 + (uint64_t)((kk * 1024) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)(((kk / 4) * (kFacBytes / 2) + (kk % 4) * 32) >> 4);
+              umma_tf32(d, ad, bd, kIdesc, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(bar_opfree);
+          umma_commit(bar_tfull0 + 8 * acc);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + kSplitWarps) {
+    // ===== operand split: ring slot -> hi / lo operand pair (or -> the factor pair at a phase start) =====
+    const int tid = threadIdx.x - 128;
+    constexpr int kSplitThreads = kSplitWarps * 32;
+    int it = 0, rit = 0;
+    for (int ph = 0; ph < n_phases; ++ph) {
+      {  // factor of this phase
+        const int s = rit % kRing;
+        mbar_wait(bar_full0 + 8 * s, (rit / kRing) & 1);
+        mbar_wait(bar_opfree, (it & 1) ^ 1);        // MMAs of the previous tile (previous phase) retired: factor may change
+        split_to(smem + kFOffRaw + s * kTileBytes, smem + kFOffFacHi, smem + kFOffFacLo, kFacBytes, tid, kSplitThreads);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_rfree0 + 8 * s);
+        ++rit;
+      }
+      for (int64_t t = first; t < n_tiles; t += step, ++it, ++rit) {
+        const int s = rit % kRing;
+        mbar_wait(bar_full0 + 8 * s, (rit / kRing) & 1);
+        mbar_wait(bar_opfree, (it & 1) ^ 1);          // MMAs of the previous tile no longer read the operand pair
+        if (!(a.dbg & 1))
+          split_to(smem + kFOffRaw + s * kTileBytes, smem + kFOffOpHi, smem + kFOffOpLo, kTileBytes, tid, kSplitThreads);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_rfree0 + 8 * s);   // ring slot may be refilled
+          mbar_arrive(bar_ready);            // operand pair (and, at a phase start, the factor pair) complete
+        }
+      }
+    }
+  } else if (warp >= 4 + kSplitWarps) {
+    // ===== epilogue: one warp per TMEM lane quadrant (= atom of the tile) =====
+    const int q = warp & 3;
+    int it = 0;
+    for (int ph = 0; ph < n_phases; ++ph) {
+      const int chunk = ph / D, mode = ph - chunk * D;
+      const bool last = (mode == D - 1);
+      const int64_t L = (int64_t)1 << (6 * (D - 1 - mode));
+      float* __restrict__ outp = last ? a.Y : ((mode & 1) ? a.ws1 : a.ws0);
+      const int64_t out_k = last ? a.k : 32 * a.cpc, out_base = last ? (int64_t)chunk * 32 * a.cpc : 0;
+      const float* __restrict__ xin = (last && (a.shift != 0.f || a.diag != nullptr || a.dots != nullptr)) ? a.X : nullptr;
+      const float* __restrict__ dg = last ? a.diag : nullptr;
+      const float alpha = last ? a.alpha : 1.f;
+      const int accumulate = last ? a.accumulate : 0;
+      const int64_t row_stride = L * out_k;
+      const int lsh = 6 * (D - 1 - mode);
+      const int64_t lmask = ((int64_t)1 << lsh) - 1;
+      double dacc = 0.0;
+      int64_t dacc_r0 = -1;
+      double* const dp = (last && a.dots != nullptr) ? a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k : 0) : nullptr;
+      for (int64_t t = first; t < n_tiles; t += step, ++it) {
+        const int acc = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        const int64_t cc = t >> pos_sh, tp = t & pos_mask;
+        const int64_t out_r0 = out_base + cc * 32;
+        const int64_t flat = tp * 4 + q;
+        const int64_t p = flat >> lsh, l = flat & lmask;
+        const int64_t base = (((p * kD) << lsh) + l) * out_k + out_r0 + lane;
+        if (dp != nullptr && out_r0 != dacc_r0) {   // column block changed: flush the per-thread partial (rare)
+          if (dacc_r0 >= 0) atomicAdd(dp + dacc_r0 + lane, dacc);
+          dacc = 0.0;
+          dacc_r0 = out_r0;
+        }
+        mbar_wait(bar_tfull0 + 8 * acc, aph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kD;
+        // two halves of 32 columns: the TMEM buffer goes back to the MMA warp as soon as the second half is in
+        // registers, before that half's global stores
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld16_at<0>(taddr + h * 32, v);
+          tmem_ld16_at<1>(taddr + h * 32, v);
+          tmem_ld_wait();
+          if (h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);
+          }
+          if (a.dbg & 4) continue;
+          const int64_t hbase = base + (int64_t)(h * 32) * row_stride;
+          if (!last || xin == nullptr) {
+            if (accumulate) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) outp[hbase + (int64_t)i * row_stride] += alpha * __uint_as_float(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) outp[hbase + (int64_t)i * row_stride] = alpha * __uint_as_float(v[i]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              float xv[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xv[i] = xin[hbase + (int64_t)(c * 16 + i) * row_stride];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int64_t o = hbase + (int64_t)(c * 16 + i) * row_stride;
+                float y = alpha * __uint_as_float(v[c * 16 + i]);
+                if (a.shift != 0.f) y += a.shift * xv[i];
+                if (dg != nullptr) y += dg[((p * kD + h * 32 + c * 16 + i) << lsh) + l] * xv[i];
+                dacc += (double)xv[i] * (double)y;
+                if (accumulate) y += outp[o];
+                outp[o] = y;
+              }
+            }
+          }
+        }
+      }
+      if (dp != nullptr && dacc_r0 >= 0) atomicAdd(dp + dacc_r0 + lane, dacc);
+      // make this warp's global stores visible device-wide (and to the TMA / async proxy) before the phase ends
+      __threadfence();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_phase);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -379,7 +700,8 @@ using namespace cola;
 extern "C" {
 
 int64_t cola_kron_tc_workspace_bytes(int64_t n, int64_t n_factors) {
-  return n_factors > 1 ? 2 * n * 32 * (int64_t)sizeof(float) : 0;
+  // two chunk-sized intermediates (up to 128 columns) + one cache line for the device-wide phase barrier
+  return n_factors > 1 ? 2 * n * 128 * (int64_t)sizeof(float) + 128 : 0;
 }
 
 int cola_kron_tc_supported(int64_t n_factors, const int64_t* dims, int64_t k) {
@@ -414,6 +736,47 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
   }
   float* ws0 = workspace;
   float* ws1 = workspace + n * 32;
+  static const bool no_fused = getenv("COLA_KRON_NO_FUSED") != nullptr;   // A/B knob
+  if (n_factors <= kMaxFused && !no_fused) {
+    // ---- one persistent launch for the whole matmat
+    FusedMaps maps;
+    FusedArgs fa;
+    // chunk width: whole RHS block up to 128 columns (fewest device-wide phases); COLA_KRON_CPC overrides (1, 2, 4)
+    static const int cpc_env = getenv("COLA_KRON_CPC") ? atoi(getenv("COLA_KRON_CPC")) : 0;
+    int cpc = cpc_env > 0 ? cpc_env : 4;
+    while (cpc > 1 && (k / 32) % cpc != 0) cpc >>= 1;
+    ws1 = workspace + n * 32 * cpc;
+    for (int64_t i = 0; i < n_factors; ++i) {
+      COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
+      int rc = make_map_fac(&maps.fac[i], factors[i], ldf[i]);
+      if (rc) return rc;
+      int64_t pre = 1, L = 1;
+      for (int64_t j = 0; j < i; ++j) pre *= kD;
+      for (int64_t j = i + 1; j < n_factors; ++j) L *= kD;
+      const float* src = (i == 0) ? X : (((i - 1) % 2 == 0) ? ws0 : ws1);
+      rc = make_map_in(&maps.in[i], src, pre, L, (i == 0) ? k : 32 * cpc);
+      if (rc) return rc;
+    }
+    fa.D = (int)n_factors;
+    fa.cpc = cpc;
+    fa.k = k; fa.n_chunks = k / (32 * cpc); fa.ws0 = ws0; fa.ws1 = ws1; fa.Y = Y; fa.X = X; fa.diag = diag; fa.alpha = alpha;
+    fa.shift = shift; fa.accumulate = accumulate; fa.dots = dots; fa.dots_row = dots_row; fa.gate = gate;
+    fa.sync_counter = reinterpret_cast<unsigned int*>(workspace + 2 * n * 128);
+    static const int fdbg = getenv("COLA_KRON_DBG") ? atoi(getenv("COLA_KRON_DBG")) : 0;
+    fa.dbg = fdbg;
+    const size_t smem = kFusedSmem;
+    static bool smem_set = false;
+    if (!smem_set) {
+      cudaFuncSetAttribute(kron_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      smem_set = true;
+    }
+    cudaMemsetAsync(fa.sync_counter, 0, sizeof(unsigned int), st);
+    const int64_t n_tiles = n / kD / 4 * cpc;
+    int64_t grid = sm_count();   // all CTAs must be co-resident for the device-wide barrier: 1 CTA per SM
+    if (grid > n_tiles) grid = n_tiles;
+    kron_fused_tc_kernel<<<(unsigned)grid, kFusedThreads, smem, st>>>(maps, fa);
+    return cuda_status("kron_fused_tc");
+  }
   CUtensorMap fac_maps[8];
   for (int64_t i = 0; i < n_factors; ++i) {
     COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
