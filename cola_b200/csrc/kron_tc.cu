@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -746,17 +747,31 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
     int cpc = cpc_env > 0 ? cpc_env : 4;
     while (cpc > 1 && (k / 32) % cpc != 0) cpc >>= 1;
     ws1 = workspace + n * 32 * cpc;
-    for (int64_t i = 0; i < n_factors; ++i) {
-      COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
-      int rc = make_map_fac(&maps.fac[i], factors[i], ldf[i]);
-      if (rc) return rc;
-      int64_t pre = 1, L = 1;
-      for (int64_t j = 0; j < i; ++j) pre *= kD;
-      for (int64_t j = i + 1; j < n_factors; ++j) L *= kD;
-      const float* src = (i == 0) ? X : (((i - 1) % 2 == 0) ? ws0 : ws1);
-      rc = make_map_in(&maps.in[i], src, pre, L, (i == 0) ? k : 32 * cpc);
-      if (rc) return rc;
+    // tensor maps depend only on (pointers, shapes): Krylov loops call with the same buffers every iteration, so the
+    // last set is cached (cuTensorMapEncodeTiled costs several microseconds each on the host)
+    struct MapKey { const void* x; const void* ws; const void* f[kMaxFused]; int64_t ldf[kMaxFused]; int64_t k, nf; int cpc; };
+    static thread_local MapKey cached_key = {};
+    static thread_local FusedMaps cached_maps;
+    static thread_local bool cached_valid = false;
+    MapKey key = {};
+    key.x = X; key.ws = workspace; key.k = k; key.nf = n_factors; key.cpc = cpc;
+    for (int64_t i = 0; i < n_factors; ++i) { key.f[i] = factors[i]; key.ldf[i] = ldf[i]; }
+    if (!(cached_valid && memcmp(&key, &cached_key, sizeof(MapKey)) == 0)) {
+      for (int64_t i = 0; i < n_factors; ++i) {
+        COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
+        int rc = make_map_fac(&cached_maps.fac[i], factors[i], ldf[i]);
+        if (rc) return rc;
+        int64_t pre = 1, L = 1;
+        for (int64_t j = 0; j < i; ++j) pre *= kD;
+        for (int64_t j = i + 1; j < n_factors; ++j) L *= kD;
+        const float* src = (i == 0) ? X : (((i - 1) % 2 == 0) ? ws0 : ws1);
+        rc = make_map_in(&cached_maps.in[i], src, pre, L, (i == 0) ? k : 32 * cpc);
+        if (rc) return rc;
+      }
+      cached_key = key;
+      cached_valid = true;
     }
+    maps = cached_maps;
     fa.D = (int)n_factors;
     fa.cpc = cpc;
     fa.k = k; fa.n_chunks = k / (32 * cpc); fa.ws0 = ws0; fa.ws1 = ws1; fa.Y = Y; fa.X = X; fa.diag = diag; fa.alpha = alpha;

@@ -29,6 +29,8 @@ from .algorithm_base import Algorithm
 
 _small_value = 1e-40
 CHECK_EVERY = 16  # iterations enqueued between polls of the device-side stop flag
+USE_CUDA_GRAPH = True  # replay batches of iterations as a CUDA graph once the loop is warm
+GRAPH_MAX_ELEMS = 64 * 1024 * 1024
 
 
 @dataclass
@@ -99,20 +101,40 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     it_ptr, done_ptr = ctl[0:1], ctl[1:2]
     lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 0, st())   # initial cond_fun
 
-    t0 = time.time()
-    it, done = 0, 0
-    while True:
-        c = ctl.cpu()
-        it, done = int(c[0]), int(c[1])
-        if done:
-            break
-        for _ in range(min(CHECK_EVERY, max_iters - it)):
+    def enqueue(n_iters):
+        for _ in range(n_iters):
             A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)
             lib.call(f"cola_cg_update_r_{sx}", be.ptr(r), be.ptr(ap), n, k, k, be.ptr(ctl), be.ptr(gamma),
                      be.ptr(pap), be.ptr(gamma), st())
             lib.call(f"cola_cg_update_xp_{sx}", be.ptr(x), be.ptr(r), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma),
                      be.ptr(pap), st())
             lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
+
+    # graphs pay off where the loop is launch-bound (vector blocks up to ~256 MB); larger problems spend
+    # milliseconds per kernel and the capture would cost more than it saves
+    graph_ok = USE_CUDA_GRAPH and n * k <= GRAPH_MAX_ELEMS and A.plan().graph_safe()
+    t0 = time.time()
+    it, done = 0, 0
+    graph, batches = None, 0
+    while True:
+        c = ctl.cpu()
+        it, done = int(c[0]), int(c[1])
+        if done:
+            break
+        remaining = max_iters - it
+        if graph_ok and graph is None and batches >= 1 and remaining >= 2 * CHECK_EVERY:
+            # Every kernel reads the iteration index and the stop flag from the device control block, so a batch of
+            # iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
+            # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue(CHECK_EVERY)
+            # capture does not execute: fall through to the replay below
+        if graph is not None:
+            graph.replay()
+        else:
+            enqueue(min(CHECK_EVERY, remaining))
+        batches += 1
     elapsed = time.time() - t0
 
     # ---- info dict exactly as while_loop_winfo builds it (torch_tqdm.py:35-62): the tracked error is sampled

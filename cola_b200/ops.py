@@ -654,6 +654,11 @@ class Plan:
         self.shift = 0.0
         self.diag = None
 
+    def graph_safe(self):
+        """True when every core launches only library kernels on the current stream (no opaque `_matmat`, which may
+        allocate or synchronise): the condition for capturing the apply in a CUDA graph."""
+        return all(not isinstance(c, _OpaqueCore) and len(ch) == 1 for _, ch in self.terms for c in ch)
+
     def describe(self):
         parts = [f"{s:g}*" + "@".join(type(c).__name__.strip("_") for c in ch) for s, ch in self.terms]
         if self.shift != 0.0:
