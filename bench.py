@@ -304,9 +304,10 @@ def run_reference(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": warm,
         "ms_per_step": loop_s / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2: CG on CSR 5-point Laplacian {g}x{g} grid (n={shape[0]}), {k} RHS, fp32; each step "
-                               f"= {per_step_iters} full-size CG iteration(s) on the host cores (bounded sample)",
-                   "iters_per_step": per_step_iters},
+        "config": {"workload": f"cfg2: CG on CSR 5-point Laplacian {g}x{g} grid (n={shape[0]}, nnz={int(data.numel())}, int32 "
+                               f"indices), {k} RHS per GPU, fp32, {ITERS} fixed iterations per solve (tol=1e-30)",
+                   "iters_per_step": per_step_iters, "rhs_per_gpu": k,
+                   "sample": f"each step = {per_step_iters} full-size CG iteration(s) of that solve on the host cores"},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{its} full-size CG iterations, loop {loop_s:.1f} s, wall {wall:.1f} s"},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

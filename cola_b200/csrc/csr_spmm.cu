@@ -189,14 +189,14 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
     T acc[KMAX];
 #pragma unroll
     for (int c = 0; c < KMAX; ++c) acc[c] = (T)0;
-#pragma unroll 2
+#pragma unroll 4
     for (int32_t j = s + sub; j < e; j += SUB) {
       const int64_t col = __ldcs(a.colidx + j);
       const T w = __ldcs(a.vals + j);
       const T* xr = a.X + col * a.ldx;
 #pragma unroll
       for (int c = 0; c < KMAX; ++c)
-        if (c < k) acc[c] += w * xr[c];
+        if (c < k) acc[c] += w * __ldg(xr + c);   // read-only path: 32-byte sector fills for the random gather
     }
 #pragma unroll
     for (int c = 0; c < KMAX; ++c)

@@ -63,8 +63,8 @@ def cfg4(probes=128, m=int(os.environ.get("LANCZOS_M", 100))):
     vtol = 1.0 / (probes ** 0.5)
     f = lambda: cb.linalg.stochastic_lanczos_quad(A, torch.log, max_iters=m, tol=1e-7, vtol=vtol * 0.9999, key=42,
                                                    probe_chunk_size=chunk, group=GROUP)
-    cb.linalg.stochastic_lanczos_quad(A, torch.log, max_iters=3, tol=1e-7, vtol=1.0 / (chunk ** 0.5) * 0.9999, key=1,
-                                      probe_chunk_size=chunk)   # warm-up: kernels loaded, allocator holds the basis block
+    cb.linalg.stochastic_lanczos_quad(A, torch.log, max_iters=m, tol=1e-7, vtol=1.0 / (chunk ** 0.5) * 0.9999, key=1,
+                                      probe_chunk_size=chunk)   # warm-up (one chunk): kernels loaded, allocator holds the basis block
     if GROUP is not None:
         dist.barrier()
     s, val = timed(f)
