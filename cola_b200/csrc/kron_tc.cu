@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // =======================================================================================================
 constexpr int kFusedThreads = 512;          // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4-11 split, 12-15 epilogue
 constexpr int kMaxFused = 3;
-constexpr int kRing = 4;                    // raw-tile ring depth: 128 KB of TMA loads in flight per SM
+constexpr int kRing = 2;                    // raw-tile ring depth (TMA runs two tiles ahead of the split warps)
 constexpr int kSplitWarps = 8;
 struct FusedMaps {
   CUtensorMap in[kMaxFused];    // source of mode i: X (3D over row length k) for i = 0, the dense chunk workspaces after
@@ -376,9 +376,8 @@ struct FusedArgs {
 // shared-memory map of the fused kernel (1024-byte aligned pieces)
 constexpr int kFOffFacHi = 0;                          // current mode's factor, hi | lo
 constexpr int kFOffFacLo = kFacBytes;
-constexpr int kFOffOpHi = 2 * kFacBytes;               // operand pair of the tile being multiplied
-constexpr int kFOffOpLo = kFOffOpHi + kTileBytes;
-constexpr int kFOffRaw = kFOffOpLo + kTileBytes;       // ring of raw tiles (a factor travels through it as a half-filled slot)
+constexpr int kFOffOp = 2 * kFacBytes;                 // two operand pairs [hi | lo]: tile t+1 is split while tile t is multiplied
+constexpr int kFOffRaw = kFOffOp + 4 * kTileBytes;     // ring of raw tiles (a factor travels through it as a half-filled slot)
 constexpr int kFOffBars = kFOffRaw + kRing * kTileBytes;
 constexpr int kFusedSmem = kFOffBars + 256 + 1024;
 
@@ -412,9 +411,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
   const int D = a.D;
   const uint32_t bar_full0 = sbase + kFOffBars;            // [kRing] ring slot landed (tile or factor)
   const uint32_t bar_rfree0 = bar_full0 + 8 * kRing;       // [kRing] ring slot consumed by the split warps (count 8)
-  const uint32_t bar_ready = bar_rfree0 + 8 * kRing;       // operand pair written (count 8)
-  const uint32_t bar_opfree = bar_ready + 8;               // MMAs reading the operand pair / factor retired
-  const uint32_t bar_tfull0 = bar_opfree + 8;              // [2] accumulator complete
+  const uint32_t bar_ready0 = bar_rfree0 + 8 * kRing;      // [2] operand pair written (count 8)
+  const uint32_t bar_opfree0 = bar_ready0 + 16;            // [2] MMAs reading the operand pair retired
+  const uint32_t bar_tfull0 = bar_opfree0 + 16;            // [2] accumulator complete
   const uint32_t bar_tempty0 = bar_tfull0 + 16;            // [2] accumulator drained (count 4)
   const uint32_t bar_phase = bar_tempty0 + 16;             // epilogue warps finished a phase (count 4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kFOffBars + 200);
@@ -422,9 +421,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kRing; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_rfree0 + 8 * s, kSplitWarps); }
-    mbar_init(bar_ready, kSplitWarps);
-    mbar_init(bar_opfree, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull0 + 8 * s, 1); mbar_init(bar_tempty0 + 8 * s, 4); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_ready0 + 8 * s, kSplitWarps);
+      mbar_init(bar_opfree0 + 8 * s, 1);
+      mbar_init(bar_tfull0 + 8 * s, 1);
+      mbar_init(bar_tempty0 + 8 * s, 4);
+    }
     mbar_init(bar_phase, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -495,8 +497,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
       // A': MN-major SW128_BASE32B: rows (j) of 128 B, K groups of 4 rows 512 B apart (SBO), 8 rows (1024 B) per
       // MMA step, the four 32-position atoms 8 KB apart (LBO).  B': K-major SW128, two 32-float k-chunks of 8 KB,
       // 32 B per K step inside a chunk, 8-row groups 1 KB apart.
-      const uint64_t ad_hi = make_desc(sbase + kFOffOpHi, kAtomBytes, 512, kLayoutSw128Base32);
-      const uint64_t ad_lo = make_desc(sbase + kFOffOpLo, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t ad_hi0 = make_desc(sbase + kFOffOp, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t ad_lo0 = make_desc(sbase + kFOffOp + kTileBytes, kAtomBytes, 512, kLayoutSw128Base32);
       const uint64_t bd_hi = make_desc(sbase + kFOffFacHi, 16, 1024, kLayoutSw128);
       const uint64_t bd_lo = make_desc(sbase + kFOffFacLo, 16, 1024, kLayoutSw128);
       for (int ph = 0; ph < n_phases; ++ph) {
@@ -504,9 +506,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
           const int acc = it & 1;
           const uint32_t aph = (it >> 1) & 1;
           mbar_wait(bar_tempty0 + 8 * acc, aph ^ 1);
-          mbar_wait(bar_ready, it & 1);
+          mbar_wait(bar_ready0 + 8 * acc, aph);
           tc_fence_after();
           const uint32_t d = tmem_base + acc * kD;
+          const uint64_t opoff = (uint64_t)((acc * 2 * kTileBytes) >> 4);   // operand pair of this tile
+          const uint64_t ad_hi = ad_hi0 + opoff, ad_lo = ad_lo0 + opoff;
           uint32_t accum = 0;
           if (!(a.dbg & 2))
 #pragma unroll
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
               accum = 1;
             }
           }
-          umma_commit(bar_opfree);
+          umma_commit(bar_opfree0 + 8 * acc);
           umma_commit(bar_tfull0 + 8 * acc);
         }
       }
@@ -536,7 +540,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
       {  // factor of this phase
         const int s = rit % kRing;
         mbar_wait(bar_full0 + 8 * s, (rit / kRing) & 1);
-        mbar_wait(bar_opfree, (it & 1) ^ 1);        // MMAs of the previous tile (previous phase) retired: factor may change
+        // every MMA of the previous phase must have retired before the factor changes: the last two tiles
+        if (it >= 1) mbar_wait(bar_opfree0 + 8 * ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        if (it >= 2) mbar_wait(bar_opfree0 + 8 * ((it - 2) & 1), ((it - 2) >> 1) & 1);
         split_to(smem + kFOffRaw + s * kTileBytes, smem + kFOffFacHi, smem + kFOffFacLo, kFacBytes, tid, kSplitThreads);
         fence_async_smem();
         __syncwarp();
@@ -545,15 +551,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
       }
       for (int64_t t = first; t < n_tiles; t += step, ++it, ++rit) {
         const int s = rit % kRing;
+        const int ob = it & 1;
         mbar_wait(bar_full0 + 8 * s, (rit / kRing) & 1);
-        mbar_wait(bar_opfree, (it & 1) ^ 1);          // MMAs of the previous tile no longer read the operand pair
-        if (!(a.dbg & 1))
-          split_to(smem + kFOffRaw + s * kTileBytes, smem + kFOffOpHi, smem + kFOffOpLo, kTileBytes, tid, kSplitThreads);
+        mbar_wait(bar_opfree0 + 8 * ob, ((it >> 1) & 1) ^ 1);   // MMAs of tile it-2 no longer read this operand pair
+        unsigned char* op = smem + kFOffOp + ob * 2 * kTileBytes;
+        if (!(a.dbg & 1)) split_to(smem + kFOffRaw + s * kTileBytes, op, op + kTileBytes, kTileBytes, tid, kSplitThreads);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar_rfree0 + 8 * s);   // ring slot may be refilled
-          mbar_arrive(bar_ready);            // operand pair (and, at a phase start, the factor pair) complete
+          mbar_arrive(bar_rfree0 + 8 * s);        // ring slot may be refilled
+          mbar_arrive(bar_ready0 + 8 * ob);       // operand pair (and, at a phase start, the factor pair) complete
         }
       }
     }
