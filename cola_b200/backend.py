@@ -186,6 +186,26 @@ def reorth_update(V, j0, j1, W, C, sign=-1.0, wnorm2=None, gate=None):
                ptr(C, torch.float64), scalar(W.dtype, sign), ptr(wnorm2), ptr(gate), stream_ptr())
 
 
+FUSED_REORTH = os.environ.get("COLA_NO_FUSED_REORTH", "") == ""
+
+
+def reorth_update_dots(V, j0, j1, W, C1, C2, sign=-1.0, gate=None):
+    """W += sign * V C1 and C2 += V^T W_new with one sweep over the basis.  Returns False (nothing launched) when
+    the shape is outside the fused kernel's envelope; the caller then runs reorth_update + reorth_dots."""
+    if not FUSED_REORTH:
+        return False
+    n, b = W.shape
+    rc = getattr(lib().cdll, f"cola_reorth_update_dots_{sfx(W.dtype)}")(
+        ptr(V, W.dtype), n * b, j0, j1, ptr(W), n, b, ptr(C1, torch.float64), scalar(W.dtype, sign),
+        ptr(C2, torch.float64), ptr(gate), stream_ptr())
+    if rc == -2:   # COLA_E_UNSUPPORTED
+        return False
+    if rc != 0:
+        msg = lib().cdll.cola_last_error()
+        raise RuntimeError(f"cola_reorth_update_dots failed with status {rc}: {msg.decode() if msg else ''}")
+    return True
+
+
 def lanczos_three_term(W, Vi, Vim1, alpha_acc, beta_prev_sq, gate=None):
     n, b = W.shape
     lib().call(f"cola_lanczos_three_term_{sfx(W.dtype)}", ptr(W), ptr(Vi, W.dtype),

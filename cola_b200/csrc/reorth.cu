@@ -11,6 +11,8 @@
 //   reorth_update  one thread owns (row, VEC columns), loops over j with coefficients in shared memory,
 //                  fuses ||w||^2 (the Lanczos beta, lanczos.py:252) into the same pass.
 // Algorithmic bytes per call: (j1-j0) * n*b*s  (+ n*b*s for W, twice for update).
+#include <cuda.h>
+#include <cstdlib>
 #include "sweep.cuh"
 
 namespace cola {
@@ -146,6 +148,290 @@ __global__ void __launch_bounds__(kUpdThreads) reorth_update_kernel(RoArgs<T> a,
   if (a.wnorm2) block_col_reduce<VEC>(red, nacc, active, tid, r, l, lanes, rows_per_pass, c0, b, -1, a.wnorm2);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fused CGS2 middle step:  W -= V C1   and   C2 = V^T W_new   with V read ONCE.
+// do_double_gram (lanczos.py:287-296) is dots -> update -> dots -> update: four sweeps over the basis.  The
+// update of pass 1 and the dots of pass 2 touch the same rows, so a CTA keeps a row-chunk of ALL basis vectors in
+// shared memory (R rows x nj vectors), finishes W for those rows, and immediately takes the pass-2 partial dots
+// from the resident chunk: 3 sweeps instead of 4 (the algorithmic-byte model of SURVEY 8d counts 4).
+//   thread (r, l) owns VEC columns of row r for the update; for the dots each warp owns the vectors
+//   j = warp (mod 8) and keeps their partials in registers for the whole kernel (fp32 per lane over <= a few
+//   thousand rows, combined in fp64: they are the O(eps) second-pass corrections).
+// colmask = 0 folds an (n,1) vector viewed as (n/VEC, VEC) onto column 0.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kFuMaxThreads = 480;   // consumer threads (15 warps) + one producer warp = 512
+constexpr int kFuBoxH = 8;          // basis vectors per TMA box
+
+__device__ __forceinline__ uint32_t fu_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fu_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// One elected thread fills a ring slot: the chunk [row0, row0+R) of every basis vector comes in as 2-D TMA boxes
+// (R*b contiguous elements x 16 vectors; 16-byte cp.async tops out near 3.5 TB/s on this part, ~40 clk per warp
+// instruction), the chunk of W as one bulk copy.  Rows past the end of a vector and vectors past nj are
+// zero-filled by the TMA unit and still count towards the expected bytes.
+template <typename T>
+__device__ __forceinline__ void fused_fill(const CUtensorMap* vmap, const RoArgs<T>& a, uint32_t stage, uint32_t bar, int R,
+                                           int nj_pad, int64_t row0, int lane, int inner) {
+  // called by the whole producer warp: lane 0 arms the barrier, lane i issues box i, lane 31 the W copy.
+  // inner == 0: 2-D map, a box is (R*b contiguous elements) x kFuBoxH vectors.  inner > 0: every vector is viewed
+  // as rows of `inner` elements and a box is inner x (R*b/inner) x kFuBoxH (chunks wider than the 256-element box limit).
+  const int64_t b = a.b;
+  const int rows = (int)min((int64_t)R, a.n - row0);
+  const uint32_t box_bytes = (uint32_t)(kFuBoxH * R * b * sizeof(T));
+  const uint32_t w_bytes = (uint32_t)(rows * b * sizeof(T));
+  if (lane == 0)
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                 "r"((uint32_t)(nj_pad / kFuBoxH) * box_bytes + w_bytes) : "memory");
+  __syncwarp();
+  const int jb = lane * kFuBoxH;
+  if (jb < nj_pad) {
+    const uint32_t dst = stage + (uint32_t)((int64_t)jb * R * b * sizeof(T));
+    if (inner == 0) {
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+          ::"r"(dst), "l"(vmap), "r"(bar), "r"((int)(row0 * b)), "r"(jb) : "memory");
+    } else {
+      asm volatile(
+          "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+          ::"r"(dst), "l"(vmap), "r"(bar), "r"(0), "r"((int)(row0 * b / inner)), "r"(jb) : "memory");
+    }
+  }
+  if (lane == 31)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(stage + (uint32_t)((int64_t)nj_pad * R * b * sizeof(T))), "l"(a.W + row0 * b), "r"(w_bytes), "r"(bar) : "memory");
+}
+
+#define FU_CONSUMER_SYNC() asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory")
+
+template <typename T, int VEC, int RPT, int KJ>
+__global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
+    reorth_fused_kernel(const __grid_constant__ CUtensorMap vmap, RoArgs<T> a, int R, int S, int nj_pad,
+                        int64_t stage_elems, int lanes, int64_t colmask, int64_t b_out, int inner, int dbg) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  // no static shared memory in this kernel, so the dynamic window starts 1024-byte aligned (TMA needs 128);
+  // deriving every pointer directly from the array keeps the accesses in the shared address space (LDS/STS)
+  extern __shared__ __align__(1024) unsigned char fu_smem[];
+  const int64_t nj = a.j1 - a.j0, b = a.b;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nthr = (int)blockDim.x - 32;                       // consumer threads; the last warp is the producer
+  T* bufs = reinterpret_cast<T*>(fu_smem);                       // S x ([nj_pad][R][b] | W [R][b])  ring of chunks
+  T* coef = bufs + (int64_t)S * stage_elems;                   // [nj][b]  (sign * C1)
+  T* part = coef + nj * b;                                     // [G][R][b] partial sums of the update
+  uint64_t* bars = reinterpret_cast<uint64_t*>(part + (int64_t)kFuMaxThreads * (RPT + 1) * VEC);   // full[S] | empty[S]
+  const int64_t n_chunks = (a.n + R - 1) / R;
+  const uint32_t bars_u32 = fu_smem_u32(bars), bufs_u32 = fu_smem_u32(bufs);
+  if (tid == 0) {
+    for (int s2 = 0; s2 < S; ++s2) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fu_smem_u32(bars + s2)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fu_smem_u32(bars + S + s2)), "r"(nthr / 32));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tid < nthr) {
+    for (int64_t i = tid; i < nj * b; i += nthr) {
+      const int64_t j = i / b, c = i - j * b;
+      coef[i] = a.sign * (T)a.Cc[(a.j0 + j) * b_out + (c & colmask)];
+    }
+  }
+  __syncthreads();                                             // barriers initialised, coef staged
+
+  if (tid >= nthr) {
+    // ---- producer warp: keeps the ring full, waits only on "slot consumed" ----
+    int slot = 0;
+    uint32_t phase = 0;
+    int64_t it = 0;
+    for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x, ++it) {
+      if (it >= S) fu_mbar_wait(bars_u32 + 8 * (S + slot), phase ^ 1);
+      fused_fill<T>(&vmap, a, bufs_u32 + (uint32_t)(slot * stage_elems * sizeof(T)), bars_u32 + 8 * slot, R, nj_pad, ch * R,
+                    lane, inner);
+      if (++slot == S) { slot = 0; phase ^= 1; }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  // thread (g, rs, l): VEC columns (l) of RPT adjacent rows of the chunk, basis vectors j = g, g + G, ...  Its slice
+  // of those vectors is read from shared memory ONCE, into registers: first for the update partials, then -- once
+  // W_new is complete -- for the pass-2 dot partials of the same vectors.  The coefficients and the dot partials
+  // of a thread's vectors live in registers for the whole kernel.
+  const int RL = R * lanes;                                    // Vec slots of one vector's chunk
+  const int GS = RL / RPT, G = nthr / GS;
+  int Q = 1;
+  while (Q * Q < G) ++Q;                                       // ~sqrt(G) adders per output in the first level
+  if (Q * RL > nthr) Q = nthr / RL;
+  T* part2 = part + (int64_t)nthr * RPT * VEC;                 // [Q][R][b] first-level sums
+  const int g = tid / GS, t_in = tid - g * GS;
+  const int rs = t_in / lanes, l_up = t_in - rs * lanes;
+  const int r0 = rs * RPT;
+  const int c_up = l_up * VEC;
+  const int Rb = R * (int)b;
+  const int elem0 = r0 * (int)b + c_up;                        // offset of this thread's first row inside a chunk
+  const bool in_group = g < G;
+  const int out_r = tid / lanes, out_e = out_r * (int)b + (tid - out_r * lanes) * VEC;   // level-2 output slot
+  const int l1_q = tid / RL, l1_o = tid - l1_q * RL;                                     // level-1 adder slot
+  T acc[KJ][VEC];
+  Vec<T, VEC> cf[KJ];
+  int xoff[KJ];                                                // element offset of vector jj's slice; -1 = no vector
+#pragma unroll
+  for (int jj = 0; jj < KJ; ++jj) {
+    const int j = g + jj * G;
+    xoff[jj] = (in_group && j < nj && !(dbg & 8)) ? j * Rb + elem0 : -1;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      acc[jj][v] = (T)0;
+      cf[jj].v[v] = (in_group && j < nj) ? coef[(int64_t)j * b + c_up + v] : (T)0;
+    }
+  }
+  const int ws_off = nj_pad * Rb;
+
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const T* vs = bufs + slot * stage_elems;
+    T* ws = bufs + slot * stage_elems + ws_off;
+    const int64_t row0 = ch * R;
+    const int rows = (int)min((int64_t)R, a.n - row0);
+    fu_mbar_wait(bars_u32 + 8 * slot, phase);
+    // 2a. partial sums of  sum_j coef[j] * V[j]  (rows past the end of the vectors arrive zero-filled)
+    Vec<T, VEC> x[KJ][RPT];
+    Vec<T, VEC> p[RPT];
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) p[rr].v[v] = (T)0;
+#pragma unroll
+    for (int jj = 0; jj < KJ; ++jj) {
+#pragma unroll
+      for (int rr = 0; rr < RPT; ++rr) {
+        if (xoff[jj] >= 0) {
+          x[jj][rr] = *reinterpret_cast<const Vec<T, VEC>*>(vs + xoff[jj] + rr * (int)b);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) x[jj][rr].v[v] = (T)0;
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) p[rr].v[v] += cf[jj].v[v] * x[jj][rr].v[v];
+      }
+    }
+    if (in_group) {
+#pragma unroll
+      for (int rr = 0; rr < RPT; ++rr)
+        *reinterpret_cast<Vec<T, VEC>*>(part + ((int64_t)g * RL + (r0 + rr) * lanes + l_up) * VEC) = p[rr];
+    }
+    if (!(dbg & 32)) FU_CONSUMER_SYNC();
+    // 2b. W_new = W + sum of the G partials, in two levels so that no thread waits on a long chain of
+    //     shared-memory loads: Q threads per output each add ~G/Q partials, then one thread adds those Q.
+    if (tid < Q * RL && !(dbg & 1)) {
+      const int q = l1_q, o = l1_o;
+      Vec<T, VEC> s4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s4[u].v[v] = (T)0;
+      for (int i = q; i < G; i += 4 * Q) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int gg = i + u * Q;
+          if (gg < G) {
+            const Vec<T, VEC> pq = *reinterpret_cast<const Vec<T, VEC>*>(part + ((int64_t)gg * RL + o) * VEC);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) s4[u].v[v] += pq.v[v];
+          }
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s4[0].v[v] = (s4[0].v[v] + s4[1].v[v]) + (s4[2].v[v] + s4[3].v[v]);
+      *reinterpret_cast<Vec<T, VEC>*>(part2 + (int64_t)tid * VEC) = s4[0];
+    }
+    if (!(dbg & 32)) FU_CONSUMER_SYNC();
+    if (tid < RL) {
+      if (out_r < rows) {
+        const int e = out_e;
+        Vec<T, VEC> s4[4];
+        s4[0] = *reinterpret_cast<const Vec<T, VEC>*>(ws + e);
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) s4[u].v[v] = (T)0;
+        for (int i = 0; i < Q; i += 4) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (i + u < Q) {
+              const Vec<T, VEC> pq = *reinterpret_cast<const Vec<T, VEC>*>(part2 + ((int64_t)(i + u) * RL + tid) * VEC);
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) s4[u].v[v] += pq.v[v];
+            }
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s4[0].v[v] = (s4[0].v[v] + s4[1].v[v]) + (s4[2].v[v] + s4[3].v[v]);
+        *reinterpret_cast<Vec<T, VEC>*>(ws + e) = s4[0];
+        // order the generic write of ws before the TMA refill of this slot; issued before the global store so
+        // that the fence does not wait for the store's round trip
+        if (!(dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (!(dbg & 2)) stg<T, VEC>(a.W + row0 * b + e, s4[0]);
+      }
+    }
+    if (!(dbg & 32)) FU_CONSUMER_SYNC();
+    // 3. pass-2 partial dots of this thread's vectors against its slice of W_new
+    if (in_group && !(dbg & 4)) {
+#pragma unroll
+      for (int rr = 0; rr < RPT; ++rr) {
+        if (r0 + rr < rows) {
+          const Vec<T, VEC> w = *reinterpret_cast<const Vec<T, VEC>*>(ws + elem0 + rr * (int)b);
+#pragma unroll
+          for (int jj = 0; jj < KJ; ++jj)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[jj][v] += x[jj][rr].v[v] * w.v[v];
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_u32 + 8 * (S + slot)) : "memory");
+    if (++slot == S) { slot = 0; phase ^= 1; }
+  }
+  // flush: combine the row-slices (and every CTA) per (vector, column) in fp64; the ring is free by now
+  FU_CONSUMER_SYNC();
+  double* red = reinterpret_cast<double*>(bufs);               // [nj][b]
+  for (int64_t i = tid; i < nj * b; i += nthr) red[i] = 0.0;
+  FU_CONSUMER_SYNC();
+  if (in_group) {
+#pragma unroll
+    for (int jj = 0; jj < KJ; ++jj) {
+      const int j = g + jj * G;
+      if (j < nj) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) atomicAdd(red + (int64_t)j * b + c_up + v, (double)acc[jj][v]);
+      }
+    }
+  }
+  FU_CONSUMER_SYNC();
+  for (int64_t i = tid; i < nj * b; i += nthr) {
+    const int64_t j = i / b, c = i - j * b;
+    const double sres = red[i];
+    if (sres != 0.0) atomicAdd(a.C + (a.j0 + j) * b_out + (c & colmask), sres);
+  }
+}
+
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encode_fn() {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) return (TmaEncodeFn)p;
+  return nullptr;
+}
+
 static inline int next_pow2(int64_t x) {
   int p = 1;
   while (p < x) p <<= 1;
@@ -265,6 +551,112 @@ int reorth_update(const T* V, int64_t vstride, int64_t j0, int64_t j1, T* W, int
   return rc;
 }
 
+template <typename T>
+int reorth_update_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, T* W, int64_t n, int64_t b,
+                       const double* C1, T sign, double* C2, const int32_t* gate, cudaStream_t st) {
+  COLA_REQUIRE(V && W && C1 && C2, "reorth_update_dots: null pointer");
+  COLA_REQUIRE(j1 > j0 && j0 >= 0, "reorth_update_dots: bad vector range");
+  const int64_t nj = j1 - j0;
+  constexpr int VEC = 16 / (int)sizeof(T);
+  // folded view for a single vector
+  int64_t nn = n, bb = b, colmask = -1, b_out = b;
+  if (b == 1 && n % VEC == 0) { nn = n / VEC; bb = VEC; colmask = 0; }
+  if (bb % VEC != 0 || ((uintptr_t)V % 16) || ((uintptr_t)W % 16) || (vstride % VEC))
+    return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: shape not supported by the fused kernel");
+  const int64_t vpr = bb / VEC;
+  if (vpr > kFuMaxThreads) return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: row wider than one CTA");
+  int dev = 0, smem_max = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem_max <= 0) smem_max = 48 * 1024;
+  const int lanes = (int)vpr;
+  const int nthr = kFuMaxThreads;
+  const int64_t nj_pad = (nj + kFuBoxH - 1) / kFuBoxH * kFuBoxH;
+  const int64_t row_bytes = (nj_pad + 1) * bb * (int64_t)sizeof(T);      // one row of every vector + W
+  const int64_t coef_bytes = nj * bb * (int64_t)sizeof(T);
+  auto stage_bytes = [&](int64_t r) { return (r * row_bytes + 127) / 128 * 128; };
+  // Configuration: RPT rows per thread (1 or 2), KJ vectors per thread (2, 4 or 8), R rows per chunk.  Every
+  // vector needs an owner (ceil(nj / G) <= KJ), the ring holds >= 3 chunks, and a chunk of one vector is either
+  // one TMA box row (R*b <= 256 elements) or a whole number of 256-element rows of the vector (3-D view).
+  // The per-chunk instruction cost is nearly fixed, so the tallest chunk wins; ties go to the smaller KJ.
+  int best_rpt = 0, best_kj = 0;
+  int64_t best_R = 0;
+  const bool can_3d = (nn * bb) % 256 == 0 && 256 % bb == 0 && (vstride % 256) == 0;
+  for (int rpt = 2; rpt >= 1; --rpt) {
+    for (int kj = 2; kj <= 8; kj *= 2) {
+      if (rpt == 2 && kj == 8) continue;                       // register budget
+      const int64_t part_bytes = (int64_t)kFuMaxThreads * (rpt + 1) * 16;
+      const int64_t budget = (int64_t)smem_max - 1024 - coef_bytes - part_bytes;
+      int64_t R = (int64_t)nthr * rpt / lanes;
+      if (R > 256) R = 256;
+      R -= R % rpt;
+      for (; R >= rpt; R -= rpt) {
+        const bool fits_2d = R * bb <= 256;
+        const bool fits_3d = can_3d && (R * bb) % 256 == 0 && R * bb / 256 <= 256;
+        if (!fits_2d && !fits_3d) continue;
+        const int64_t GS = R * lanes / rpt, G = nthr / GS;
+        if (G >= 1 && (nj + G - 1) / G <= kj && budget / stage_bytes(R) >= 3) break;
+      }
+      if (R >= rpt && (R > best_R || (R == best_R && kj < best_kj))) { best_R = R; best_rpt = rpt; best_kj = kj; }
+    }
+  }
+  if (best_R == 0) return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: basis chunk does not fit shared memory / registers");
+  const int64_t R = best_R;
+  const int64_t part_bytes = (int64_t)kFuMaxThreads * (best_rpt + 1) * 16;
+  int64_t S = ((int64_t)smem_max - 1024 - coef_bytes - part_bytes) / stage_bytes(R);
+  if (S > 8) S = 8;
+  if (const char* e = getenv("COLA_FU_S")) { const int64_t ss = atoi(e); if (ss >= 1 && ss < S) S = ss; }
+  static TmaEncodeFn enc = tma_encode_fn();
+  if (!enc) return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: cuTensorMapEncodeTiled unavailable");
+  CUtensorMap vmap;
+  const int inner = R * bb <= 256 ? 0 : 256;
+  {
+    const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64;
+    CUresult r;
+    if (inner == 0) {
+      if (nn * bb >= ((int64_t)1 << 31)) return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: vector too long for one TMA coordinate");
+      cuuint64_t dims[2] = {(cuuint64_t)(nn * bb), (cuuint64_t)nj};
+      cuuint64_t strides[1] = {(cuuint64_t)(vstride * (int64_t)sizeof(T))};
+      cuuint32_t box[2] = {(cuuint32_t)(R * bb), (cuuint32_t)kFuBoxH};
+      cuuint32_t es[2] = {1, 1};
+      r = enc(&vmap, dt, 2, (void*)(V + j0 * vstride), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)(nn * bb / inner), (cuuint64_t)nj};
+      cuuint64_t strides[2] = {(cuuint64_t)(inner * (int64_t)sizeof(T)), (cuuint64_t)(vstride * (int64_t)sizeof(T))};
+      cuuint32_t box[3] = {(cuuint32_t)inner, (cuuint32_t)(R * bb / inner), (cuuint32_t)kFuBoxH};
+      cuuint32_t es[3] = {1, 1, 1};
+      r = enc(&vmap, dt, 3, (void*)(V + j0 * vstride), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: cuTensorMapEncodeTiled failed");
+  }
+  RoArgs<T> a{};
+  a.V = V; a.vstride = vstride; a.j0 = j0; a.j1 = j1; a.W = W; a.n = nn; a.b = bb; a.Cc = C1; a.C = C2; a.sign = sign;
+  a.gate = gate;
+  const int64_t stage_elems = stage_bytes(R) / (int64_t)sizeof(T);
+  const size_t smem = (size_t)(S * stage_bytes(R) + coef_bytes + part_bytes + 16 * 8);
+  const int64_t n_chunks = (nn + R - 1) / R;
+  int64_t grid = (int64_t)sm_count();
+  if (grid > n_chunks) grid = n_chunks;
+  int dbg = 0;
+  if (const char* e = getenv("COLA_FU_DBG")) dbg = atoi(e);
+#define COLA_FU_LAUNCH(RPT_, KJ_)                                                                              \
+  do {                                                                                                         \
+    auto kern = reorth_fused_kernel<T, VEC, RPT_, KJ_>;                                                        \
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
+    kern<<<(unsigned)grid, nthr + 32, smem, st>>>(vmap, a, (int)R, (int)S, (int)nj_pad, stage_elems, lanes,    \
+                                                  colmask, b_out, inner, dbg);                                          \
+  } while (0)
+  if (best_rpt == 2 && best_kj == 2) COLA_FU_LAUNCH(2, 2);
+  else if (best_rpt == 2) COLA_FU_LAUNCH(2, 4);
+  else if (best_kj == 2) COLA_FU_LAUNCH(1, 2);
+  else if (best_kj == 4) COLA_FU_LAUNCH(1, 4);
+  else COLA_FU_LAUNCH(1, 8);
+#undef COLA_FU_LAUNCH
+  return cuda_status("reorth_update_dots");
+}
+
 }  // namespace cola
 
 using namespace cola;
@@ -279,6 +671,14 @@ extern "C" {
     return reorth_update<T>(V, vstride, j0, j1, W, n, b, C, sign, wnorm2, gate,                                      \
                             reinterpret_cast<cudaStream_t>(stream));                                                 \
   }
+int cola_reorth_update_dots_f32(const float* V, int64_t vstride, int64_t j0, int64_t j1, float* W, int64_t n, int64_t b,
+                                const double* C1, float sign, double* C2, const int32_t* gate, void* stream) {
+  return reorth_update_dots<float>(V, vstride, j0, j1, W, n, b, C1, sign, C2, gate, reinterpret_cast<cudaStream_t>(stream));
+}
+int cola_reorth_update_dots_f64(const double* V, int64_t vstride, int64_t j0, int64_t j1, double* W, int64_t n, int64_t b,
+                                const double* C1, double sign, double* C2, const int32_t* gate, void* stream) {
+  return reorth_update_dots<double>(V, vstride, j0, j1, W, n, b, C1, sign, C2, gate, reinterpret_cast<cudaStream_t>(stream));
+}
 COLA_RO_API(f32, float)
 COLA_RO_API(f64, double)
 }

@@ -44,6 +44,7 @@ def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
     alpha_acc = torch.zeros((m, b), dtype=torch.float64, device=dev)      # diag   (<w, v_i>)
     sub_sq = torch.zeros((m + 1, b), dtype=torch.float64, device=dev)     # subdiag^2 (||w||^2)
     C = torch.zeros((m + 2, b), dtype=torch.float64, device=dev)
+    C2 = torch.zeros((m + 2, b), dtype=torch.float64, device=dev)
     nrm = torch.zeros(b, dtype=torch.float64, device=dev)
     # init_lanczos: V[1] = rhs / ||rhs||   (lanczos.py:281-283)
     be.col_dots(rhs, rhs, nrm)
@@ -74,10 +75,14 @@ def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
         w = V[i + 1]
         A.matmat_into(vi, w, dots=alpha_acc[i - 1])        # w = A v_i ; diag[i-1] = <w, v_i>
         be.lanczos_three_term(w, vi, V[i - 1] if i > 1 else None, alpha_acc[i - 1], sub_sq[i - 1] if i > 1 else None)
-        for rep in range(2):                               # do_double_gram (lanczos.py:287-296)
-            C[1:i + 1].zero_()
-            be.reorth_dots(V, 1, i + 1, w, C)
-            be.reorth_update(V, 1, i + 1, w, C, sign=-1.0, wnorm2=sub_sq[i] if rep == 1 else None)
+        # do_double_gram (lanczos.py:287-296): dots, update, dots, update -- the middle two share one sweep
+        C[1:i + 1].zero_()
+        C2[1:i + 1].zero_()
+        be.reorth_dots(V, 1, i + 1, w, C)
+        if not be.reorth_update_dots(V, 1, i + 1, w, C, C2, sign=-1.0):
+            be.reorth_update(V, 1, i + 1, w, C, sign=-1.0)
+            be.reorth_dots(V, 1, i + 1, w, C2)
+        be.reorth_update(V, 1, i + 1, w, C2, sign=-1.0, wnorm2=sub_sq[i])
         sub_host[i] = np.sqrt(sub_sq[i].cpu().numpy())     # poll: the stop rule needs subdiag[i]
         if i == 1:
             pass

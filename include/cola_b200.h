@@ -189,6 +189,18 @@ int cola_reorth_update_f32(const float* V, int64_t vstride, int64_t j0, int64_t 
 int cola_reorth_update_f64(const double* V, int64_t vstride, int64_t j0, int64_t j1, double* W, int64_t n, int64_t b,
                            const double* C, double sign, double* wnorm2, const int32_t* gate, void* stream);
 
+/* Fused middle step of CGS2 (lanczos.py:287-296): W += sign * V C1 and C2[j*b+c] += sum_i V[j][i,c] * W_new[i,c] with
+ * the basis read ONCE (a row-chunk of all vectors is kept in shared memory): 3 sweeps over V per Lanczos step
+ * instead of 4.  Returns COLA_E_UNSUPPORTED when the shape does not fit (b*sizeof(T) not a multiple of 16 bytes
+ * -- a single column is folded when n allows --, too many vectors for the per-thread register slices, or a chunk
+ * too large for shared memory); callers then use cola_reorth_update_* + cola_reorth_dots_*. */
+int cola_reorth_update_dots_f32(const float* V, int64_t vstride, int64_t j0, int64_t j1, float* W, int64_t n,
+                                int64_t b, const double* C1, float sign, double* C2, const int32_t* gate,
+                                void* stream);
+int cola_reorth_update_dots_f64(const double* V, int64_t vstride, int64_t j0, int64_t j1, double* W, int64_t n,
+                                int64_t b, const double* C1, double sign, double* C2, const int32_t* gate,
+                                void* stream);
+
 /* Lanczos three-term step after the matmat (lanczos.py:245-248), fused:
  *   W -= alpha[c] * Vi + beta_prev[c] * Vim1   with alpha[c] = (T)alpha_acc[c] (the <w,v_i> dots of the matmat),
  *   beta_prev[c] = (T)sqrt(beta_prev_sq[c]).  Vim1 / beta_prev_sq may be NULL (first step). */

@@ -35,6 +35,41 @@ def timed(fn, reps=1):
     return e0.elapsed_time(e1) / reps * 1e-3, out
 
 
+def cfg1():
+    """BASELINE config 1 (Dense 1024^2 SPD, 1 RHS, fp32) on the GPU path (the config itself is the CPU-runnable one)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tests import problems as pb
+    P = pb.problem("cfg1_dense1024")
+    A = pb.to_b200(P["spec"], str(dev), P["ann"])
+    b = P["B"].to(dev)
+    alg = cb.linalg.CG(tol=1e-6, max_iters=1000)
+    alg(A, b)
+    s, (x, info) = timed(lambda: alg(A, b), reps=5)
+    its = info["iterations"] - 1
+    print(json.dumps({"workload": "cfg1: CG, PSD(Dense 1024x1024), 1 RHS, fp32, tol 1e-6 (GPU path; CUDA-graph batches)",
+                      "iterations": its, "iters_per_s": its / s, "solve_ms": s * 1e3,
+                      "final_error": float(info["errors"][-1])}))
+
+
+def refcuda(iters=10):
+    """The reference ALGORITHM (oracle port: same eager torch ops, two host syncs per iteration) on CUDA tensors:
+    cuSPARSE SpMM + ~45 elementwise launches per iteration -- the 'reference on the same B200' bar of SURVEY 8d."""
+    from oracle import krylov_oracle as ko
+    from bench import laplacian_coo, rhs_block
+    data, rows, cols, shape = laplacian_coo(2048, torch.float32, "cpu")
+    A = ko.SparseOp(data, rows, cols, shape)
+    A.csr = A.csr.to(dev)
+    B = rhs_block(shape[0], 64, 0).to(dev)
+    ko.cg(A, B, tol=1e-30, max_iters=2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, _, its, info = ko.cg(A, B, tol=1e-30, max_iters=iters)
+    torch.cuda.synchronize()
+    s = time.perf_counter() - t0
+    print(json.dumps({"workload": "cfg2 with the reference's eager torch algorithm on CUDA tensors (oracle port, cuSPARSE SpMM)",
+                      "iters_per_s": its / s, "ms_per_iter": s / its * 1e3}))
+
+
 def cfg3(iters=100):
     Fs = [factor(64, i) for i in range(3)]
     K = cb.ops.Kronecker(*[cb.PSD(cb.ops.Dense(F)) for F in Fs])
@@ -118,7 +153,7 @@ if __name__ == "__main__":
     probes = int(sys.argv[sys.argv.index("--probes") + 1]) if "--probes" in sys.argv else 128
     log2n = int(sys.argv[sys.argv.index("--nodes") + 1]) if "--nodes" in sys.argv else 24
     for w in which:
-        {"cfg3": cfg3, "cfg4": lambda: cfg4(probes), "cfg5": lambda: cfg5(log2n)}[w]()
+        {"cfg1": cfg1, "cfg3": cfg3, "cfg4": lambda: cfg4(probes), "cfg5": lambda: cfg5(log2n), "cfgref": refcuda}[w]()
     if GROUP is not None:
         dist.barrier()
         dist.destroy_process_group()

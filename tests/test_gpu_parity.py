@@ -389,6 +389,50 @@ def test_reorth_kernels_shapes(cb):
             assert rel(nrm, (W2.double()**2).sum(0)) < 1e-12
 
 
+def test_reorth_fused_update_dots(cb):
+    """The one-sweep middle step of CGS2 (W -= V C1, C2 = V^T W_new) against the two separate kernels and an fp64
+    restatement: ragged row counts (partial last chunk), folded single column, tall 3-D TMA chunks, both dtypes,
+    every vector count from 1 up; shapes outside the fused envelope report 'not launched' (False)."""
+    be = cb.backend
+    launched = 0
+    for dt, t in [(torch.float32, 3e-6), (torch.float64, 1e-13)]:
+        for n, b, nv in [(4096, 64, 2), (4099, 64, 13), (5003, 64, 51), (2050, 64, 101), (3001, 128, 30), (9001, 8, 33),
+                         (1 << 15, 1, 65), (40000, 1, 9), (1022, 16, 120), (777, 3, 5), (2048, 256, 6)]:
+            torch.manual_seed(n + b + nv)
+            V = torch.randn(nv, n, b, dtype=dt, device=DEV) / n**0.5
+            W = torch.randn(n, b, dtype=dt, device=DEV)
+            C1 = torch.zeros(nv, b, dtype=torch.float64, device=DEV)
+            be.reorth_dots(V, 1, nv, W, C1)
+            W_f = W.clone()
+            C2_f = torch.zeros_like(C1)
+            ok = be.reorth_update_dots(V, 1, nv, W_f, C1, C2_f, sign=-1.0)
+            if not ok:
+                assert b == 3 or (b == 1 and n % (16 // W.element_size()) != 0), (dt, n, b, nv)
+                assert torch.equal(W_f, W) and float(C2_f.abs().sum()) == 0.0   # nothing was launched
+                continue
+            launched += 1
+            W_s = W.clone()
+            C2_s = torch.zeros_like(C1)
+            be.reorth_update(V, 1, nv, W_s, C1, sign=-1.0)
+            be.reorth_dots(V, 1, nv, W_s, C2_s)
+            refW = W.double() - torch.einsum("jnb,jb->nb", V[1:].double(), C1[1:].to(dt).double())
+            assert rel(W_f, refW) < 10 * t, (dt, n, b, nv)
+            assert rel(W_f, W_s) < 10 * t, (dt, n, b, nv)
+            # pass-2 coefficients are O(eps) cancellations: compare on the scale of the pass-1 coefficients
+            refC2 = torch.einsum("jnb,nb->jb", V[1:].double(), W_f.double())
+            scale = float(C1[1:].abs().max())
+            assert float((C2_f[1:] - refC2).abs().max()) < 20 * t * scale, (dt, n, b, nv)
+            assert float(C2_f[0].abs().sum()) == 0.0
+    assert launched >= 18
+    # the device-side gate skips the launch's work
+    gate = torch.ones(1, dtype=torch.int32, device=DEV)
+    V = torch.randn(5, 4096, 64, device=DEV); W = torch.randn(4096, 64, device=DEV)
+    C1 = torch.ones(5, 64, dtype=torch.float64, device=DEV); C2 = torch.zeros_like(C1)
+    W0 = W.clone()
+    assert be.reorth_update_dots(V, 1, 5, W, C1, C2, gate=gate)
+    assert torch.equal(W, W0) and float(C2.abs().sum()) == 0.0
+
+
 def test_vector_sweeps_fold_and_ragged(cb):
     be = cb.backend
     for dt in (torch.float32, torch.float64):
