@@ -8,9 +8,15 @@ Same names, arguments, return values and error behaviour as wilson-labs/cola for
 (CG / Lanczos / Arnoldi / SLQ-Hutchinson and the Dense, Sparse, Kronecker, BlockDiag, Diagonal, Sum, Product
 matmats).  All arithmetic runs in hand-written CUDA kernels loaded from cola_b200/csrc/libcola_b200.so through
 the C ABI in include/cola_b200.h; there is no CPU or eager-torch fallback.
+
+`cola_b200.install()` rebinds the reference's own loop functions and structured matmats to this engine for CUDA
+float32/float64 operators (cola_b200/plugin.py), which makes it a drop-in inside an existing wilson-labs/cola
+program.
 """
-from . import backend, linalg, ops, rng, sharding
+from . import backend, linalg, ops, plugin, rng, sharding
 from .ops import (PSD, Hermitian, LinearOperator, SelfAdjoint, Stiefel, Unitary, block_diag, kron, lazify)
 
-__all__ = ["backend", "linalg", "ops", "rng", "sharding", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
+from .plugin import from_cola, install, uninstall
+
+__all__ = ["backend", "linalg", "ops", "plugin", "rng", "sharding", "install", "uninstall", "from_cola", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
            "LinearOperator", "lazify", "kron", "block_diag"]

@@ -254,6 +254,22 @@ class Sparse(LinearOperator):
         self.nnz = int(self.data.numel())
         self.max_row_nnz = int(counts.max()) if counts.numel() > 0 else 0
 
+    @classmethod
+    def from_csr(cls, indptr, indices, data, shape):
+        """Wrap existing CSR arrays (e.g. those of the reference's `Sparse.A`, operators.py:71-75) without
+        re-sorting: the operator is exactly the one those arrays describe."""
+        self = cls.__new__(cls, data)
+        LinearOperator.__init__(self, dtype=data.dtype, shape=shape)
+        self.indptr = indptr.to(torch.int32).contiguous()
+        self.indices = indices.to(torch.int32).contiguous()
+        self.data = data.contiguous()
+        counts = (self.indptr[1:] - self.indptr[:-1]).to(torch.int64)
+        self.row_indices = torch.repeat_interleave(torch.arange(shape[0], device=data.device), counts)
+        self.col_indices = self.indices
+        self.nnz = int(self.data.numel())
+        self.max_row_nnz = int(counts.max()) if counts.numel() > 0 else 0
+        return self
+
     def _transpose(self):
         return Sparse(self.data, self.col_indices, self.row_indices, (self.shape[1], self.shape[0]))
 

@@ -1,0 +1,221 @@
+"""Drop-in hook for wilson-labs/cola.
+
+The reference resolves its Krylov loops by module attribute at call time (`cg.py:91`, `lanczos.py:221`,
+`arnoldi.py:199`, `slq.py:75`, `diagonal_estimation.py:57-58`) and applies operators through `_matmat`, so one
+`install()` is the whole integration: it rebinds
+
+    cola.linalg.inverse.cg.run_batched_cg                          (cg.py:94-119)
+    cola.linalg.decompositions.lanczos.lanczos_fact                (lanczos.py:235-272)
+    cola.linalg.decompositions.arnoldi.arnoldi_fact                (arnoldi.py:289-324)
+    cola.linalg.trace.diagonal_estimation.hutchinson_diag_estimate (diagonal_estimation.py:158-210)
+    cola.linalg.tbd.slq.slq_fwd                                    (slq.py:37-52)
+    Dense/Sparse/Kronecker/BlockDiag/Diagonal/Sum/Product/ScalarMul._matmat  (operators.py)
+
+to adapters that take the B200 path when the operator lives on a CUDA device in float32/float64 and its tree
+converts (`from_cola`), and call the saved reference function otherwise (CPU, complex, JAX/NumPy backends,
+non-identity preconditioners, off-diagonal Hutchinson, exotic operators).  The adapters translate between the
+reference's state layouts and this package's: the reference keeps the Krylov basis as (b, n, m+2) with the
+vector index fastest, the kernels as (m+2, n, b); what is handed back is a strided view with the reference's
+logical shape.  `uninstall()` restores everything.
+
+The reference is not importable on the GPU box, so the adapters are exercised on CPU in
+tests/test_plugin_reference.py with oracle-backed stand-ins for the CUDA loops (FORCE_FAST_PATH), while the CUDA
+loops themselves are checked against the oracle in tests/test_gpu_parity.py.
+"""
+import importlib
+
+import torch
+
+from . import ops as bops
+
+# cola_b200.linalg re-exports functions named cg / lanczos / arnoldi, which shadow the submodules as attributes
+b_cg = importlib.import_module(__package__ + ".linalg.cg")
+b_lanczos = importlib.import_module(__package__ + ".linalg.lanczos")
+b_arnoldi = importlib.import_module(__package__ + ".linalg.arnoldi")
+b_stoch = importlib.import_module(__package__ + ".linalg.stochastic")
+
+FORCE_FAST_PATH = False      # tests only: route CPU operators through the adapters as well
+_SAVED = {}
+_ANNOTATIONS = ("PSD", "SelfAdjoint", "Unitary", "Stiefel")
+
+
+class NotConvertible(Exception):
+    pass
+
+
+def _is_fast_dtype(dtype):
+    return dtype in (torch.float32, torch.float64)
+
+
+def _on_fast_device(A):
+    if FORCE_FAST_PATH:
+        return True
+    dev = getattr(A, "device", None)
+    try:
+        return dev is not None and torch.device(dev).type == "cuda"
+    except (TypeError, RuntimeError):
+        return False
+
+
+def from_cola(A, cola):
+    """Reference operator tree -> mirror classes, one to one (same constructor arguments); annotations are
+    carried over by name.  Leaves that are not on the hot path raise NotConvertible (the caller then stays on
+    the reference path), except plain `LinearOperator`s with a matmat closure, which are wrapped as opaque."""
+    cached = getattr(A, "_b200_mirror", None)
+    if cached is not None:
+        return cached
+    R = cola.ops
+    if not _is_fast_dtype(A.dtype):
+        raise NotConvertible(f"dtype {A.dtype}")
+    unary = getattr(getattr(cola.linalg, "unary", None), "unary", None)
+    if isinstance(A, R.Sparse):
+        csr = A.A
+        M = bops.Sparse.from_csr(csr.crow_indices(), csr.col_indices(), csr.values(), tuple(A.shape))
+    elif isinstance(A, R.Dense) and type(A).__name__.startswith(("Dense", "Triangular")):
+        M = bops.Dense(A.A)
+    elif isinstance(A, R.Identity):
+        M = bops.Identity(tuple(A.shape), A.dtype)
+        M.device = torch.device(A.device) if getattr(A, "device", None) is not None else M.device
+    elif isinstance(A, R.ScalarMul):
+        M = bops.ScalarMul(float(A.c), tuple(A.shape), A.dtype, getattr(A, "device", None))
+    elif isinstance(A, R.Diagonal):
+        M = bops.Diagonal(A.diag)
+    elif isinstance(A, R.Tridiagonal):
+        M = bops.Tridiagonal(A.alpha, A.beta, A.gamma)
+    elif isinstance(A, R.Kronecker):
+        M = bops.Kronecker(*[from_cola(m, cola) for m in A.Ms])
+    elif isinstance(A, R.BlockDiag):
+        M = bops.BlockDiag(*[from_cola(m, cola) for m in A.Ms], multiplicities=list(A.multiplicities))
+    elif isinstance(A, R.Sum):
+        M = bops.Sum(*[from_cola(m, cola) for m in A.Ms])
+    elif isinstance(A, R.Product):
+        M = bops.Product(*[from_cola(m, cola) for m in A.Ms])
+    elif isinstance(A, R.Transpose):
+        M = from_cola(A.A, cola).T
+    elif unary is not None and isinstance(A, unary.LanczosUnary):
+        M = b_stoch.LanczosUnary(from_cola(A.A, cola), A.f, **{k: v for k, v in getattr(A, "kwargs", {}).items()
+                                                                if k in ("max_iters", "tol", "pbar")})
+    else:
+        raise NotConvertible(type(A).__name__)
+    ref_names = {getattr(a, "__name__", str(a)) for a in getattr(A, "annotations", ())}
+    for name in _ANNOTATIONS:
+        if name in ref_names:
+            M.annotations = set(M.annotations) | {getattr(bops, name)}
+    try:
+        A._b200_mirror = M
+    except (AttributeError, TypeError):
+        pass
+    return M
+
+
+def _mirror_or_none(A, cola):
+    if not (_on_fast_device(A) and _is_fast_dtype(A.dtype)):
+        return None
+    try:
+        return from_cola(A, cola)
+    except NotConvertible:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------ adapters
+def _make_run_batched_cg(cola, ref):
+    def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar):
+        M = _mirror_or_none(A, cola) if isinstance(preconditioner, cola.ops.Identity) else None
+        if M is None:
+            return ref(A, b, x0, max_iters, tol, preconditioner, pbar)
+        return b_cg.run_batched_cg(M, b, x0, max_iters, tol, bops.I_like(M), pbar)
+    return run_batched_cg
+
+
+def _make_lanczos_fact(cola, ref):
+    def lanczos_fact(A, init_val, max_iters=100, tol=1e-7, pbar=False):
+        M = _mirror_or_none(A, cola)
+        if M is None:
+            return ref(A, init_val, max_iters, tol, pbar)
+        V0, diag0, _, _ = init_val                               # init_lanczos (lanczos.py:275-284): V0[..., 1] = rhs/|rhs|
+        rhs = V0[..., 1].T.contiguous()                          # (n, b)
+        st = b_lanczos.lanczos_fact(M, rhs, max_iters, tol, pbar)
+        dt = diag0.dtype
+        m = diag0.shape[-1]
+        V = st.V.permute(2, 1, 0)                                # (b, n, m+2) view of the (m+2, n, b) basis
+        diag = st.alpha_acc[:m].to(dt).T.contiguous()            # (b, m)
+        subdiag = torch.sqrt(st.sub_sq[:m + 1]).to(dt).T.contiguous()   # (b, m+1)
+        i = torch.tensor(st.i, dtype=torch.int32, device=V.device)
+        return V, diag, subdiag, i, st.info
+    return lanczos_fact
+
+
+def _make_arnoldi_fact(cola, ref):
+    def arnoldi_fact(A, init_val, max_iters, tol, pbar):
+        M = _mirror_or_none(A, cola)
+        if M is None:
+            return ref(A, init_val, max_iters, tol, pbar)
+        Q0 = init_val[0]                                         # init_arnoldi (arnoldi.py:327-335): Q0[..., 0] = rhs/|rhs|
+        rhs = Q0[..., 0].T.contiguous()
+        Q, H, idx, info = b_arnoldi.arnoldi_fact(M, rhs, max_iters, tol, pbar)
+        return Q.permute(2, 1, 0), H, torch.tensor(int(idx), dtype=torch.int32, device=H.device), info
+    return arnoldi_fact
+
+
+def _make_hutch(cola, ref):
+    def hutchinson_diag_estimate(A, k=0, bs=100, tol=3e-2, max_iters=10000, pbar=False, rand='normal', key=None):
+        M = _mirror_or_none(A, cola) if k == 0 else None
+        if M is None:
+            return ref(A, k, bs, tol, max_iters, pbar, rand, key)
+        return b_stoch.hutchinson_diag_estimate(M, k, bs, tol, max_iters, pbar, rand, key)
+    return hutchinson_diag_estimate
+
+
+def _make_slq_fwd(cola, ref):
+    def slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key):
+        M = _mirror_or_none(A, cola)
+        if M is None:
+            return ref(A, fun, num_samples, max_iters, tol, pbar, key)
+        return b_stoch.slq_fwd(M, fun, num_samples, max_iters, tol, pbar, key)
+    return slq_fwd
+
+
+def _make_matmat(cola, ref):
+    def _matmat(self, X):
+        if torch.is_tensor(X) and (X.is_cuda or FORCE_FAST_PATH) and _is_fast_dtype(X.dtype) and X.dtype == self.dtype:
+            M = _mirror_or_none(self, cola)
+            if M is not None:
+                return M._matmat(X.contiguous())
+        return ref(self, X)
+    return _matmat
+
+
+_LOOPS = (
+    ("cola.linalg.inverse.cg", "run_batched_cg", _make_run_batched_cg),
+    ("cola.linalg.decompositions.lanczos", "lanczos_fact", _make_lanczos_fact),
+    ("cola.linalg.decompositions.arnoldi", "arnoldi_fact", _make_arnoldi_fact),
+    ("cola.linalg.trace.diagonal_estimation", "hutchinson_diag_estimate", _make_hutch),
+    ("cola.linalg.tbd.slq", "slq_fwd", _make_slq_fwd),
+)
+_MATMAT_CLASSES = ("Dense", "Sparse", "Kronecker", "BlockDiag", "Diagonal", "Sum", "Product", "ScalarMul")
+
+
+def install(cola=None, matmats=True):
+    """Rebind the reference's hot-path functions (idempotent).  `cola` defaults to `import cola`."""
+    if _SAVED:
+        return
+    if cola is None:
+        cola = importlib.import_module("cola")
+    for modname, attr, make in _LOOPS:
+        mod = importlib.import_module(modname)
+        ref = getattr(mod, attr)
+        _SAVED[(mod, attr)] = ref
+        setattr(mod, attr, make(cola, ref))
+    if matmats:
+        for name in _MATMAT_CLASSES:
+            klass = getattr(cola.ops, name)
+            if "_matmat" in vars(klass):
+                ref = vars(klass)["_matmat"]
+                _SAVED[(klass, "_matmat")] = ref
+                setattr(klass, "_matmat", _make_matmat(cola, ref))
+
+
+def uninstall():
+    for (owner, attr), ref in list(_SAVED.items()):
+        setattr(owner, attr, ref)
+    _SAVED.clear()

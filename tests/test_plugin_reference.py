@@ -1,0 +1,190 @@
+"""cola_b200.plugin against the REAL reference (build container only: needs /root/reference and the import
+shims of tests/golden/refshim; skipped elsewhere).
+
+Three things are pinned here, all on CPU:
+  1. install()/uninstall() rebind exactly the documented symbols, and with CPU operators every call falls through
+     to the reference code (results unchanged);
+  2. from_cola maps reference operator trees to the mirror classes one to one (classes, shapes, leaves, annotations);
+  3. the adapters' layout glue: with FORCE_FAST_PATH and the CUDA loops replaced by oracle-backed stand-ins that
+     speak this package's layouts ((m+2, n, b) basis, fp64 accumulators), the reference's own public API
+     (CG, Lanczos, Arnoldi, stochastic_lanczos_quad) returns what the unpatched reference returns.
+The CUDA loops themselves are compared with the same oracle in tests/test_gpu_parity.py.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+REF = "/root/reference"
+if not os.path.isdir(os.path.join(REF, "cola")):
+    pytest.skip("reference tree not present (GPU box)", allow_module_level=True)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.dont_write_bytecode = True
+for p in (os.path.join(HERE, "golden", "refshim"), REF):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import cola  # noqa: E402  (the reference)
+from cola.linalg.inverse.cg import CG  # noqa: E402
+from cola.linalg.tbd.slq import stochastic_lanczos_quad  # noqa: E402
+
+from cola_b200 import ops as bops  # noqa: E402
+from cola_b200 import plugin  # noqa: E402
+b_lanczos = plugin.b_lanczos  # the submodule (cola_b200.linalg.lanczos the attribute is the function)
+from oracle import krylov_oracle as ko  # noqa: E402
+
+assert cola.__file__.startswith(REF)
+R = cola.ops
+
+
+def make_tree(dtype=torch.float64):
+    g = torch.Generator().manual_seed(3)
+    K1 = torch.randn(4, 4, dtype=dtype, generator=g); K1 = K1 @ K1.T / 4 + 0.5 * torch.eye(4, dtype=dtype)
+    K2 = torch.randn(3, 3, dtype=dtype, generator=g); K2 = K2 @ K2.T / 3 + 0.5 * torch.eye(3, dtype=dtype)
+    d = torch.rand(12, dtype=dtype, generator=g) + 0.5
+    A = R.Kronecker(cola.PSD(R.Dense(K1)), cola.PSD(R.Dense(K2))) + R.Diagonal(d)
+    return cola.PSD(A), (K1, K2, d)
+
+
+def mirror_to_oracle(M):
+    if isinstance(M, bops.Sparse):
+        return ko.SparseOp(M.data, M.row_indices, M.col_indices, M.shape)
+    if isinstance(M, bops.Dense):
+        return ko.DenseOp(M.A)
+    if isinstance(M, bops.Identity):
+        return ko.IdentityOp(M.shape[0], M.dtype)
+    if isinstance(M, bops.ScalarMul):
+        return ko.ScaledIdentityOp(float(M.c), M.shape[0], M.dtype)
+    if isinstance(M, bops.Diagonal):
+        return ko.DiagonalOp(M.diag)
+    if isinstance(M, bops.Kronecker):
+        return ko.KroneckerOp(*[mirror_to_oracle(m) for m in M.Ms])
+    if isinstance(M, bops.BlockDiag):
+        return ko.BlockDiagOp(*[mirror_to_oracle(m) for m in M.Ms], multiplicities=M.multiplicities)
+    if isinstance(M, bops.Sum):
+        return ko.SumOp(*[mirror_to_oracle(m) for m in M.Ms])
+    if isinstance(M, bops.Product):
+        return ko.ProductOp(*[mirror_to_oracle(m) for m in M.Ms])
+    raise TypeError(type(M))
+
+
+@pytest.fixture
+def installed():
+    plugin.install(cola)
+    yield
+    plugin.FORCE_FAST_PATH = False
+    plugin.uninstall()
+
+
+def test_install_rebinds_and_cpu_falls_through(installed):
+    from importlib import import_module as im   # `cola.linalg.trace` the attribute is a function, not the package
+    ra, rl = im("cola.linalg.decompositions.arnoldi"), im("cola.linalg.decompositions.lanczos")
+    rcg, rslq = im("cola.linalg.inverse.cg"), im("cola.linalg.tbd.slq")
+    rde = im("cola.linalg.trace.diagonal_estimation")
+    for mod, name in [(rcg, "run_batched_cg"), (rl, "lanczos_fact"), (ra, "arnoldi_fact"),
+                      (rde, "hutchinson_diag_estimate"), (rslq, "slq_fwd")]:
+        assert getattr(mod, name).__module__ == "cola_b200.plugin", name
+    assert R.Dense._matmat.__module__ == "cola_b200.plugin"
+    A, _ = make_tree()
+    b = torch.randn(12, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0))
+    x_in, _ = CG(tol=1e-10, max_iters=50)(A, b)
+    plugin.uninstall()
+    assert rcg.run_batched_cg.__module__ == "cola.linalg.inverse.cg"
+    assert R.Dense._matmat.__module__ == "cola.ops.operators"
+    x_ref, _ = CG(tol=1e-10, max_iters=50)(A, b)
+    assert torch.equal(x_in, x_ref)          # CPU operators never leave the reference code
+
+
+def test_from_cola_tree_mapping():
+    A, (K1, K2, d) = make_tree()
+    M = plugin.from_cola(A, cola)
+    assert isinstance(M, bops.Sum) and M.shape == (12, 12) and M.isa(bops.PSD)
+    kron, diag = M.Ms
+    assert isinstance(kron, bops.Kronecker) and [type(f) for f in kron.Ms] == [bops.Dense, bops.Dense]
+    assert kron.Ms[0].A is K1 and kron.Ms[1].A is K2 and all(f.isa(bops.PSD) for f in kron.Ms)
+    assert isinstance(diag, bops.Diagonal) and diag.diag is d
+    assert plugin.from_cola(A, cola) is M                         # cached on the reference instance
+    # scalar * identity, product, block diagonal, transpose, sparse (CSR arrays taken as they are)
+    I = R.I_like(A)
+    P = plugin.from_cola(2.5 * I, cola)
+    assert isinstance(P, bops.Product) and isinstance(P.Ms[0], bops.ScalarMul) and float(P.Ms[0].c) == 2.5
+    B = plugin.from_cola(R.BlockDiag(R.Dense(K1), R.Dense(K2), multiplicities=[2, 1]), cola)
+    assert isinstance(B, bops.BlockDiag) and B.multiplicities == [2, 1] and B.shape == (11, 11)
+    rows = torch.tensor([0, 0, 1, 2, 2]); cols = torch.tensor([0, 2, 1, 0, 2])
+    vals = torch.tensor([1., 2., 3., 4., 5.], dtype=torch.float64)
+    S_ref = R.Sparse(vals, rows, cols, (3, 3))
+    S = plugin.from_cola(S_ref, cola)
+    assert isinstance(S, bops.Sparse) and S.nnz == 5 and S.max_row_nnz == 2
+    assert torch.equal(S.indptr, S_ref.A.crow_indices().to(torch.int32))
+    assert torch.equal(S.data, S_ref.A.values())
+    with pytest.raises(plugin.NotConvertible):
+        plugin.from_cola(R.Dense(K1.to(torch.complex64)), cola)
+    with pytest.raises(plugin.NotConvertible):
+        plugin.from_cola(R.Householder(d[:, None]), cola)
+
+
+def _standin_cg(M, b, x0, max_iters, tol, P, pbar=False):
+    x, r, k, info = ko.cg(mirror_to_oracle(M), b, x0=x0, tol=tol, max_iters=max_iters)
+    return x, r, k, info
+
+
+def _standin_lanczos_fact(M, rhs, max_iters=100, tol=1e-7, pbar=False):
+    V, diag, sub, i, info = ko.lanczos_fact(mirror_to_oracle(M), rhs, max_iters, tol)
+    Vm = V.permute(2, 1, 0).contiguous()                            # this package's (m+2, n, b) layout
+    return b_lanczos.LanczosState(Vm, diag.T.double().contiguous(), (sub.T.double()**2).contiguous(), int(i), info)
+
+
+def _standin_arnoldi_fact(M, rhs, max_iters, tol, pbar=False):
+    Q, H, j, info = ko.arnoldi_fact(mirror_to_oracle(M), rhs, max_iters, tol)
+    return Q.permute(2, 1, 0).contiguous(), H, int(j), info
+
+
+def test_adapter_layouts_against_reference(installed, monkeypatch):
+    b_arnoldi, b_cg = plugin.b_arnoldi, plugin.b_cg
+    A, _ = make_tree()
+    g = torch.Generator().manual_seed(1)
+    B = torch.randn(12, 4, dtype=torch.float64, generator=g)
+    v = torch.randn(12, dtype=torch.float64, generator=g)
+
+    plugin.uninstall()
+    x_ref, info_ref = CG(tol=1e-9, max_iters=40)(A, B)
+    from importlib import import_module as im
+    ref_lanczos = im("cola.linalg.decompositions.lanczos").lanczos
+    ref_arnoldi = im("cola.linalg.decompositions.arnoldi").arnoldi
+    Ql_ref, Tl_ref, il_ref = ref_lanczos(A, v, 8, 1e-12)
+    Qb_ref, Tb_ref, _ = ref_lanczos(A, B, 6, 1e-12)
+    Qa_ref, Ha_ref, ia_ref = ref_arnoldi(A, v, 7, 1e-12)
+    key = A.xnp.PRNGKey(5)
+    slq_ref = stochastic_lanczos_quad(A, torch.log, max_iters=10, tol=1e-9, vtol=0.25, key=key)
+
+    plugin.install(cola)
+    plugin.FORCE_FAST_PATH = True
+    monkeypatch.setattr(b_cg, "run_batched_cg", _standin_cg)
+    monkeypatch.setattr(b_lanczos, "lanczos_fact", _standin_lanczos_fact)
+    monkeypatch.setattr(b_arnoldi, "arnoldi_fact", _standin_arnoldi_fact)
+    monkeypatch.setattr(plugin.b_stoch, "lanczos_fact", _standin_lanczos_fact)      # name imported into the module
+    monkeypatch.setattr(plugin.b_stoch, "probe_chunk", lambda *a, **k: 5)           # 16 probes in chunks of 5
+    # operator applications inside the stand-ins must not recurse into the (CUDA-only) mirror matmats
+    plugin.uninstall(); plugin.install(cola, matmats=False); plugin.FORCE_FAST_PATH = True
+
+    x, info = CG(tol=1e-9, max_iters=40)(A, B)
+    assert torch.allclose(x, x_ref, rtol=1e-10, atol=1e-12)
+    assert info["iterations"] == info_ref["iterations"]
+    Ql, Tl, il = ref_lanczos(A, v, 8, 1e-12)
+    assert Ql.to_dense().shape == Ql_ref.to_dense().shape
+    assert torch.allclose(Ql.to_dense(), Ql_ref.to_dense(), atol=1e-10)
+    assert torch.allclose(Tl.to_dense(), Tl_ref.to_dense(), atol=1e-10)
+    assert il["iterations"] == il_ref["iterations"]
+    Qb, Tb, _ = ref_lanczos(A, B, 6, 1e-12)
+    # batched start block: the leaves of the vmapped Dense / Tridiagonal carry the batch dimension
+    assert Qb.A.shape == Qb_ref.A.shape == (4, 12, 6)
+    assert torch.allclose(Qb.A, Qb_ref.A, atol=1e-10)
+    assert torch.allclose(Tb.beta, Tb_ref.beta, atol=1e-10) and torch.allclose(Tb.alpha, Tb_ref.alpha, atol=1e-10)
+    Qa, Ha, ia = ref_arnoldi(A, v, 7, 1e-12)
+    assert torch.allclose(Qa.to_dense(), Qa_ref.to_dense(), atol=1e-10)
+    assert torch.allclose(Ha.to_dense(), Ha_ref.to_dense(), atol=1e-10)
+    assert ia["iterations"] == ia_ref["iterations"]
+    slq = stochastic_lanczos_quad(A, torch.log, max_iters=10, tol=1e-9, vtol=0.25, key=key)
+    assert abs(float(slq) - float(slq_ref)) < 1e-8 * abs(float(slq_ref))
