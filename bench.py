@@ -229,7 +229,7 @@ def run_ours(args):
     iter_bytes = nnz * 8 + 4 * (n + 1) + 11 * n * k * 4   # B_param + 11 n k s
     ms_iter = elapsed_ms / iters_done
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kern[dom]["GBps"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": kern[dom]["GBps"] / peak, "traffic": ncu_traffic(dom, g, k), "peak_source": peak_src,
                 "kernels": kern,
                 "iteration": {"algorithmic_bytes": iter_bytes, "ms": ms_iter, "GBps": iter_bytes / ms_iter * 1e-6,
                               "frac": iter_bytes / ms_iter * 1e-6 / peak,
@@ -314,6 +314,16 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(out))
+
+
+def ncu_traffic(kernel, g, k):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/r1_ncu_full_traffic.json); None when there is no capture for this kernel / workload size."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_ncu_full_traffic.json")
+    if not (os.path.exists(path) and g == 2048 and k == 64):
+        return None
+    rec = json.load(open(path)).get("kernels", {}).get(kernel)
+    return None if rec is None else rec["traffic_bytes"]
 
 
 def main():

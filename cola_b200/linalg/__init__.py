@@ -3,6 +3,7 @@ from .arnoldi import arnoldi, arnoldi_eigs, arnoldi_fact
 from .cg import CG, cg, run_batched_cg
 from .dispatch import (Arnoldi, Cholesky, Eigh, Exact, Lanczos, diag, eig, exact_diag, get_slice, inv, log, logdet,
                        slogdet, solve, trace)
+from .gmres import GMRES, gmres, gmres_fwd
 from .lanczos import lanczos, lanczos_eigs, lanczos_fact
 from .stochastic import (Hutch, LanczosUnary, hutchinson_diag_estimate, slq_fwd, slq_per_probe,
                          stochastic_lanczos_quad)

@@ -16,6 +16,7 @@ from ..ops import (PSD, BlockDiag, Dense, Diagonal, Identity, Kronecker, LinearO
 from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
 from .arnoldi import arnoldi, arnoldi_eigs
 from .cg import CG
+from .gmres import GMRES
 from .lanczos import lanczos, lanczos_eigs
 from .stochastic import Hutch, LanczosUnary, hutchinson_diag_estimate
 
@@ -102,8 +103,6 @@ class _DenseInverse(LinearOperator):
 def inv(A: LinearOperator, alg: Algorithm = Auto()):
     """cola/linalg/inverse/inv.py:42-151"""
     # structure rules first (inv.py:108-151)
-    if isinstance(alg, Algorithm) and not isinstance(alg, (CG, Auto, Cholesky)) and False:
-        pass
     if A.isa(Unitary):
         return Unitary(A.H)
     if isinstance(A, Identity):
@@ -123,11 +122,15 @@ def inv(A: LinearOperator, alg: Algorithm = Auto()):
         small = bool(np.prod(A.shape) <= 1e6)
         if A.isa(PSD):
             alg = Cholesky() if small else CG(**alg.__dict__)
+        elif small:
+            raise NotImplementedError("small non-PSD operators route to a dense LU in the reference (inv.py:84-85), "
+                                      "which is outside the Krylov hot path")
         else:
-            raise NotImplementedError("non-PSD operators route to LU/GMRES in the reference; GMRES is a 'next' row of "
-                                      "the hot-path scope (DESIGN.md)")
+            alg = GMRES(**alg.__dict__)
     if isinstance(alg, CG):     # inv.py:66-69
         assert A.isa(PSD), "CG only valid for PSD matrices, wrap in cola.PSD if desired"
+        return IterativeOperatorWInfo(A, alg)
+    if isinstance(alg, GMRES):  # inv.py:60-62
         return IterativeOperatorWInfo(A, alg)
     if isinstance(alg, Cholesky):
         assert A.isa(PSD), "Cholesky only valid for PSD matrices, wrap in cola.PSD if desired"

@@ -383,6 +383,33 @@ def arnoldi(A, start, max_iters=100, tol=1e-7):
     return Q, H, info
 
 
+def gmres(A, rhs, x0=None, max_iters=100, tol=1e-7):
+    """cola/linalg/inverse/gmres.py:41-124 (use_householder=False, use_triangular=False; P is accepted by the
+    reference but never used, gmres.py:92-124).  rhs (n,) or (n,b) -> (soln, info).  Note the reference's own
+    formulation: it drops the LAST ROW of the (m+1, m) Hessenberg and solves the normal equations of the
+    square part, `(H^H H + D) y = H^H[:, 0] * beta`, D = identity on the rows that stayed zero."""
+    is_vec = rhs.dim() == 1
+    if x0 is None:
+        x0 = torch.zeros_like(rhs)
+    if is_vec:
+        rhs, x0 = rhs[..., None], x0[..., None]
+    res = rhs - A.matmat(x0)
+    m = max_iters
+    Q, H, _, info = arnoldi_fact(A, res, m, tol)                  # arnoldi() hands back the untrimmed arrays
+    Q, H = Q[:, :, :-1], H[:, :-1, :]
+    beta = torch.linalg.norm(res, dim=-2)
+    HT = torch.conj(torch.permute(H, [0, 2, 1]))
+    largest = torch.max(torch.abs(H), -1)[0]
+    overall = torch.max(largest.reshape(largest.shape[0], -1), -1)[0]
+    thresh = 10 * tol * overall[:, None]
+    padding = torch.where(largest < thresh, torch.ones_like(largest), torch.zeros_like(largest))
+    y = torch.linalg.solve(HT @ H + torch.diag_embed(padding), HT[..., 0, None]).squeeze(-1) * beta[:, None]
+    y = torch.where(largest < thresh, torch.zeros_like(y), y)
+    pred = torch.permute(Q @ y[..., None], [1, 0, 2])[:, :, 0]
+    soln = x0 + pred
+    return (soln[:, 0] if is_vec else soln), info
+
+
 def arnoldi_eigs(A, start, max_iters=100, tol=1e-7):      # arnoldi.py:35-62
     Q, H, info = arnoldi(A, start, max_iters, tol)
     Q, H = Q[:, :-1], H[:-1]

@@ -28,13 +28,14 @@ import torch  # noqa: E402
 import cola  # noqa: E402  (the reference)
 from cola.linalg.decompositions.decompositions import Arnoldi, Lanczos  # noqa: E402
 from cola.linalg.inverse.cg import CG  # noqa: E402
+from cola.linalg.inverse.gmres import GMRES  # noqa: E402
 from cola.linalg.tbd.slq import stochastic_lanczos_quad  # noqa: E402
 from cola.linalg.trace.diagonal_estimation import Hutch  # noqa: E402
 from cola.linalg.unary.unary import LanczosUnary  # noqa: E402
 from cola.ops import operators as rops  # noqa: E402
 
 from tests import problems as pb  # noqa: E402
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS  # noqa: E402
+from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS  # noqa: E402
 
 assert cola.__file__.startswith("/root/reference"), cola.__file__
 
@@ -192,6 +193,24 @@ def gen_arnoldi():
     save("eig_arnoldi_nonsym48_f64", eigvals_sorted_abs=np.abs(vals.numpy())[order])
 
 
+# --------------------------------------------------------------------------- GMRES
+def gen_gmres():
+    for case, (name, m, tol, vec) in GMRES_CASES.items():
+        P = pb.problem(name)
+        A = to_reference(P["spec"], P["ann"])
+        b = P["B"][:, 0].contiguous() if vec else P["B"]
+        x, info = GMRES(tol=tol, max_iters=m)(A, b)
+        save(case, x=x, errors=info["errors"], iterations=info["iterations"])
+    # with an initial guess, and through solve() (inv.py:23-39)
+    P = pb.problem("nonsym48_f64")
+    A = to_reference(P["spec"], P["ann"])
+    x0 = pb.randn_np(tuple(P["B"].shape), P["dtype"], 78)
+    # 20 steps: the full-space run (48 steps on n = 48) squares an ill-conditioned H and is not a usable pin
+    x, info = GMRES(tol=1e-12, max_iters=20, x0=x0)(A, P["B"])
+    save("gmres_nonsym48_f64_x0", x=x, iterations=info["iterations"])
+    save("solve_gmres_nonsym48_f64", x=cola.linalg.solve(A, P["B"], GMRES(tol=1e-12, max_iters=20)))
+
+
 # --------------------------------------------------------------------------- SLQ / Hutch / f(A)v
 def gen_stochastic():
     for name, m, vtol in [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2), ("lap24_f64", 40, 0.25)]:
@@ -226,6 +245,7 @@ if __name__ == "__main__":
     gen_cg()
     gen_lanczos()
     gen_arnoldi()
+    gen_gmres()
     gen_stochastic()
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump(MANIFEST, fh, indent=1, sort_keys=True)

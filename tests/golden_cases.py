@@ -33,3 +33,11 @@ ARNOLDI_CASES = {
     "arnoldi_nonsym48_f64": ("nonsym48_f64", 20, 1e-12, True),
     "arnoldi_nonsym48_f64_vec": ("nonsym48_f64", 48, 1e-12, False),
 }
+
+GMRES_CASES = {  # case -> (problem, max_iters, tol, vector?)
+    "gmres_nonsym48_f64": ("nonsym48_f64", 48, 1e-12, False),
+    "gmres_nonsym48_f32": ("nonsym48_f32", 30, 1e-7, False),
+    "gmres_nonsym48_f64_vec": ("nonsym48_f64", 20, 1e-12, True),
+    "gmres_lap24_f64": ("lap24_f64", 40, 1e-12, False),
+    "gmres_kron465_diag_f64": ("kron465_diag_f64", 25, 1e-12, False),
+}

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from tests import problems as pb
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+from tests.golden_cases import GMRES_CASES, ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
 
 pytestmark = pytest.mark.gpu
 
@@ -274,6 +274,61 @@ def test_eig_arnoldi(golden, cb):
                                                                 max_iters=48, tol=1e-12))
     mags = np.sort(np.abs(vals.cpu().numpy()))
     assert rel(mags, golden("eig_arnoldi_nonsym48_f64")["eigvals_sorted_abs"]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------- GMRES (8f item 2)
+@pytest.mark.parametrize("case", sorted(GMRES_CASES))
+def test_gmres_vs_oracle_and_golden(case, golden, cb):
+    """GMRES = device Arnoldi + the reference's normal-equation solve of the square Hessenberg (gmres.py:110-118).
+    That solve squares cond(H), so the bar on x is set by the oracle's own sensitivity to a 1-ulp perturbation of
+    b; the residual of the returned solution must be as small as the oracle's."""
+    from oracle import krylov_oracle as ko
+    name, m, tol, vec = GMRES_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    Ao = pb.to_oracle(P["spec"])
+    b = P["B"][:, 0].contiguous() if vec else P["B"]
+    x, info = cb.linalg.GMRES(tol=tol, max_iters=m)(A, b.to(DEV))
+    xo, info_o = ko.gmres(Ao, b, max_iters=m, tol=tol)
+    g = golden(case)
+    assert info["iterations"] == info_o["iterations"] == int(g["iterations"])
+    assert tuple(x.shape) == tuple(g["x"].shape)
+    t = tol_of(P["dtype"])
+    ulp = 1e-7 if P["dtype"] == torch.float32 else 1e-15
+    Ad = pb.to_oracle(pb.upcast(P["spec"]))
+    b64 = b.double()
+
+    def resid(sol):
+        sol = torch.as_tensor(np.asarray(sol.cpu() if torch.is_tensor(sol) else sol)).double()
+        return float(torch.linalg.norm(b64 - Ad @ sol) / torch.linalg.norm(b64))
+    sens, worst_resid = t, resid(xo)
+    for seed in (6, 7, 8, 9):            # the oracle under 1-ulp perturbations of b (full-space runs are ill-posed)
+        noise = 1.0 + ulp * pb.t(pb.rs(seed).normal(size=tuple(b.shape)), P["dtype"])
+        xp, _ = ko.gmres(Ao, b * noise, max_iters=m, tol=tol)
+        sens, worst_resid = max(sens, rel(xp, xo)), max(worst_resid, resid(xp))
+    bar = 20 * sens
+    assert rel(x, xo) < bar and rel(x, g["x"]) < bar, (rel(x, xo), rel(x, g["x"]), bar)
+    assert resid(x) <= 2 * worst_resid + 100 * t, (resid(x), worst_resid)
+    print(f"{case}: rel(x, oracle) {rel(x, xo):.2e} (bar {bar:.2e}), residual {resid(x):.2e} vs oracle {resid(xo):.2e}")
+
+
+def test_gmres_x0_solve_and_auto(golden, cb):
+    P = pb.problem("nonsym48_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    B = P["B"].to(DEV)
+    x0 = pb.randn_np(tuple(P["B"].shape), P["dtype"], 78)
+    x, info = cb.linalg.GMRES(tol=1e-12, max_iters=20, x0=x0.to(DEV))(A, B)
+    g = golden("gmres_nonsym48_f64_x0")
+    assert info["iterations"] == int(g["iterations"]) and rel(x, g["x"]) < 1e-8
+    x = cb.linalg.solve(A, B, cb.linalg.GMRES(tol=1e-12, max_iters=20))       # inv.py:23-39, 60-62
+    assert rel(x, golden("solve_gmres_nonsym48_f64")["x"]) < 1e-8
+    Ainv = cb.linalg.inv(A, cb.linalg.GMRES(tol=1e-12, max_iters=20))
+    y = Ainv @ B[:, 0].contiguous()
+    assert y.shape == (48,) and Ainv.info["iterations"] > 0
+    with pytest.raises(RuntimeError):
+        cb.linalg.GMRES()(A, P["B"])                                          # CPU right-hand side: no fallback
+    with pytest.raises(NotImplementedError):
+        cb.linalg.gmres(A, B, use_householder=True)
 
 
 # ------------------------------------------------------------------------------------------- SLQ / Hutch

@@ -9,7 +9,7 @@ import torch
 
 from oracle import krylov_oracle as ko
 from tests import problems as pb
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
 
 
 def rel(a, b):
@@ -126,6 +126,30 @@ def test_arnoldi_eigs(golden):
     lam, V, info = ko.arnoldi_eigs(A, P["B"][:, 0].contiguous(), 48, 1e-12)
     mags = np.sort(np.abs(lam.numpy()))
     assert rel(mags, golden("eig_arnoldi_nonsym48_f64")["eigvals_sorted_abs"]) < 1e-9
+
+
+@pytest.mark.parametrize("case", sorted(GMRES_CASES))
+def test_gmres(case, golden):
+    name, m, tol, vec = GMRES_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    b = P["B"][:, 0].contiguous() if vec else P["B"]
+    x, info = ko.gmres(A, b, max_iters=m, tol=tol)
+    g = golden(case)
+    assert info["iterations"] == int(g["iterations"])
+    assert tuple(x.shape) == tuple(g["x"].shape)
+    assert rel(x, g["x"]) < 1e3 * tol_of(P["dtype"])      # normal equations of H: cond(H)^2 amplification
+
+
+def test_gmres_x0_and_solve(golden):
+    P = pb.problem("nonsym48_f64")
+    A = pb.to_oracle(P["spec"])
+    x0 = pb.randn_np(tuple(P["B"].shape), P["dtype"], 78)
+    x, info = ko.gmres(A, P["B"], x0=x0, max_iters=20, tol=1e-12)
+    g = golden("gmres_nonsym48_f64_x0")
+    assert info["iterations"] == int(g["iterations"]) and rel(x, g["x"]) < 1e-9
+    x, _ = ko.gmres(A, P["B"], max_iters=20, tol=1e-12)
+    assert rel(x, golden("solve_gmres_nonsym48_f64")["x"]) < 1e-9
 
 
 @pytest.mark.parametrize("name,m,vtol", [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2),
