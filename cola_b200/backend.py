@@ -213,6 +213,13 @@ def lanczos_three_term(W, Vi, Vim1, alpha_acc, beta_prev_sq, gate=None):
                ptr(beta_prev_sq) if beta_prev_sq is not None else None, ptr(gate), stream_ptr())
 
 
+def tridiag_eig_first_row(d, e, z, status=None, gate=None):
+    """d, e, z: (m, b) float64 contiguous; see cola_tridiag_eig_first_row_f64."""
+    m, b = d.shape
+    lib().call("cola_tridiag_eig_first_row_f64", ptr(d, torch.float64), ptr(e, torch.float64), ptr(z, torch.float64), m, b,
+               b, ptr(status, torch.int32) if status is not None else None, ptr(gate), stream_ptr())
+
+
 def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
     n, b = W.shape
     lib().call(f"cola_mgs_link_{sfx(W.dtype)}", ptr(W), ptr(Qprev) if Qprev is not None else None,

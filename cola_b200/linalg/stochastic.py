@@ -153,12 +153,36 @@ def hutchinson_diag_estimate(A: LinearOperator, k=0, bs=100, tol=3e-2, max_iters
     return sums[0] / (i * bs), info
 
 
+USE_TRIDIAG_QL = True   # False: dense batched torch.linalg.eigh on the (b, m, m) tridiagonals, as the reference does
+
+
+def _tridiag_eig_first_row(st):
+    """(eigvals (b, iters), tau (b, iters)) of the Lanczos tridiagonals: eigenvalues and first eigenvector
+    components, all SLQ needs (slq.py:44-46), from the O(m^2) QL kernel instead of a dense O(m^3) eigh.  The
+    entries of T are first rounded to the operator dtype, which is what the reference's T holds."""
+    iters = st.iters
+    dt = st.V.dtype
+    d = st.alpha_acc[:iters].to(dt).to(torch.float64).contiguous()                # (iters, b)
+    e = torch.zeros_like(d)
+    if iters > 1:
+        e[:iters - 1] = torch.sqrt(st.sub_sq[1:iters]).to(dt).to(torch.float64)
+    z = torch.empty_like(d)
+    status = torch.zeros(d.shape[1], dtype=torch.int32, device=d.device)
+    be.tridiag_eig_first_row(d, e, z, status)
+    if bool(status.any()):
+        raise RuntimeError("tridiagonal QL iteration did not converge")
+    return d.T.to(dt), z.T.to(dt)
+
+
 def slq_per_probe(A, fun, Z, max_iters, tol, pbar=False):
     """n * sum_j tau_j^2 f(lambda_j) for every probe column of Z (n, b)  (slq.py:42-51)."""
     st = lanczos_fact(A, Z, max_iters, tol, pbar)
     eps = torch.finfo(A.dtype).eps
-    eigvals, Q = torch.linalg.eigh(_tridiag_dense(st))
-    tau = Q[..., 0, :]
+    if USE_TRIDIAG_QL:
+        eigvals, tau = _tridiag_eig_first_row(st)
+    else:
+        eigvals, Q = torch.linalg.eigh(_tridiag_dense(st))
+        tau = Q[..., 0, :]
     const = 10 * eps * torch.max(eigvals, dim=1, keepdim=True)[0]
     fn_vals = torch.where(torch.abs(eigvals) > const, fun(eigvals), torch.zeros_like(eigvals))
     return A.shape[-2] * torch.sum(tau**2 * fn_vals, dim=-1)

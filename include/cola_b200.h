@@ -201,6 +201,14 @@ int cola_reorth_update_dots_f64(const double* V, int64_t vstride, int64_t j0, in
                                 int64_t b, const double* C1, double sign, double* C2, const int32_t* gate,
                                 void* stream);
 
+/* Eigenvalues and FIRST eigenvector components of b symmetric tridiagonal m x m matrices (the Lanczos T of
+ * slq.py:42-51, which the reference hands to a dense batched eigh): implicit-shift QL in fp64, one thread per
+ * matrix, O(m^2).  Arrays are [i][matrix] with row stride ld >= b.  In: d = diagonal (m rows), e = off-diagonal
+ * (e[i] couples i and i+1; m rows of storage, the last is scratch).  Out: d = eigenvalues (unordered),
+ * z = first components (signs arbitrary), e destroyed, status[matrix] = 1 if an eigenvalue did not converge. */
+int cola_tridiag_eig_first_row_f64(double* d, double* e, double* z, int64_t m, int64_t b, int64_t ld, int32_t* status,
+                                   const int32_t* gate, void* stream);
+
 /* Lanczos three-term step after the matmat (lanczos.py:245-248), fused:
  *   W -= alpha[c] * Vi + beta_prev[c] * Vim1   with alpha[c] = (T)alpha_acc[c] (the <w,v_i> dots of the matmat),
  *   beta_prev[c] = (T)sqrt(beta_prev_sq[c]).  Vim1 / beta_prev_sq may be NULL (first step). */

@@ -422,6 +422,65 @@ def test_kronecker_tensor_core_path(cb):
 
 
 # ------------------------------------------------------------------------------------------- kernels directly
+def test_tridiag_ql_first_row(cb):
+    """Eigenvalues and first eigenvector components from the QL kernel against fp64 torch.linalg.eigh, including
+    matrices with (near-)zero couplings (early-terminated Lanczos) and m = 1, 2."""
+    be = cb.backend
+    g = torch.Generator().manual_seed(5)
+    for m, b in [(1, 3), (2, 5), (7, 33), (40, 64), (100, 70), (129, 2)]:
+        d = torch.randn(m, b, dtype=torch.float64, generator=g) + 3.0
+        e = torch.rand(m, b, dtype=torch.float64, generator=g) + 0.05
+        if m > 4:
+            e[2, 0] = 0.0            # exactly decoupled block
+            e[3, 1] = 1e-30          # numerically decoupled
+        e[m - 1] = 0.0
+        T = torch.diag_embed(d.T) + torch.diag_embed(e[:m - 1].T, offset=1) + torch.diag_embed(e[:m - 1].T, offset=-1)
+        lam_ref, Q = torch.linalg.eigh(T)
+        w_ref = Q[:, 0, :]**2
+        dd, ee, zz = d.to(DEV).contiguous(), e.to(DEV).contiguous(), torch.empty(m, b, dtype=torch.float64, device=DEV)
+        status = torch.ones(b, dtype=torch.int32, device=DEV)
+        be.tridiag_eig_first_row(dd, ee, zz, status)
+        assert int(status.abs().sum()) == 0
+        lam, order = torch.sort(dd.T.cpu(), dim=1)
+        w = torch.gather((zz.T.cpu())**2, 1, order)
+        assert float((lam - lam_ref).abs().max()) < 1e-12 * float(lam_ref.abs().max()), (m, b)
+        assert float((w.sum(1) - 1).abs().max()) < 1e-12
+        # weights of (numerically) equal eigenvalues are only defined as a sum: compare the quadrature itself
+        for f in (lambda x: torch.log(x * x + 1.0), lambda x: x**3, lambda x: torch.exp(-x * x)):
+            q, q_ref = (w * f(lam)).sum(1), (w_ref * f(lam_ref)).sum(1)
+            assert float((q - q_ref).abs().max()) < 1e-11 * float(q_ref.abs().max()), (m, b)
+
+
+def test_mode_contract_big_tile_path(cb):
+    """The 128x128x8 register-tiled fp32 path (factors with d_out % 128 == 0) against fp64 torch, including a
+    ragged last column tile, a rectangular factor, the shift/diag epilogue and accumulate; and that shapes it
+    does not take (dots requested, fp64) still agree."""
+    be = cb.backend
+    g = torch.Generator().manual_seed(11)
+    for (d_out, d_in, pre, post) in [(128, 128, 1, 4096), (128, 128, 3, 200), (256, 64, 2, 132), (128, 136, 1, 64)]:
+        M = torch.randn(d_out, d_in, generator=g).to(DEV)
+        X = torch.randn(pre, d_in, post, generator=g).to(DEV)
+        Y = torch.empty(pre, d_out, post, device=DEV)
+        be.mode_contract(M, d_out, d_in, pre, post, X, Y)
+        ref = torch.einsum("aj,pjq->paq", M.double(), X.double())
+        assert rel(Y, ref) < 2e-6, (d_out, d_in, pre, post)
+    d, pre, post = 128, 2, 260
+    M = torch.randn(d, d, generator=g).to(DEV)
+    X = torch.randn(pre, d, post, generator=g).to(DEV)
+    dg = torch.rand(pre * d, generator=g).to(DEV)
+    Y0 = torch.randn(pre, d, post, generator=g).to(DEV)
+    Y = Y0.clone()
+    be.mode_contract(M, d, d, pre, post, X, Y, alpha=0.5, shift=0.25, diag=dg, epi_x=X, accumulate=True)
+    ref = 0.5 * torch.einsum("aj,pjq->paq", M.double(), X.double()) + (0.25 + dg.double().reshape(pre, d, 1)) * X.double() \
+        + Y0.double()
+    assert rel(Y, ref) < 2e-6
+    dots = torch.zeros(post, dtype=torch.float64, device=DEV)
+    Y2 = torch.empty_like(Y)
+    be.mode_contract(M, d, d, pre, post, X, Y2, epi_x=X, dots=dots)             # dots -> 64x64 tile kernel
+    assert rel(Y2, torch.einsum("aj,pjq->paq", M.double(), X.double())) < 2e-6
+    assert rel(dots, (X.double() * Y2.double()).sum((0, 1))) < 1e-6
+
+
 def test_reorth_kernels_shapes(cb):
     """C = V^T W and W -= V C for ragged / wide / single-column probe blocks in both dtypes."""
     be = cb.backend

@@ -166,6 +166,7 @@ def test_adapter_layouts_against_reference(installed, monkeypatch):
     monkeypatch.setattr(b_arnoldi, "arnoldi_fact", _standin_arnoldi_fact)
     monkeypatch.setattr(plugin.b_stoch, "lanczos_fact", _standin_lanczos_fact)      # name imported into the module
     monkeypatch.setattr(plugin.b_stoch, "probe_chunk", lambda *a, **k: 5)           # 16 probes in chunks of 5
+    monkeypatch.setattr(plugin.b_stoch, "USE_TRIDIAG_QL", False)                    # the QL kernel is CUDA-only
     # operator applications inside the stand-ins must not recurse into the (CUDA-only) mirror matmats
     plugin.uninstall(); plugin.install(cola, matmats=False); plugin.FORCE_FAST_PATH = True
 
