@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
 #pragma unroll
       for (int c = 0; c < KMAX; ++c)
         if (c < k) acc[c] += w * __ldg(xr + c);   // read-only path: 32-byte sector fills for the random gather
+                                                  // (an L2 evict_last policy on these loads changed nothing: 3.90 ms both ways)
     }
 #pragma unroll
     for (int c = 0; c < KMAX; ++c)
@@ -287,10 +288,12 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     if (k <= 4) {   // SpMV-like: sub-warp-per-row kernel, no staging
       a.k = k;
       const double avg_nnz = n_rows > 0 ? (double)nnz / (double)n_rows : 1.0;
-      const int subw = avg_nnz >= 12 ? 8 : (avg_nnz >= 6 ? 4 : 2);
+      int subw = avg_nnz >= 24 ? 8 : (avg_nnz >= 6 ? 4 : 2);   // measured on the cfg5 graph (17 nnz/row): 4 beats 8 by 4 %
+      if (const char* e = getenv("COLA_SPMV_SUB")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16) subw = v; }
       int64_t groups_needed = n_rows;
       int64_t blocks = (groups_needed * subw + 255) / 256;
-      int64_t cap_blocks = (int64_t)sm_count() * 8;
+      int64_t cap_blocks = (int64_t)sm_count() * 64;   // many short CTAs: the row chains of different CTAs overlap (-9 %)
+      if (const char* e = getenv("COLA_SPMV_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 100000) cap_blocks = (int64_t)sm_count() * v; }
       if (blocks > cap_blocks) blocks = cap_blocks;
 #define COLA_SPMV_LAUNCH(SUBV)                                                                            \
   do {                                                                                                    \
@@ -298,7 +301,7 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     else if (epi) csr_spmv_kernel<T, 4, SUBV, true, false><<<(unsigned)blocks, 256, 0, st>>>(a);          \
     else csr_spmv_kernel<T, 4, SUBV, false, false><<<(unsigned)blocks, 256, 0, st>>>(a);                  \
   } while (0)
-      if (subw == 8) COLA_SPMV_LAUNCH(8); else if (subw == 4) COLA_SPMV_LAUNCH(4); else COLA_SPMV_LAUNCH(2);
+      if (subw == 16) COLA_SPMV_LAUNCH(16); else if (subw == 8) COLA_SPMV_LAUNCH(8); else if (subw == 4) COLA_SPMV_LAUNCH(4); else COLA_SPMV_LAUNCH(2);
       rc = cuda_status("csr_spmv");
       break;
     }

@@ -77,8 +77,9 @@ def cfg3(iters=100):
     n, k = 64**3, 128
     B = torch.randn(n, k, generator=torch.Generator().manual_seed(0)).to(dev)
     alg = cb.linalg.CG(tol=1e-30, max_iters=iters)
-    alg(A, B)
-    s, (x, info) = timed(lambda: alg(A, B), reps=3)
+    for _ in range(5):     # a 100-iteration solve is ~50 ms: let the clocks ramp before timing
+        alg(A, B)
+    s, (x, info) = timed(lambda: alg(A, B), reps=10)
     by = 3 * 64 * 64 * 4 + 11 * n * k * 4
     r_true = float((torch.linalg.norm(B - A @ x, dim=0) / torch.linalg.norm(B, dim=0)).mean())
     print(json.dumps({"workload": "cfg3: CG, Kronecker(64x64 x3)+0.1 I, n=262144, 128 RHS, fp32 (tcgen05 3xTF32 matmat)",
@@ -139,6 +140,8 @@ def cfg5(log2n=24, m=int(os.environ.get("LANCZOS_M", 128))):
     del rows, cols, vals
     torch.cuda.empty_cache()
     alg = cb.linalg.Lanczos(max_iters=m, tol=1e-12, key=7)
+    # warm-up: a 4-step run loads the kernels and creates the cuSOLVER handle used by the final (m x m) eigh
+    cb.linalg.eig(L, 2, "LM", cb.linalg.Lanczos(max_iters=4, tol=1e-12, key=7))
     s, (ev, V) = timed(lambda: cb.linalg.eig(L, 64, "LM", alg))
     by = (2 * m * m + 16 * m) * n * 8 + m * (nnz * 12 + 4 * (n + 1))
     vtop = V.to_dense()[:, -1].contiguous()
