@@ -77,27 +77,57 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     sx = be.sfx(dt)
     st = be.stream_ptr
 
+    # graphs pay off where the loop is launch-bound (vector blocks up to ~256 MB); larger problems spend
+    # milliseconds per kernel and the capture would cost more than it saves
+    graph_ok = USE_CUDA_GRAPH and n * k <= GRAPH_MAX_ELEMS and A.plan().graph_safe()
+    # A captured batch of iterations is tied to the buffers it was captured on.  For graph-eligible sizes the
+    # state lives in a workspace kept on the operator (one per operator, latest shape), so that a second solve with
+    # the same shape replays the graph of the first instead of capturing (and later destroying) its own: capture,
+    # instantiation and teardown cost more than a whole 100-iteration solve at these sizes.
+    ws = None
+    if graph_ok:
+        key = (n, k, dt, max_iters, str(dev))
+        cached = A.__dict__.get("_cg_workspace")
+        if cached is not None and cached["key"] == key:
+            ws = cached
+        else:
+            ws = {"key": key, "graph": None,
+                  "x": torch.empty_like(b), "r": torch.empty_like(b), "p": torch.empty_like(b), "ap": torch.empty_like(b),
+                  "gamma": torch.empty((max_iters + 2, k), dtype=torch.float64, device=dev),
+                  "pap": torch.empty((max_iters + 1, k), dtype=torch.float64, device=dev),
+                  "tol_eff": torch.empty(k, dtype=dt, device=dev),
+                  "ctl": torch.empty(4, dtype=torch.int32, device=dev)}
+            A.__dict__["_cg_workspace"] = ws
+
     # ---- setup: normalise RHS, residual, gamma0, tolerances (cg.py:96-101, 122-130)
     mult_sq = torch.zeros(k, dtype=torch.float64, device=dev)
     be.col_dots(b, b, mult_sq)
-    r = torch.empty_like(b)
+    r = ws["r"] if ws else torch.empty_like(b)
     be.col_scale(b, r, mult_sq, take_sqrt=True, mode=1)          # b / ||b|| (safe)
+    x = ws["x"] if ws else torch.empty_like(b)
     if x0 is None:
-        x = torch.zeros_like(b)
+        x.zero_()
     else:
-        x = x0.to(dt).contiguous().clone()
+        x.copy_(x0.to(dt))
         ax = torch.empty_like(b)
         A.matmat_into(x, ax)
         be.axpby(ax, r, -1.0, 1.0)                               # r0 = b - A x0
         del ax
-    p = r.clone()
-    ap = torch.empty_like(b)
-    gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)
-    pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
+    if ws:
+        p, ap, gamma, pap, tol_eff, ctl = ws["p"], ws["ap"], ws["gamma"], ws["pap"], ws["tol_eff"], ws["ctl"]
+        p.copy_(r)
+        gamma.zero_()
+        pap.zero_()
+        ctl.copy_(torch.tensor([0, 0, max_iters, k], dtype=torch.int32))
+    else:
+        p = r.clone()
+        ap = torch.empty_like(b)
+        gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)
+        pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
+        tol_eff = torch.empty(k, dtype=dt, device=dev)
+        ctl = torch.tensor([0, 0, max_iters, k], dtype=torch.int32, device=dev)
     be.col_dots(r, r, gamma[0])
-    tol_eff = torch.empty(k, dtype=dt, device=dev)
     lib.call(f"cola_cg_tol_{sx}", be.ptr(gamma), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
-    ctl = torch.tensor([0, 0, max_iters, k], dtype=torch.int32, device=dev)
     it_ptr, done_ptr = ctl[0:1], ctl[1:2]
     lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 0, st())   # initial cond_fun
 
@@ -110,12 +140,11 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
                      be.ptr(pap), st())
             lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
 
-    # graphs pay off where the loop is launch-bound (vector blocks up to ~256 MB); larger problems spend
-    # milliseconds per kernel and the capture would cost more than it saves
-    graph_ok = USE_CUDA_GRAPH and n * k <= GRAPH_MAX_ELEMS and A.plan().graph_safe()
     t0 = time.time()
     it, done = 0, 0
-    graph, batches = None, 0
+    if ws and ws["graph"] is not None and ws.get("token") != A.plan().graph_token():
+        ws["graph"] = None                                       # the operator's scratch buffers moved: recapture
+    graph, batches = (ws["graph"] if ws else None), 0
     while True:
         c = ctl.cpu()
         it, done = int(c[0]), int(c[1])
@@ -129,6 +158,7 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 enqueue(CHECK_EVERY)
+            ws["graph"], ws["token"] = graph, A.plan().graph_token()
             # capture does not execute: fall through to the replay below
         if graph is not None:
             graph.replay()
@@ -142,6 +172,10 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     trace = torch.sqrt(gamma[:it + 1]).mean(dim=1).cpu().numpy()
     samples = np.concatenate([trace, trace[-1:]])
     info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
-    be.col_scale(x, x, mult_sq, take_sqrt=True, mode=0)          # x * ||b||  (cg.py:119)
-    be.col_scale(r, r, mult_sq, take_sqrt=True, mode=0)
-    return x, r, it, info
+    if ws:                                                       # hand back copies: the workspace is reused
+        x_out, r_out = torch.empty_like(x), torch.empty_like(r)
+    else:
+        x_out, r_out = x, r
+    be.col_scale(x, x_out, mult_sq, take_sqrt=True, mode=0)      # x * ||b||  (cg.py:119)
+    be.col_scale(r, r_out, mult_sq, take_sqrt=True, mode=0)
+    return x_out, r_out, it, info

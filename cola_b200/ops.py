@@ -675,6 +675,16 @@ class Plan:
         allocate or synchronise): the condition for capturing the apply in a CUDA graph."""
         return all(not isinstance(c, _OpaqueCore) and len(ch) == 1 for _, ch in self.terms for c in ch)
 
+    def graph_token(self):
+        """Identity of every scratch buffer the apply touches (Kronecker / BlockDiag workspaces grow on demand and a
+        captured graph keeps the old pointers): a cached graph is only replayed while this is unchanged."""
+        tok = []
+        for _, ch in self.terms:
+            for c in ch:
+                for key, buf in sorted(getattr(c, "_ws", {}).items(), key=lambda kv: str(kv[0])):
+                    tok.append((str(key), buf.data_ptr(), buf.numel()))
+        return tuple(tok)
+
     def describe(self):
         parts = [f"{s:g}*" + "@".join(type(c).__name__.strip("_") for c in ch) for s, ch in self.terms]
         if self.shift != 0.0:

@@ -146,6 +146,40 @@ def test_cg_edge_cases(cb):
     assert float(x[:, 1].abs().sum()) == 0.0
 
 
+def test_cg_graph_workspace_reuse(cb):
+    """Graph-eligible solves keep their state (and the captured iteration batch) on the operator: a second solve
+    with the same shape replays the first one's graph.  Results must not depend on that history, earlier outputs
+    must stay intact, and a change of shape / max_iters / scratch buffers must recapture."""
+    from oracle import krylov_oracle as ko
+    P = pb.problem("kron888_f32")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    Ao = pb.to_oracle(P["spec"])
+    B1 = P["B"]
+    B2 = pb.randn_np(tuple(B1.shape), P["dtype"], 321)
+    alg = cb.linalg.CG(tol=1e-6, max_iters=200)
+    x1, i1 = alg(A, B1.to(DEV))
+    x1_copy = x1.clone()
+    assert A.__dict__["_cg_workspace"]["graph"] is not None          # 3 batches of 16 iterations at least
+    g_first = A.__dict__["_cg_workspace"]["graph"]
+    x2, i2 = alg(A, B2.to(DEV))
+    assert A.__dict__["_cg_workspace"]["graph"] is g_first           # replayed, not recaptured
+    assert torch.equal(x1, x1_copy)                                  # outputs are copies of the workspace
+    x1b, i1b = alg(A, B1.to(DEV))
+    assert rel(x1b, x1) < 1e-6 and i1b["iterations"] == i1["iterations"]       # same inputs, replayed graph
+    for B, x, info in ((B1, x1, i1), (B2, x2, i2)):
+        xo, _, _, info_o = ko.cg(Ao, B, tol=1e-6, max_iters=200)
+        assert abs(info["iterations"] - info_o["iterations"]) <= 1     # the stop test can flip on the last ulp
+        assert rel(x, xo) < 2e-5
+    x0 = pb.randn_np(tuple(B1.shape), P["dtype"], 5)
+    x3, _ = cb.linalg.CG(tol=1e-6, max_iters=200, x0=x0.to(DEV))(A, B1.to(DEV))
+    assert rel(x3, x1) < 5e-4                                        # other start, same tolerance: cond * tol apart
+    # different number of right-hand sides -> new workspace; then back
+    x4, _ = alg(A, B1[:, :3].contiguous().to(DEV))
+    assert A.__dict__["_cg_workspace"]["key"][1] == 3 and rel(x4, x1[:, :3]) < 5e-4   # `any` stop rule over 3 columns
+    x5, _ = alg(A, B1.to(DEV))
+    assert rel(x5, x1) < 1e-6
+
+
 def test_cg_full_size_properties(cb):
     """BASELINE config 2 at a GPU-friendly slice of full size (1024^2 grid, 64 RHS, fp32): properties that
     do not need the oracle: the true residual b - A x matches the recurrence residual and decreases."""
