@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
   T* bufs = reinterpret_cast<T*>(fu_smem);                       // S x ([nj_pad][R][b] | W [R][b])  ring of chunks
   T* coef = bufs + (int64_t)S * stage_elems;                   // [nj][b]  (sign * C1)
   T* part = coef + nj * b;                                     // [G][R][b] partial sums of the update
-  uint64_t* bars = reinterpret_cast<uint64_t*>(part + (int64_t)kFuMaxThreads * (RPT + 1) * VEC);   // full[S] | empty[S]
+  T* wnew = part + (int64_t)kFuMaxThreads * (RPT + 1) * VEC;  // [R][b] finished rows of W (R*b <= kFuMaxThreads*RPT*VEC)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wnew + (int64_t)kFuMaxThreads * RPT * VEC);   // full[S] | empty[S]
   const int64_t n_chunks = (a.n + R - 1) / R;
   const uint32_t bars_u32 = fu_smem_u32(bars), bufs_u32 = fu_smem_u32(bufs);
   if (tid == 0) {
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
   uint32_t phase = 0;
   for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
     const T* vs = bufs + slot * stage_elems;
-    T* ws = bufs + slot * stage_elems + ws_off;
+    const T* ws = bufs + slot * stage_elems + ws_off;
     const int64_t row0 = ch * R;
     const int rows = (int)min((int64_t)R, a.n - row0);
     fu_mbar_wait(bars_u32 + 8 * slot, phase);
@@ -327,7 +328,12 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
       for (int rr = 0; rr < RPT; ++rr)
         *reinterpret_cast<Vec<T, VEC>*>(part + ((int64_t)g * RL + (r0 + rr) * lanes + l_up) * VEC) = p[rr];
     }
+    Vec<T, VEC> w_old;                                          // the output thread's element of W, read while the
+    if (tid < RL && out_r < rows) w_old = *reinterpret_cast<const Vec<T, VEC>*>(ws + out_e);   // slot is still held
     if (!(dbg & 32)) FU_CONSUMER_SYNC();
+    // Everything this chunk needs from the ring slot is in registers now: hand the slot back to the producer before
+    // the reduction and the dots, so that two slots of R rows do the work of three (R is what bounds the kernel).
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_u32 + 8 * (S + slot)) : "memory");
     // 2b. W_new = W + sum of the G partials, in two levels so that no thread waits on a long chain of
     //     shared-memory loads: Q threads per output each add ~G/Q partials, then one thread adds those Q.
     if (tid < Q * RL && !(dbg & 1)) {
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
       if (out_r < rows) {
         const int e = out_e;
         Vec<T, VEC> s4[4];
-        s4[0] = *reinterpret_cast<const Vec<T, VEC>*>(ws + e);
+        s4[0] = w_old;
 #pragma unroll
         for (int u = 1; u < 4; ++u)
 #pragma unroll
@@ -374,10 +380,7 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
         }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) s4[0].v[v] = (s4[0].v[v] + s4[1].v[v]) + (s4[2].v[v] + s4[3].v[v]);
-        *reinterpret_cast<Vec<T, VEC>*>(ws + e) = s4[0];
-        // order the generic write of ws before the TMA refill of this slot; issued before the global store so
-        // that the fence does not wait for the store's round trip
-        if (!(dbg & 16)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        *reinterpret_cast<Vec<T, VEC>*>(wnew + e) = s4[0];
         if (!(dbg & 2)) stg<T, VEC>(a.W + row0 * b + e, s4[0]);
       }
     }
@@ -387,7 +390,7 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
 #pragma unroll
       for (int rr = 0; rr < RPT; ++rr) {
         if (r0 + rr < rows) {
-          const Vec<T, VEC> w = *reinterpret_cast<const Vec<T, VEC>*>(ws + elem0 + rr * (int)b);
+          const Vec<T, VEC> w = *reinterpret_cast<const Vec<T, VEC>*>(wnew + elem0 + rr * (int)b);
 #pragma unroll
           for (int jj = 0; jj < KJ; ++jj)
 #pragma unroll
@@ -395,8 +398,6 @@ __global__ void __launch_bounds__(kFuMaxThreads + 32, 1)
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bars_u32 + 8 * (S + slot)) : "memory");
     if (++slot == S) { slot = 0; phase ^= 1; }
   }
   // flush: combine the row-slices (and every CTA) per (vector, column) in fp64; the ring is free by now
@@ -581,13 +582,15 @@ int reorth_update_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, T* W
   // The per-chunk instruction cost is nearly fixed, so the tallest chunk wins; ties go to the smaller KJ.
   int best_rpt = 0, best_kj = 0;
   int64_t best_R = 0;
+  int min_stages = 2;   // a slot is handed back as soon as its chunk is in registers, so two slots already overlap
+  if (const char* e = getenv("COLA_FU_MIN_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= 8) min_stages = v; }
   const bool can_3d = (nn * bb) % 256 == 0 && 256 % bb == 0 && (vstride % 256) == 0;
   for (int rpt = 2; rpt >= 1; --rpt) {
     for (int kj = 2; kj <= 8; kj *= 2) {
       if (rpt == 2 && kj == 8) continue;                       // register budget
-      const int64_t part_bytes = (int64_t)kFuMaxThreads * (rpt + 1) * 16;
+      const int64_t part_bytes = (int64_t)kFuMaxThreads * (2 * rpt + 1) * 16;
       const int64_t budget = (int64_t)smem_max - 1024 - coef_bytes - part_bytes;
-      int64_t R = (int64_t)nthr * rpt / lanes;
+      int64_t R = (int64_t)nthr / lanes;                       // one output thread per Vec of the chunk (level 2)
       if (R > 256) R = 256;
       R -= R % rpt;
       for (; R >= rpt; R -= rpt) {
@@ -595,14 +598,14 @@ int reorth_update_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, T* W
         const bool fits_3d = can_3d && (R * bb) % 256 == 0 && R * bb / 256 <= 256;
         if (!fits_2d && !fits_3d) continue;
         const int64_t GS = R * lanes / rpt, G = nthr / GS;
-        if (G >= 1 && (nj + G - 1) / G <= kj && budget / stage_bytes(R) >= 3) break;
+        if (G >= 1 && (nj + G - 1) / G <= kj && budget / stage_bytes(R) >= min_stages) break;
       }
       if (R >= rpt && (R > best_R || (R == best_R && kj < best_kj))) { best_R = R; best_rpt = rpt; best_kj = kj; }
     }
   }
   if (best_R == 0) return fail(COLA_E_UNSUPPORTED, "reorth_update_dots: basis chunk does not fit shared memory / registers");
   const int64_t R = best_R;
-  const int64_t part_bytes = (int64_t)kFuMaxThreads * (best_rpt + 1) * 16;
+  const int64_t part_bytes = (int64_t)kFuMaxThreads * (2 * best_rpt + 1) * 16;
   int64_t S = ((int64_t)smem_max - 1024 - coef_bytes - part_bytes) / stage_bytes(R);
   if (S > 8) S = 8;
   if (const char* e = getenv("COLA_FU_S")) { const int64_t ss = atoi(e); if (ss >= 1 && ss < S) S = ss; }
