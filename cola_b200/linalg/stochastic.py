@@ -31,6 +31,23 @@ def _tridiag_dense(st):
     return T
 
 
+def friendly_chunks(k, cb, dtype, start=0):
+    """Column ranges covering probes [start, start + k) in blocks no wider than cb whose widths are powers of two
+    (>= one 16-byte vector): 100 probes -> 64 + 32 + 4.  The reorthogonalisation kernels take their 16-byte vector
+    path for those widths only; a 100- or 52-wide block falls to scalar loads and ran the API form of cfg4 at
+    2.7 s per 100 probes instead of 1.6 s."""
+    vec = 16 // (torch.finfo(dtype).bits // 8)
+    out, c0, end = [], start, start + k
+    while c0 < end:
+        left = end - c0
+        w = 1 << (min(left, cb).bit_length() - 1)        # largest power of two <= min(left, cb)
+        if w < vec:
+            w = left                                       # tail narrower than one vector: one scalar block
+        out.append((c0, c0 + w))
+        c0 += w
+    return out
+
+
 def probe_chunk(n, m, dtype, device, requested=None):
     """Largest probe-block width whose (m+2, n, b) basis fits comfortably in free HBM (<= 256, multiple of 32
     when possible so the reorth kernels take their 16-byte vector path)."""
@@ -63,8 +80,8 @@ class LanczosUnary(LinearOperator):
         n, k = V.shape
         out = torch.empty_like(V)
         cb = probe_chunk(n, max_iters, self.dtype, V.device, kw.pop("probe_chunk", None))
-        for c0 in range(0, k, cb):
-            blk = V[:, c0:c0 + cb].contiguous()
+        for c0, c1 in friendly_chunks(k, cb, self.dtype):
+            blk = V[:, c0:c1].contiguous()
             st = lanczos_fact(self.A, blk, max_iters=max_iters, **kw)
             self.info.update(st.info)
             T = _tridiag_dense(st)
@@ -81,7 +98,7 @@ class LanczosUnary(LinearOperator):
             C[1:] = coef.T.to(torch.float64)
             w = torch.zeros_like(blk)
             be.reorth_update(st.V, 1, st.iters + 1, w, C, sign=1.0)
-            out[:, c0:c0 + cb] = w
+            out[:, c0:c1] = w
             del st
         return out
 
@@ -203,8 +220,8 @@ def slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key, probe_chunk_size=Non
         probes = DeferredProbes(n, num_samples, A.dtype, A.device, key)
     cb = probe_chunk(n, max_iters, A.dtype, A.device, probe_chunk_size)
     total = torch.zeros(2, dtype=torch.float64, device=A.device)
-    for c0 in range(lo, hi, cb):
-        Z = probes.columns(c0, min(c0 + cb, hi))
+    for c0, c1 in friendly_chunks(hi - lo, cb, A.dtype, start=lo):
+        Z = probes.columns(c0, c1)
         est = slq_per_probe(A, fun, Z, max_iters, tol, pbar)
         total[0] += est.to(torch.float64).sum()
         total[1] += est.numel()
