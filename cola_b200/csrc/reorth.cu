@@ -446,13 +446,14 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
   COLA_REQUIRE(j1 >= j0 && j0 >= 0, "reorth_dots: bad vector range");
   if (j1 == j0 || n <= 0 || b <= 0) return COLA_OK;
   const int maxv = 16 / (int)sizeof(T);
-  // vector path: b*sizeof(T) multiple of 16 B, rows 16 B aligned, and b/VEC a power of two or a multiple of 32
+  // vector path: b*sizeof(T) a multiple of 16 B and rows 16 B aligned
   int vec = 1;
   {
     int v = pick_vec<T>(b, b, V, W);
     if (vstride % v) v = 1;
     int64_t per_row = b / v;
-    if (v == maxv && ((per_row <= 32 && (per_row & (per_row - 1)) == 0) || per_row % 32 == 0)) vec = v;
+    (void)per_row;
+    if (v == maxv) vec = v;   // any width that is a whole number of 16-byte vectors: idle lanes are guarded by col < b
   }
   int64_t per_row = (b + vec - 1) / vec;
   int Lr = per_row >= 32 ? 32 : next_pow2(per_row);

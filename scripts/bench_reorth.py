@@ -6,7 +6,7 @@ import cola_b200 as cb
 from cola_b200 import backend as be
 from bench import time_kernel
 dev = torch.device("cuda:0")
-for (n, b, dt, nj) in [(1 << 20, 64, torch.float32, 50), (1 << 20, 64, torch.float32, 100), (1 << 20, 128, torch.float32, 50), (1 << 24, 1, torch.float64, 64), (1 << 22, 8, torch.float32, 32)]:
+for (n, b, dt, nj) in [(1 << 20, 100, torch.float32, 50), (1 << 20, 64, torch.float32, 50), (1 << 20, 64, torch.float32, 100), (1 << 20, 128, torch.float32, 50), (1 << 24, 1, torch.float64, 64), (1 << 22, 8, torch.float32, 32)]:
     s = 4 if dt == torch.float32 else 8
     V = torch.randn(nj + 1, n, b, dtype=dt, device=dev)
     W = torch.randn(n, b, dtype=dt, device=dev)
