@@ -5,5 +5,6 @@ from .dispatch import (Arnoldi, Cholesky, Eigh, Exact, Lanczos, diag, eig, exact
                        slogdet, solve, trace)
 from .gmres import GMRES, gmres, gmres_fwd
 from .lanczos import lanczos, lanczos_eigs, lanczos_fact
+from .preconditioners import NystromPrecond, get_nys_approx
 from .stochastic import (Hutch, LanczosUnary, hutchinson_diag_estimate, slq_fwd, slq_per_probe,
                          stochastic_lanczos_quad)

@@ -64,8 +64,7 @@ def cg(A: LinearOperator, rhs, x0=None, P=None, tol=1e-6, max_iters=5000, pbar=F
 def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     """cola/linalg/inverse/cg.py:94-119 on the device.  b (n,k) -> (x (n,k), r (n,k), k_iters, info)."""
     if not isinstance(preconditioner, Identity):
-        raise NotImplementedError("cola_b200 CG runs with the identity preconditioner only "
-                                  "(Nystrom preconditioning is a 'next' row, DESIGN.md)")
+        return _run_batched_pcg(A, b, x0, max_iters, tol, preconditioner, pbar)
     if not b.is_cuda:
         raise RuntimeError("cola_b200 is a CUDA-only path: right-hand side is on the CPU (no CPU fallback)")
     dt = A.dtype
@@ -179,3 +178,79 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     be.col_scale(x, x_out, mult_sq, take_sqrt=True, mode=0)      # x * ||b||  (cg.py:119)
     be.col_scale(r, r_out, mult_sq, take_sqrt=True, mode=0)
     return x_out, r_out, it, info
+
+
+def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
+    """Preconditioned branch of cola/linalg/inverse/cg.py:94-170: z = P r, gamma = <r, z>,
+    p = z + beta p, while the stopping rule, the `has_converged` mask's trace and `info['errors']` keep using ||r||.
+    Built from the same kernels as the plain loop:
+        matmat(p -> Ap, <p, Ap> fused)  ->  r-sweep (r -= alpha Ap, writes ||r||^2 into its own trace)
+        ->  P applied to r with <r, z> fused into gamma  ->  xp-sweep with z in the role of r  ->  advance on ||r||^2.
+    P is any operator of this package (its plan is applied like A's); device-side gating and the 16-iteration
+    batches between host polls are unchanged.  One deviation: the per-column `has_converged` mask inside the sweeps
+    tests gamma = <r, P r> instead of ||r||^2 against 1e-80; both vanish together for a positive definite P, and
+    the mask only matters for residuals that are exactly zero."""
+    if not b.is_cuda:
+        raise RuntimeError("cola_b200 is a CUDA-only path: right-hand side is on the CPU (no CPU fallback)")
+    assert tuple(P.shape) == tuple(A.shape), "preconditioner shape mismatch"
+    dt = A.dtype
+    b = b.to(dt).contiguous()
+    n, k = b.shape
+    dev = b.device
+    max_iters = int(max_iters)
+    lib = be.lib()
+    sx = be.sfx(dt)
+    st = be.stream_ptr
+
+    mult_sq = torch.zeros(k, dtype=torch.float64, device=dev)
+    be.col_dots(b, b, mult_sq)
+    r = torch.empty_like(b)
+    be.col_scale(b, r, mult_sq, take_sqrt=True, mode=1)          # b / ||b|| (safe)
+    if x0 is None:
+        x = torch.zeros_like(b)
+    else:
+        x = x0.to(dt).contiguous().clone()
+        ax = torch.empty_like(b)
+        A.matmat_into(x, ax)
+        be.axpby(ax, r, -1.0, 1.0)                               # r0 = b - A x0
+        del ax
+    gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)    # <r, z>
+    rnorm2 = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)   # <r, r>
+    pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
+    z = torch.empty_like(b)
+    P.matmat_into(r, z, dots=gamma[0])                           # z0 = P r0, gamma0 = <r0, z0>  (cg.py:124-127)
+    p = z.clone()
+    ap = torch.empty_like(b)
+    be.col_dots(r, r, rnorm2[0])
+    tol_eff = torch.empty(k, dtype=dt, device=dev)
+    lib.call(f"cola_cg_tol_{sx}", be.ptr(rnorm2), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
+    ctl = torch.tensor([0, 0, max_iters, k], dtype=torch.int32, device=dev)
+    it_ptr, done_ptr = ctl[0:1], ctl[1:2]
+    lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(rnorm2), be.ptr(tol_eff), 0, st())
+    gamma_next = gamma[1:]                                       # row `it` of this view is gamma[it + 1]
+
+    def enqueue(n_iters):
+        for _ in range(n_iters):
+            A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)
+            lib.call(f"cola_cg_update_r_{sx}", be.ptr(r), be.ptr(ap), n, k, k, be.ptr(ctl), be.ptr(gamma),
+                     be.ptr(pap), be.ptr(rnorm2), st())          # ||r_new||^2 -> rnorm2[it + 1]
+            P.matmat_into(r, z, dots=gamma_next, dots_row=it_ptr, gate=done_ptr)   # <r_new, z_new> -> gamma[it + 1]
+            lib.call(f"cola_cg_update_xp_{sx}", be.ptr(x), be.ptr(z), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma),
+                     be.ptr(pap), st())
+            lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(rnorm2), be.ptr(tol_eff), 1, st())
+
+    t0 = time.time()
+    it = 0
+    while True:
+        c = ctl.cpu()
+        it, done = int(c[0]), int(c[1])
+        if done:
+            break
+        enqueue(min(CHECK_EVERY, max_iters - it))
+    elapsed = time.time() - t0
+    trace = torch.sqrt(rnorm2[:it + 1]).mean(dim=1).cpu().numpy()
+    samples = np.concatenate([trace, trace[-1:]])
+    info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
+    be.col_scale(x, x, mult_sq, take_sqrt=True, mode=0)          # x * ||b||  (cg.py:119)
+    be.col_scale(r, r, mult_sq, take_sqrt=True, mode=0)
+    return x, r, it, info

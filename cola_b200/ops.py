@@ -712,11 +712,16 @@ class Plan:
                 core = chain[ci]
                 final = ci == 0
                 if final:
-                    if last_term:
-                        epi = _Epilogue(scale, self.shift, self.diag, n_terms > 1, dots, dots_row, gate)
+                    if last_term and len(chain) > 1 and (self.shift != 0.0 or self.diag is not None or dots is not None):
+                        # The fused epilogue of a core reads the core's own input; at the head of a Product chain
+                        # that is the intermediate, not X.  Apply the chain plainly, then one diagonal sweep adds
+                        # (shift + diag) o X and takes the <X, Y> column dots.
+                        core.apply(src, Y, _Epilogue(scale, 0.0, None, t > 0, None, None, gate))
+                        be.diag_matmat(X, Y, self.shift, self.diag, True, dots, dots_row, gate)
+                    elif last_term:
+                        core.apply(src, Y, _Epilogue(scale, self.shift, self.diag, n_terms > 1, dots, dots_row, gate))
                     else:
-                        epi = _Epilogue(scale, 0.0, None, t > 0, None, None, gate)
-                    core.apply(src, Y, epi)
+                        core.apply(src, Y, _Epilogue(scale, 0.0, None, t > 0, None, None, gate))
                 else:
                     tmp = torch.empty((core.shape[0], X.shape[1]), dtype=X.dtype, device=X.device)
                     core.apply(src, tmp, _Epilogue(gate=gate))

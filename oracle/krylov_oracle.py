@@ -263,6 +263,27 @@ def cg(A, B, x0=None, tol=1e-6, max_iters=1000, P=None):
     return x, r, k, info
 
 
+class NystromPrecondOp(Op):
+    """cola/linalg/preconditioning/preconditioners.py:97-157: P = U diag(s) U^T + I from the rank-r Nystrom sketch."""
+    def __init__(self, A, rank, mu=1e-7, eps=1e-8, adjust_mu=True, key=None):
+        super().__init__(A.shape, A.dtype)
+        key = PRNGKey(42) if key is None else key
+        Omega = keyed_randn(A.shape[0], rank, dtype=A.dtype, key=key)
+        Omega, _ = torch.linalg.qr(Omega, mode="reduced")              # get_nys_approx :145-157
+        Y = A.matmat(Omega)
+        nu = eps * torch.linalg.norm(Y)
+        Y = Y + nu * Omega
+        C = torch.linalg.cholesky(Omega.T @ Y)
+        B = torch.linalg.solve_triangular(C, Y.T, upper=False).T
+        U, Sigma, _ = torch.linalg.svd(B, full_matrices=False)
+        self.Lambda, self.U = torch.clip(Sigma**2.0 - nu, min=0.0), U
+        amu = mu * torch.max(self.Lambda) if adjust_mu else mu        # _create_approx :118-126
+        self.scaling = ((torch.min(self.Lambda) + amu) / (self.Lambda + amu) - 1)[:, None]
+
+    def matmat(self, V):                                               # :128-130
+        return self.U @ (self.scaling * (self.U.T @ V)) + V
+
+
 # ----------------------------------------------------------------------------------
 # Lanczos with CGS2 full reorthogonalisation  (cola/linalg/decompositions/lanczos.py:185-296)
 # ----------------------------------------------------------------------------------

@@ -35,7 +35,8 @@ from cola.linalg.unary.unary import LanczosUnary  # noqa: E402
 from cola.ops import operators as rops  # noqa: E402
 
 from tests import problems as pb  # noqa: E402
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS  # noqa: E402
+from tests.golden_cases import (ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS,  # noqa: E402
+                                PCG_CASES)
 
 assert cola.__file__.startswith("/root/reference"), cola.__file__
 
@@ -211,6 +212,17 @@ def gen_gmres():
     save("solve_gmres_nonsym48_f64", x=cola.linalg.solve(A, P["B"], GMRES(tol=1e-12, max_iters=20)))
 
 
+# --------------------------------------------------------------------------- preconditioned CG
+def gen_pcg():
+    from cola.linalg.preconditioning.preconditioners import NystromPrecond
+    for case, (name, rank, tol, iters) in PCG_CASES.items():
+        P_ = pb.problem(name)
+        A = to_reference(P_["spec"], P_["ann"])
+        Nys = NystromPrecond(A, rank=rank, key=A.xnp.PRNGKey(3))
+        x, info = CG(tol=tol, max_iters=iters, P=Nys)(A, P_["B"])
+        save(case, x=x, errors=info["errors"], iterations=info["iterations"], PB=Nys @ P_["B"], Lambda=Nys.Lambda)
+
+
 # --------------------------------------------------------------------------- SLQ / Hutch / f(A)v
 def gen_stochastic():
     for name, m, vtol in [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2), ("lap24_f64", 40, 0.25)]:
@@ -246,6 +258,7 @@ if __name__ == "__main__":
     gen_lanczos()
     gen_arnoldi()
     gen_gmres()
+    gen_pcg()
     gen_stochastic()
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump(MANIFEST, fh, indent=1, sort_keys=True)

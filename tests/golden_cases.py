@@ -41,3 +41,10 @@ GMRES_CASES = {  # case -> (problem, max_iters, tol, vector?)
     "gmres_lap24_f64": ("lap24_f64", 40, 1e-12, False),
     "gmres_kron465_diag_f64": ("kron465_diag_f64", 25, 1e-12, False),
 }
+
+PCG_CASES = {  # case -> (problem, rank, tol, max_iters)   CG with P = NystromPrecond(A, rank, key=PRNGKey(3))
+    "pcg_dense96_f64": ("dense96_f64", 12, 1e-11, 500),
+    "pcg_dense96_f32": ("dense96_f32", 12, 1e-6, 500),
+    "pcg_lap24_f64": ("lap24_f64", 24, 1e-9, 1000),
+    "pcg_kron465_diag_f64": ("kron465_diag_f64", 10, 1e-10, 200),
+}

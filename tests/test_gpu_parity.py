@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from tests import problems as pb
-from tests.golden_cases import GMRES_CASES, ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+from tests.golden_cases import GMRES_CASES, PCG_CASES, ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
 
 pytestmark = pytest.mark.gpu
 
@@ -144,6 +144,63 @@ def test_cg_edge_cases(cb):
     xo, _, _, info_o = ko.cg(pb.to_oracle(P["spec"]), B, tol=1e-9, max_iters=300)
     assert abs(info["iterations"] - info_o["iterations"]) <= 1 and rel(x, xo) < 1e-7
     assert float(x[:, 1].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("case", sorted(PCG_CASES))
+def test_pcg_nystrom_vs_oracle_and_golden(case, golden, cb):
+    """Preconditioned CG: NystromPrecond built on the device (library QR/Cholesky/SVD of the
+    n x r sketch, as in the reference) and applied through the operator plan inside the CG loop."""
+    from oracle import krylov_oracle as ko
+    name, rank, tol, iters = PCG_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    Ao = pb.to_oracle(P["spec"])
+    saved = cb.rng.PROBE_DEVICE
+    cb.rng.PROBE_DEVICE = "cpu"                      # draw the sketch on the CPU generator, like the oracle / golden run
+    try:
+        Nys = cb.linalg.NystromPrecond(A, rank=rank, key=cb.rng.PRNGKey(3))
+    finally:
+        cb.rng.PROBE_DEVICE = saved
+    Nys_o = ko.NystromPrecondOp(Ao, rank, key=ko.PRNGKey(3))
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    B = P["B"].to(DEV)
+    assert rel(Nys.Lambda, Nys_o.Lambda) < 50 * t and rel(Nys.Lambda, g["Lambda"]) < 50 * t
+    assert rel(Nys @ B, Nys_o.matmat(P["B"])) < 50 * t and rel(Nys @ B, g["PB"]) < 50 * t
+    dots = torch.zeros(B.shape[1], dtype=torch.float64, device=DEV)
+    Z = torch.empty_like(B)
+    Nys.matmat_into(B, Z, dots=dots)                # <b, P b> fused into the apply of a Product chain + shift
+    assert rel(dots, (B.double() * Z.double()).sum(0)) < (1e-6 if P["dtype"] == torch.float32 else 1e-12)
+    x, info = cb.linalg.CG(tol=tol, max_iters=iters, P=Nys)(A, B)
+    xo, _, _, info_o = ko.cg(Ao, P["B"], tol=tol, max_iters=iters, P=Nys_o)
+    assert abs(info["iterations"] - info_o["iterations"]) <= 1 and abs(info["iterations"] - int(g["iterations"])) <= 1
+    tol_x = 2e-5 if P["dtype"] == torch.float32 else 1e-8
+    assert rel(x, xo) < tol_x and rel(x, g["x"]) < tol_x
+    # leading residual norms (the sketch factorizations run in cuSOLVER here and LAPACK there; CG amplifies the ulps)
+    m = min(len(info["errors"]), len(info_o["errors"]), 8)
+    assert rel(info["errors"][:m], info_o["errors"][:m]) < (5e-3 if P["dtype"] == torch.float32 else 1e-8)
+    # preconditioning must pay for itself on these problems
+    _, info_plain = cb.linalg.CG(tol=tol, max_iters=iters)(A, B)
+    assert info["iterations"] <= info_plain["iterations"]
+
+
+def test_product_chain_epilogue(cb):
+    """shift / diagonal / fused <x, y> dots on an operator whose only core is a Product chain: the epilogue must see
+    the operator's input, not the chain's intermediate."""
+    g = torch.Generator().manual_seed(2)
+    M = torch.randn(40, 24, dtype=torch.float64, generator=g).to(DEV)
+    d = (torch.rand(40, dtype=torch.float64, generator=g) + 0.5).to(DEV)
+    A = cb.PSD(cb.ops.Product(cb.ops.Dense(M), cb.ops.Dense(M.T.contiguous())) + cb.ops.Diagonal(d)
+               + 0.3 * cb.ops.I_like(cb.ops.Dense(M @ M.T)))
+    X = torch.randn(40, 5, dtype=torch.float64, generator=g).to(DEV)
+    ref = M @ (M.T @ X) + d[:, None] * X + 0.3 * X
+    assert rel(A @ X, ref) < 1e-13
+    dots = torch.zeros(5, dtype=torch.float64, device=DEV)
+    Y = torch.empty_like(X)
+    A.matmat_into(X, Y, dots=dots)
+    assert rel(Y, ref) < 1e-13 and rel(dots, (X * ref).sum(0)) < 1e-13
+    x, info = cb.linalg.CG(tol=1e-12, max_iters=200)(A, X)
+    assert rel(A @ x, X) < 1e-10
 
 
 def test_cg_graph_workspace_reuse(cb):

@@ -9,7 +9,7 @@ import torch
 
 from oracle import krylov_oracle as ko
 from tests import problems as pb
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, PCG_CASES
 
 
 def rel(a, b):
@@ -126,6 +126,24 @@ def test_arnoldi_eigs(golden):
     lam, V, info = ko.arnoldi_eigs(A, P["B"][:, 0].contiguous(), 48, 1e-12)
     mags = np.sort(np.abs(lam.numpy()))
     assert rel(mags, golden("eig_arnoldi_nonsym48_f64")["eigvals_sorted_abs"]) < 1e-9
+
+
+@pytest.mark.parametrize("case", sorted(PCG_CASES))
+def test_pcg_nystrom(case, golden):
+    """CG with P = NystromPrecond(A, rank, key=PRNGKey(3)) (preconditioners.py:97-157, cg.py:94-170)."""
+    name, rank, tol, iters = PCG_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    Nys = ko.NystromPrecondOp(A, rank, key=ko.PRNGKey(3))
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    assert rel(Nys.Lambda, g["Lambda"]) < 50 * t
+    assert rel(Nys.matmat(P["B"]), g["PB"]) < 50 * t
+    x, r, k, info = ko.cg(A, P["B"], tol=tol, max_iters=iters, P=Nys)
+    assert info["iterations"] == int(g["iterations"])
+    assert rel(x, g["x"]) < 100 * t
+    m = min(len(info["errors"]), 20)
+    assert rel(info["errors"][:m], g["errors"][:m]) < 1e3 * t
 
 
 @pytest.mark.parametrize("case", sorted(GMRES_CASES))
