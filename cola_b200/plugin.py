@@ -13,7 +13,7 @@ The reference resolves its Krylov loops by module attribute at call time (`cg.py
 
 to adapters that take the B200 path when the operator lives on a CUDA device in float32/float64 and its tree
 converts (`from_cola`), and call the saved reference function otherwise (CPU, complex, JAX/NumPy backends,
-non-identity preconditioners, off-diagonal Hutchinson, exotic operators).  The adapters translate between the
+preconditioners that do not convert, off-diagonal Hutchinson, exotic operators).  The adapters translate between the
 reference's state layouts and this package's: the reference keeps the Krylov basis as (b, n, m+2) with the
 vector index fastest, the kernels as (m+2, n, b); what is handed back is a strided view with the reference's
 logical shape.  `uninstall()` restores everything.
@@ -92,6 +92,11 @@ def from_cola(A, cola):
         M = bops.Product(*[from_cola(m, cola) for m in A.Ms])
     elif isinstance(A, R.Transpose):
         M = from_cola(A.A, cola).T
+    elif type(A).__name__ in ("NystromPrecond", "NystromPrecondLazy", "AdaNysPrecond") and hasattr(A, "subspace_scaling"):
+        # preconditioners.py:128-130: U diag(s) U^T + I as a two-core chain plus the identity
+        U = A.U.contiguous()
+        M = bops.Sum(bops.Product(bops.Dense(U), bops.Dense((A.subspace_scaling * U.T).contiguous())),
+                     bops.Identity(tuple(A.shape), A.dtype))
     elif unary is not None and isinstance(A, unary.LanczosUnary):
         M = b_stoch.LanczosUnary(from_cola(A.A, cola), A.f, **{k: v for k, v in getattr(A, "kwargs", {}).items()
                                                                 if k in ("max_iters", "tol", "pbar")})
@@ -120,10 +125,16 @@ def _mirror_or_none(A, cola):
 # ------------------------------------------------------------------------------------------------ adapters
 def _make_run_batched_cg(cola, ref):
     def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar):
-        M = _mirror_or_none(A, cola) if isinstance(preconditioner, cola.ops.Identity) else None
+        M = _mirror_or_none(A, cola)
         if M is None:
             return ref(A, b, x0, max_iters, tol, preconditioner, pbar)
-        return b_cg.run_batched_cg(M, b, x0, max_iters, tol, bops.I_like(M), pbar)
+        if isinstance(preconditioner, cola.ops.Identity):
+            P = bops.I_like(M)
+        else:
+            P = _mirror_or_none(preconditioner, cola)       # e.g. NystromPrecond -> U diag(s) U^T + I in the plan
+            if P is None:
+                return ref(A, b, x0, max_iters, tol, preconditioner, pbar)
+        return b_cg.run_batched_cg(M, b, x0, max_iters, tol, P, pbar)
     return run_batched_cg
 
 

@@ -119,6 +119,13 @@ def test_from_cola_tree_mapping():
     assert isinstance(S, bops.Sparse) and S.nnz == 5 and S.max_row_nnz == 2
     assert torch.equal(S.indptr, S_ref.A.crow_indices().to(torch.int32))
     assert torch.equal(S.data, S_ref.A.values())
+    from importlib import import_module as im
+    Nys = im("cola.linalg.preconditioning.preconditioners").NystromPrecond(A, rank=4, key=A.xnp.PRNGKey(1))
+    Pm = plugin.from_cola(Nys, cola)
+    assert isinstance(Pm, bops.Sum) and isinstance(Pm.Ms[0], bops.Product) and isinstance(Pm.Ms[1], bops.Identity)
+    Um, SUt = Pm.Ms[0].Ms[0].A, Pm.Ms[0].Ms[1].A
+    X = torch.randn(12, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    assert torch.allclose(Um @ (SUt @ X) + X, Nys @ X, atol=1e-12)
     with pytest.raises(plugin.NotConvertible):
         plugin.from_cola(R.Dense(K1.to(torch.complex64)), cola)
     with pytest.raises(plugin.NotConvertible):
@@ -126,7 +133,8 @@ def test_from_cola_tree_mapping():
 
 
 def _standin_cg(M, b, x0, max_iters, tol, P, pbar=False):
-    x, r, k, info = ko.cg(mirror_to_oracle(M), b, x0=x0, tol=tol, max_iters=max_iters)
+    Po = None if isinstance(P, bops.Identity) else mirror_to_oracle(P)
+    x, r, k, info = ko.cg(mirror_to_oracle(M), b, x0=x0, tol=tol, max_iters=max_iters, P=Po)
     return x, r, k, info
 
 
@@ -158,6 +166,8 @@ def test_adapter_layouts_against_reference(installed, monkeypatch):
     Qa_ref, Ha_ref, ia_ref = ref_arnoldi(A, v, 7, 1e-12)
     key = A.xnp.PRNGKey(5)
     slq_ref = stochastic_lanczos_quad(A, torch.log, max_iters=10, tol=1e-9, vtol=0.25, key=key)
+    Nys = im("cola.linalg.preconditioning.preconditioners").NystromPrecond(A, rank=4, key=A.xnp.PRNGKey(1))
+    xp_ref, infop_ref = CG(tol=1e-9, max_iters=40, P=Nys)(A, B)
 
     plugin.install(cola)
     plugin.FORCE_FAST_PATH = True
@@ -173,6 +183,8 @@ def test_adapter_layouts_against_reference(installed, monkeypatch):
     x, info = CG(tol=1e-9, max_iters=40)(A, B)
     assert torch.allclose(x, x_ref, rtol=1e-10, atol=1e-12)
     assert info["iterations"] == info_ref["iterations"]
+    xp, infop = CG(tol=1e-9, max_iters=40, P=Nys)(A, B)             # preconditioner converted by from_cola
+    assert torch.allclose(xp, xp_ref, rtol=1e-9, atol=1e-11) and infop["iterations"] == infop_ref["iterations"]
     Ql, Tl, il = ref_lanczos(A, v, 8, 1e-12)
     assert Ql.to_dense().shape == Ql_ref.to_dense().shape
     assert torch.allclose(Ql.to_dense(), Ql_ref.to_dense(), atol=1e-10)
