@@ -287,6 +287,88 @@ static void launch_big(const McArgs<float>& a, cudaStream_t st) {
 }
 static void launch_big(const McArgs<double>&, cudaStream_t) {}
 
+// ---------------------------------------------------------------------------------------------------
+// Short-and-wide factors (d_out <= 64, d_in huge, pre = 1): the U^T r product of a Nystrom preconditioner
+// (preconditioners.py:128-130), r x n times n x k.  Tiling the output gives one tile; instead the K range is split
+// over the whole grid, every CTA accumulates a full d_out x post partial in registers (4 x 16 per thread) and adds
+// it to the zeroed output with one atomic per element.  Summation order across CTAs is not fixed, so results are
+// reproducible to rounding, not bitwise.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SK_M = 64, SK_N = 256, SK_K = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(MC_THREADS) mc_zero_kernel(T* out, int64_t count, const int32_t* gate) {
+  if (gate != nullptr && *gate != 0) return;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (T)0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(MC_THREADS) mc_splitk_kernel(McArgs<T> a, int64_t k_per_cta) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  __shared__ T As[SK_K][SK_M + 1];
+  __shared__ T Bs[SK_K][SK_N];
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int d_out = (int)a.d_out, post = (int)a.post;
+  const int64_t k_begin = (int64_t)blockIdx.x * k_per_cta;
+  const int64_t k_end = min(a.d_in, k_begin + k_per_cta);
+  if (k_begin >= k_end) return;
+  T acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = (T)0;
+  const int tn = (post + 15) / 16;                      // live column groups of this thread (<= 16)
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += SK_K) {
+#pragma unroll
+    for (int e = 0; e < (SK_M * SK_K) / MC_THREADS; ++e) {
+      const int idx = tid + e * MC_THREADS;
+      const int kk = idx % SK_K, mm = idx / SK_K;
+      const int64_t gk = k0 + kk;
+      As[kk][mm] = (mm < d_out && gk < k_end) ? a.M[(int64_t)mm * a.ldm + gk] : (T)0;
+    }
+    for (int idx = tid; idx < SK_K * post; idx += MC_THREADS) {
+      const int kk = idx / post, nn = idx - kk * post;
+      const int64_t gk = k0 + kk;
+      Bs[kk][nn] = gk < k_end ? a.in[gk * a.post + nn] : (T)0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SK_K; ++kk) {
+      T av[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < tn) {
+          const int q = tx + 16 * j;
+          const T bv = q < post ? Bs[kk][q] : (T)0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i][j] += av[i] * bv;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ga = ty + 16 * i;
+    if (ga >= d_out) continue;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int q = tx + 16 * j;
+      if (j < tn && q < post) atomicAdd(a.out + (int64_t)ga * a.post + q, a.alpha * acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+static bool splitk_ok(const McArgs<T>& a) {
+  const bool epi = (a.shift != (T)0) || a.diag || a.dots || a.accumulate;
+  return !epi && a.pre == 1 && a.d_out <= SK_M && a.post <= SK_N && a.d_in >= 8192 && a.d_in >= 64 * a.d_out &&
+         getenv("COLA_MC_NO_SPLITK") == nullptr;
+}
+
 template <typename T>
 int mode_contract(const T* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t pre, int64_t post, const T* in,
                   T* out, T alpha, T shift, const T* diag, const T* epi_x, int accumulate, double* dots,
@@ -309,6 +391,16 @@ int mode_contract(const T* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t 
   if (big_ok(a)) {
     launch_big(a, st);
     return cuda_status("mode_contract(big)");
+  }
+  if (splitk_ok(a)) {
+    const int64_t count = d_out * post;
+    mc_zero_kernel<T><<<(unsigned)((count + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(out, count, gate);
+    int64_t ctas = (int64_t)sm_count() * 4;
+    int64_t k_per_cta = (d_in + ctas - 1) / ctas;
+    k_per_cta = (k_per_cta + SK_K - 1) / SK_K * SK_K;
+    ctas = (d_in + k_per_cta - 1) / k_per_cta;
+    mc_splitk_kernel<T><<<(unsigned)ctas, MC_THREADS, 0, st>>>(a, k_per_cta);
+    return cuda_status("mode_contract(split-k)");
   }
   const int64_t na = (d_out + BM - 1) / BM, nq = (post + BN - 1) / BN;
   COLA_REQUIRE(!dots || nq <= 65535, "mode_contract: dots with post > 4M columns unsupported");

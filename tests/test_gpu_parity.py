@@ -184,6 +184,48 @@ def test_pcg_nystrom_vs_oracle_and_golden(case, golden, cb):
     assert info["iterations"] <= info_plain["iterations"]
 
 
+def test_mode_contract_split_k(cb):
+    """Short-and-wide factors (the U^T r product of a Nystrom preconditioner): K split over the grid with atomics."""
+    be = cb.backend
+    g = torch.Generator().manual_seed(21)
+    for dt, t in [(torch.float32, 2e-6), (torch.float64, 1e-13)]:
+        for (d_out, d_in, post) in [(24, 20000, 40), (64, 9001, 256), (1, 8192, 1), (33, 70001, 7)]:
+            M = (torch.randn(d_out, d_in, dtype=dt, generator=g) / d_in**0.5).to(DEV)
+            X = torch.randn(d_in, post, dtype=dt, generator=g).to(DEV)
+            Y = torch.full((d_out, post), 7.0, dtype=dt, device=DEV)          # must be overwritten, not accumulated
+            be.mode_contract(M, d_out, d_in, 1, post, X, Y, alpha=0.5)
+            assert rel(Y, 0.5 * (M.double() @ X.double())) < t, (dt, d_out, d_in, post)
+    gate = torch.ones(1, dtype=torch.int32, device=DEV)
+    Y = torch.full((24, 40), 7.0, device=DEV)
+    M = torch.randn(24, 20000, generator=g).to(DEV); X = torch.randn(20000, 40, generator=g).to(DEV)
+    be.mode_contract(M, 24, 20000, 1, 40, X, Y, gate=gate)
+    assert float((Y - 7.0).abs().max()) == 0.0                                # gated launch leaves the output alone
+
+
+def test_pcg_nystrom_larger_grid(cb):
+    """PCG on a 128x128 grid Laplacian + 0.05 I (n = 16384): the U^T r product takes the split-K path."""
+    from oracle import krylov_oracle as ko
+    vals, rows, cols, shape = pb.laplacian_2d_coo(128, torch.float64)
+    n = shape[0]
+    S = cb.ops.Sparse(vals.to(DEV), rows.to(DEV), cols.to(DEV), shape)
+    A = cb.PSD(S + 0.05 * cb.ops.I_like(S))
+    Ao = ko.SumOp(ko.SparseOp(vals, rows, cols, shape), ko.ScaledIdentityOp(0.05, n, torch.float64))
+    B = pb.randn_np((n, 4), torch.float64, 12)
+    saved = cb.rng.PROBE_DEVICE
+    cb.rng.PROBE_DEVICE = "cpu"
+    try:
+        Nys = cb.linalg.NystromPrecond(A, rank=40, mu=1e-4, key=cb.rng.PRNGKey(9))
+    finally:
+        cb.rng.PROBE_DEVICE = saved
+    Nys_o = ko.NystromPrecondOp(Ao, 40, mu=1e-4, key=ko.PRNGKey(9))
+    assert rel(Nys @ B.to(DEV), Nys_o.matmat(B)) < 1e-9
+    x, info = cb.linalg.CG(tol=1e-8, max_iters=2000, P=Nys)(A, B.to(DEV))
+    xo, _, _, info_o = ko.cg(Ao, B, tol=1e-8, max_iters=2000, P=Nys_o)
+    assert abs(info["iterations"] - info_o["iterations"]) <= 2
+    assert rel(x, xo) < 1e-6
+    assert rel(A @ x, B) < 1e-6
+
+
 def test_product_chain_epilogue(cb):
     """shift / diagonal / fused <x, y> dots on an operator whose only core is a Product chain: the epilogue must see
     the operator's input, not the chain's intermediate."""
