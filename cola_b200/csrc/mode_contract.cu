@@ -294,7 +294,7 @@ static void launch_big(const McArgs<double>&, cudaStream_t) {}
 // it to the zeroed output with one atomic per element.  Summation order across CTAs is not fixed, so results are
 // reproducible to rounding, not bitwise.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SK_M = 64, SK_N = 256, SK_K = 16;
+constexpr int SK_M = 64, SK_N = 256;
 
 template <typename T>
 __global__ void __launch_bounds__(MC_THREADS) mc_zero_kernel(T* out, int64_t count, const int32_t* gate) {
@@ -303,61 +303,112 @@ __global__ void __launch_bounds__(MC_THREADS) mc_zero_kernel(T* out, int64_t cou
     out[i] = (T)0;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(MC_THREADS) mc_splitk_kernel(McArgs<T> a, int64_t k_per_cta) {
+// Thread tiles: 4 output rows x VEC columns (one 16-byte vector), tile t = (row group t / QG, column group t % QG);
+// a thread owns tiles t = slot, slot + MC_THREADS, ... and -- when there are fewer tiles than threads -- the thread
+// groups split the k rows of a slab between them (partials meet in the atomics anyway).  Per k a thread issues one
+// or two 16-byte shared loads per operand for 4 x VEC FMAs.
+constexpr int SK_BK = 32;     // k rows staged per step
+constexpr int SK_NT = 4;      // tiles per thread (64 x 256 fp32 outputs = 1024 tiles)
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(MC_THREADS, 2) mc_splitk_kernel(McArgs<T> a, int64_t k_per_cta, int AG, int QG) {
   if (a.gate != nullptr && *a.gate != 0) return;
-  __shared__ T As[SK_K][SK_M + 1];
-  __shared__ T Bs[SK_K][SK_N];
-  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  extern __shared__ __align__(16) unsigned char sk_smem[];
+  const int AP = AG * 4, QP = QG * VEC;
+  T* As = reinterpret_cast<T*>(sk_smem);                 // [SK_BK][AP]   As[kk][m] = M[m][k0 + kk]
+  T* Bs = As + SK_BK * AP;                               // [SK_BK][QP]
+  const int tid = threadIdx.x;
   const int d_out = (int)a.d_out, post = (int)a.post;
+  const int tiles = AG * QG;
+  const int groups = tiles >= MC_THREADS ? 1 : MC_THREADS / tiles;     // k-splitting thread groups
+  const int grp = tiles >= MC_THREADS ? 0 : tid / tiles;
+  const int slot = tiles >= MC_THREADS ? tid : tid - grp * tiles;
+  const bool live = grp < groups;
   const int64_t k_begin = (int64_t)blockIdx.x * k_per_cta;
   const int64_t k_end = min(a.d_in, k_begin + k_per_cta);
   if (k_begin >= k_end) return;
-  T acc[4][16];
+  T acc[SK_NT][4][VEC];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int t = 0; t < SK_NT; ++t)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[i][j] = (T)0;
-  const int tn = (post + 15) / 16;                      // live column groups of this thread (<= 16)
-  for (int64_t k0 = k_begin; k0 < k_end; k0 += SK_K) {
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int e = 0; e < (SK_M * SK_K) / MC_THREADS; ++e) {
-      const int idx = tid + e * MC_THREADS;
-      const int kk = idx % SK_K, mm = idx / SK_K;
+      for (int v = 0; v < VEC; ++v) acc[t][i][v] = (T)0;
+  const bool vec_in = (post % VEC == 0) && ((reinterpret_cast<uintptr_t>(a.in) % 16) == 0);
+  for (int64_t k0 = k_begin; k0 < k_end; k0 += SK_BK) {
+    // factor slab: AP x SK_BK, read along k (contiguous in M), stored transposed
+    for (int idx = tid; idx < AP * SK_BK; idx += MC_THREADS) {
+      const int kk = idx % SK_BK, mm = idx / SK_BK;
       const int64_t gk = k0 + kk;
-      As[kk][mm] = (mm < d_out && gk < k_end) ? a.M[(int64_t)mm * a.ldm + gk] : (T)0;
+      As[kk * AP + mm] = (mm < d_out && gk < k_end) ? a.M[(int64_t)mm * a.ldm + gk] : (T)0;
     }
-    for (int idx = tid; idx < SK_K * post; idx += MC_THREADS) {
-      const int kk = idx / post, nn = idx - kk * post;
-      const int64_t gk = k0 + kk;
-      Bs[kk][nn] = gk < k_end ? a.in[gk * a.post + nn] : (T)0;
+    if (vec_in) {
+      for (int idx = tid; idx < SK_BK * QG; idx += MC_THREADS) {
+        const int kk = idx / QG, qg = idx - kk * QG;
+        const int64_t gk = k0 + kk;
+        Vec<T, VEC> x;
+        if (gk < k_end) {
+          x = ldg_stream<T, VEC>(a.in + gk * a.post + (int64_t)qg * VEC);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) x.v[v] = (T)0;
+        }
+        *reinterpret_cast<Vec<T, VEC>*>(Bs + kk * QP + qg * VEC) = x;
+      }
+    } else {
+      for (int idx = tid; idx < SK_BK * QP; idx += MC_THREADS) {
+        const int kk = idx / QP, nn = idx - kk * QP;
+        const int64_t gk = k0 + kk;
+        Bs[kk * QP + nn] = (gk < k_end && nn < post) ? a.in[gk * a.post + nn] : (T)0;
+      }
     }
     __syncthreads();
+    if (live) {
 #pragma unroll
-    for (int kk = 0; kk < SK_K; ++kk) {
-      T av[4];
+      for (int t = 0; t < SK_NT; ++t) {
+        const int tile = slot + t * MC_THREADS;
+        if (tile < tiles) {
+          const int ag = tile / QG, qg = tile - ag * QG;
+          const T* ap = As + ag * 4;
+          const T* bp = Bs + qg * VEC;
+#pragma unroll 4
+          for (int kk = grp; kk < SK_BK; kk += groups) {
+            const Vec<T, VEC> bv = *reinterpret_cast<const Vec<T, VEC>*>(bp + kk * QP);
+            T av[4];
+            if constexpr (sizeof(T) == 4) {
+              const Vec<T, 4> a4 = *reinterpret_cast<const Vec<T, 4>*>(ap + kk * AP);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty + 16 * i];
+              for (int i = 0; i < 4; ++i) av[i] = a4.v[i];
+            } else {
+              const Vec<T, 2> a0 = *reinterpret_cast<const Vec<T, 2>*>(ap + kk * AP);
+              const Vec<T, 2> a1 = *reinterpret_cast<const Vec<T, 2>*>(ap + kk * AP + 2);
+              av[0] = a0.v[0]; av[1] = a0.v[1]; av[2] = a1.v[0]; av[3] = a1.v[1];
+            }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < tn) {
-          const int q = tx + 16 * j;
-          const T bv = q < post ? Bs[kk][q] : (T)0;
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i][j] += av[i] * bv;
+              for (int v = 0; v < VEC; ++v) acc[t][i][v] += av[i] * bv.v[v];
+          }
         }
       }
     }
     __syncthreads();
   }
+  if (!live) return;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ga = ty + 16 * i;
-    if (ga >= d_out) continue;
+  for (int t = 0; t < SK_NT; ++t) {
+    const int tile = slot + t * MC_THREADS;
+    if (tile >= tiles) continue;
+    const int ag = tile / QG, qg = tile - ag * QG;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int q = tx + 16 * j;
-      if (j < tn && q < post) atomicAdd(a.out + (int64_t)ga * a.post + q, a.alpha * acc[i][j]);
+    for (int i = 0; i < 4; ++i) {
+      const int ga = ag * 4 + i;
+      if (ga >= d_out) continue;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const int q = qg * VEC + v;
+        if (q < post) atomicAdd(a.out + (int64_t)ga * a.post + q, a.alpha * acc[t][i][v]);
+      }
     }
   }
 }
@@ -365,7 +416,9 @@ __global__ void __launch_bounds__(MC_THREADS) mc_splitk_kernel(McArgs<T> a, int6
 template <typename T>
 static bool splitk_ok(const McArgs<T>& a) {
   const bool epi = (a.shift != (T)0) || a.diag || a.dots || a.accumulate;
-  return !epi && a.pre == 1 && a.d_out <= SK_M && a.post <= SK_N && a.d_in >= 8192 && a.d_in >= 64 * a.d_out &&
+  const int64_t tiles = ((a.d_out + 3) / 4) * ((a.post + 16 / (int64_t)sizeof(T) - 1) / (16 / (int64_t)sizeof(T)));
+  return !epi && a.pre == 1 && a.d_out <= SK_M && a.post <= SK_N && tiles <= (int64_t)SK_NT * MC_THREADS &&
+         a.d_in >= 8192 && a.d_in >= 64 * a.d_out &&
          getenv("COLA_MC_NO_SPLITK") == nullptr;
 }
 
@@ -397,9 +450,14 @@ int mode_contract(const T* M, int64_t ldm, int64_t d_out, int64_t d_in, int64_t 
     mc_zero_kernel<T><<<(unsigned)((count + MC_THREADS - 1) / MC_THREADS), MC_THREADS, 0, st>>>(out, count, gate);
     int64_t ctas = (int64_t)sm_count() * 4;
     int64_t k_per_cta = (d_in + ctas - 1) / ctas;
-    k_per_cta = (k_per_cta + SK_K - 1) / SK_K * SK_K;
+    k_per_cta = (k_per_cta + SK_BK - 1) / SK_BK * SK_BK;
     ctas = (d_in + k_per_cta - 1) / k_per_cta;
-    mc_splitk_kernel<T><<<(unsigned)ctas, MC_THREADS, 0, st>>>(a, k_per_cta);
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const int AG = (int)((d_out + 3) / 4), QG = (int)((post + VEC - 1) / VEC);
+    const size_t smem = (size_t)SK_BK * (AG * 4 + QG * VEC) * sizeof(T);
+    auto kern = mc_splitk_kernel<T, VEC>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)ctas, MC_THREADS, smem, st>>>(a, k_per_cta, AG, QG);
     return cuda_status("mode_contract(split-k)");
   }
   const int64_t na = (d_out + BM - 1) / BM, nq = (post + BN - 1) / BN;
