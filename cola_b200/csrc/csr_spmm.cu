@@ -313,7 +313,14 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
               : nzl == 2 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 2>                                      \
                          : csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 1>;                                     \
     int per_sm = 0;                                                                                           \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    /* raise the dynamic shared-memory limit once per kernel variant: the call is not allowed while a stream   \
+       is being captured (the CG loop captures its iteration batches), and the first eager batch sets it */     \
+    static int attr_smem[4] = {0, 0, 0, 0};                                                                   \
+    const int vi = nzl == 8 ? 3 : nzl == 4 ? 2 : nzl == 2 ? 1 : 0;                                            \
+    if (smem > 48 * 1024 && (int)smem > attr_smem[vi]) {                                                      \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+      attr_smem[vi] = (int)smem;                                                                              \
+    }                                                                                                         \
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCsrThreads, smem);                          \
     if (per_sm < 1) per_sm = 1;                                                                               \
     int64_t grid = (int64_t)sm_count() * per_sm; /* persistent: whole waves of resident CTAs */               \

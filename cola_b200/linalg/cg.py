@@ -16,6 +16,7 @@ What is different underneath (see DESIGN.md "CG"):
   * the per-iteration residual norms are kept on the device (gamma trace) and `info['errors']` is rebuilt
     from them once at the end.
 """
+import gc
 import time
 from dataclasses import dataclass
 from typing import Any
@@ -155,8 +156,18 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
             # iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
             # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                enqueue(CHECK_EVERY)
+            # No garbage collection while the stream is capturing: a cyclic collection can finalise another
+            # operator's cached CUDAGraph (cudaGraphExecDestroy / cudaFree), which invalidates the capture in progress
+            # (seen as cudaErrorStreamCaptureInvalidated, depending on test order).  torch.cuda.graph() itself runs
+            # gc.collect() just before capture begins.
+            gc_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(graph):
+                    enqueue(CHECK_EVERY)
+            finally:
+                if gc_on:
+                    gc.enable()
             ws["graph"], ws["token"] = graph, A.plan().graph_token()
             # capture does not execute: fall through to the replay below
         if graph is not None:
