@@ -106,3 +106,36 @@ def test_rng_matches_reference_key_chain():
     z1 = cb.rng.randn(5, 3, dtype=torch.float32, device="cpu", key=cb.rng.PRNGKey(7))
     z2 = ko.keyed_randn(5, 3, dtype=torch.float32, key=ko.PRNGKey(7))
     assert torch.equal(z1, z2)
+
+
+def test_probe_blocks_are_split_into_vector_friendly_widths():
+    """100 Hutchinson probes -> 64 + 32 + 4 (stochastic.friendly_chunks): every block a power of two no wider than
+    the chunk limit, tails narrower than one 16-byte vector as a single block, ranges contiguous from `start`."""
+    from cola_b200.linalg.stochastic import friendly_chunks
+    assert friendly_chunks(100, 96, torch.float32) == [(0, 64), (64, 96), (96, 100)]
+    assert friendly_chunks(1024, 64, torch.float32) == [(64 * i, 64 * (i + 1)) for i in range(16)]
+    assert friendly_chunks(24, 64, torch.float32, start=12) == [(12, 28), (28, 36)]
+    assert friendly_chunks(3, 64, torch.float32) == [(0, 3)]
+    assert friendly_chunks(7, 64, torch.float64) == [(0, 4), (4, 6), (6, 7)]
+    for k, cb_ in [(1, 1), (37, 8), (513, 128), (130, 64)]:
+        ch = friendly_chunks(k, cb_, torch.float32)
+        assert ch[0][0] == 0 and ch[-1][1] == k and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+        assert all(c1 - c0 <= max(cb_, 3) for c0, c1 in ch)
+
+
+def test_sparse_from_csr_wraps_arrays_as_they_are():
+    indptr = torch.tensor([0, 2, 3, 6], dtype=torch.int64)
+    indices = torch.tensor([3, 1, 3, 2, 0, 1], dtype=torch.int64)          # deliberately unsorted inside rows
+    data = torch.tensor([5., 2., 3., 6., 1., 4.])
+    S = ops.Sparse.from_csr(indptr, indices, data, (3, 4))
+    assert S.indptr.dtype == torch.int32 and S.indices.tolist() == [3, 1, 3, 2, 0, 1] and S.data is not None
+    assert S.nnz == 6 and S.max_row_nnz == 3 and S.row_indices.tolist() == [0, 0, 1, 2, 2, 2]
+    assert S.shape == (3, 4) and S.dtype == torch.float32
+
+
+def test_preconditioned_cg_and_gmres_are_cuda_only():
+    A = cb.PSD(ops.Dense(torch.eye(4)))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        cb.linalg.GMRES(max_iters=3)(A, torch.ones(4, 2))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        cb.linalg.CG(P=ops.Diagonal(torch.ones(4)))(A, torch.ones(4, 2))
