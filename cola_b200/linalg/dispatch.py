@@ -17,6 +17,7 @@ from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
 from .arnoldi import arnoldi, arnoldi_eigs
 from .cg import CG
 from .gmres import GMRES
+from .power_iteration import PowerIteration
 from .lanczos import lanczos, lanczos_eigs
 from .stochastic import Hutch, LanczosUnary, hutchinson_diag_estimate
 
@@ -150,15 +151,27 @@ def get_slice(num, which):
     raise NotImplementedError(f"which={which} is not implemented")
 
 
+def eigmax(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/eig/eigs.py:44-57"""
+    es, _ = eig(A, k=1, which="LM", alg=alg)
+    return es[0]
+
+
 def eig(A: LinearOperator, k: int, which: str = "LM", alg: Algorithm = Auto()):
     """cola/linalg/eig/eigs.py:19-182 (Lanczos, Arnoldi and Auto/Eigh rules)."""
     eig_slice = get_slice(k, which)
     if isinstance(alg, Auto):   # eigs.py:76-96
         small = bool(np.prod(A.shape) <= 1e6)
-        if A.isa(SelfAdjoint):
+        if k == 1 and which == "LM":
+            alg = PowerIteration(**alg.__dict__)
+        elif A.isa(SelfAdjoint):
             alg = Eigh() if small else Lanczos(**alg.__dict__)
         else:
             alg = Arnoldi(**alg.__dict__)
+    if isinstance(alg, PowerIteration):   # eigs.py:136-140
+        assert k == 1 and which == 'LM', "PowerIteration only valid for k=1 and which='LM'"
+        v, emax, _ = alg(A)
+        return emax[None], v[:, None]
     if isinstance(alg, Lanczos):   # eigs.py:106-111
         assert A.isa(SelfAdjoint)
         eig_vals, eig_vecs, _ = lanczos_eigs(A, **alg.__dict__)

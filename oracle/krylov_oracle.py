@@ -431,6 +431,29 @@ def gmres(A, rhs, x0=None, max_iters=100, tol=1e-7):
     return (soln[:, 0] if is_vec else soln), info
 
 
+def power_iteration(A, tol=1e-6, max_iter=1000, key=None):
+    """cola/linalg/eig/power_iteration.py:35-81 (momentum=None) -> (v, eigmax, info)."""
+    key = PRNGKey(42) if key is None else key
+    v = keyed_randn(A.shape[-1], dtype=A.dtype, key=key)
+
+    def body(s):
+        i, v, vprev, eig, eigprev = s
+        p = A.matmat(v.reshape(-1, 1)).reshape(-1)
+        eig, eigprev = v @ p, eig
+        return i + 1, p / torch.linalg.norm(p), v, eig, eigprev
+
+    def err(s):
+        *_, eig, eigprev = s
+        return abs(eigprev - eig) / eig
+
+    def cond(s):
+        return (s[0] < max_iter) & (err(s) > tol)
+
+    eig0, eigprev0 = torch.tensor(10., dtype=A.dtype), torch.tensor(1., dtype=A.dtype)
+    (_, v, _, emax, _), info = _tracked_while(err, cond, body, (0, v, v, eig0, eigprev0))
+    return v, emax, info
+
+
 def arnoldi_eigs(A, start, max_iters=100, tol=1e-7):      # arnoldi.py:35-62
     Q, H, info = arnoldi(A, start, max_iters, tol)
     Q, H = Q[:, :-1], H[:-1]

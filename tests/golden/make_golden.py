@@ -36,7 +36,7 @@ from cola.ops import operators as rops  # noqa: E402
 
 from tests import problems as pb  # noqa: E402
 from tests.golden_cases import (ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS,  # noqa: E402
-                                PCG_CASES)
+                                PCG_CASES, POWER_CASES)
 
 assert cola.__file__.startswith("/root/reference"), cola.__file__
 
@@ -223,6 +223,19 @@ def gen_pcg():
         save(case, x=x, errors=info["errors"], iterations=info["iterations"], PB=Nys @ P_["B"], Lambda=Nys.Lambda)
 
 
+# --------------------------------------------------------------------------- power iteration
+def gen_power():
+    from cola.linalg.eig.power_iteration import PowerIteration
+    for case, (name, tol, iters) in POWER_CASES.items():
+        P_ = pb.problem(name)
+        A = to_reference(P_["spec"], P_["ann"])
+        v, emax, info = PowerIteration(tol=tol, max_iter=iters, key=A.xnp.PRNGKey(11))(A)
+        save(case, v=v, eigmax=emax, errors=info["errors"], iterations=info["iterations"])
+    P_ = pb.problem("dense96_f64")
+    A = to_reference(P_["spec"], P_["ann"])
+    save("eigmax_dense96_f64", eigmax=cola.linalg.eigmax(A, PowerIteration(tol=1e-9, max_iter=400, key=A.xnp.PRNGKey(11))))
+
+
 # --------------------------------------------------------------------------- SLQ / Hutch / f(A)v
 def gen_stochastic():
     for name, m, vtol in [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2), ("lap24_f64", 40, 0.25)]:
@@ -259,6 +272,7 @@ if __name__ == "__main__":
     gen_arnoldi()
     gen_gmres()
     gen_pcg()
+    gen_power()
     gen_stochastic()
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
         json.dump(MANIFEST, fh, indent=1, sort_keys=True)

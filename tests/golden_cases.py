@@ -48,3 +48,10 @@ PCG_CASES = {  # case -> (problem, rank, tol, max_iters)   CG with P = NystromPr
     "pcg_lap24_f64": ("lap24_f64", 24, 1e-9, 1000),
     "pcg_kron465_diag_f64": ("kron465_diag_f64", 10, 1e-10, 200),
 }
+
+POWER_CASES = {  # case -> (problem, tol, max_iter)   power_iteration(A, key=PRNGKey(11))
+    "power_dense96_f64": ("dense96_f64", 1e-9, 400),
+    "power_dense96_f32": ("dense96_f32", 1e-5, 400),
+    "power_kron465_diag_f64": ("kron465_diag_f64", 1e-8, 300),
+    "power_lap24_f64_capped": ("lap24_f64", 1e-12, 25),
+}

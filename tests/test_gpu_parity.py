@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from tests import problems as pb
-from tests.golden_cases import GMRES_CASES, PCG_CASES, ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
+from tests.golden_cases import GMRES_CASES, PCG_CASES, POWER_CASES, ARNOLDI_CASES, CG_CASES, LANCZOS_CASES, MATMAT_PROBLEMS
 
 pytestmark = pytest.mark.gpu
 
@@ -407,6 +407,48 @@ def test_eig_arnoldi(golden, cb):
                                                                 max_iters=48, tol=1e-12))
     mags = np.sort(np.abs(vals.cpu().numpy()))
     assert rel(mags, golden("eig_arnoldi_nonsym48_f64")["eigvals_sorted_abs"]) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------- power iteration (8f item 3)
+@pytest.mark.parametrize("case", sorted(POWER_CASES))
+def test_power_iteration_vs_oracle_and_golden(case, golden, cb):
+    from oracle import krylov_oracle as ko
+    name, tol, iters = POWER_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    saved = cb.rng.PROBE_DEVICE
+    cb.rng.PROBE_DEVICE = "cpu"                      # same start vector as the oracle / golden run
+    try:
+        v, emax, info = cb.linalg.PowerIteration(tol=tol, max_iter=iters, key=cb.rng.PRNGKey(11))(A)
+    finally:
+        cb.rng.PROBE_DEVICE = saved
+    vo, emax_o, info_o = ko.power_iteration(pb.to_oracle(P["spec"]), tol=tol, max_iter=iters, key=ko.PRNGKey(11))
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    # the stop test |eig_prev - eig| / eig > tol can flip on the last ulp near convergence
+    assert abs(info["iterations"] - info_o["iterations"]) <= 1 and abs(info["iterations"] - int(g["iterations"])) <= 1
+    assert abs(float(emax) - float(emax_o)) <= 10 * t * abs(float(emax_o))
+    assert abs(float(emax) - float(g["eigmax"])) <= 10 * t * abs(float(g["eigmax"]))
+    if info["iterations"] == info_o["iterations"]:
+        assert rel(v, vo) < 1e3 * t and rel(v, g["v"]) < 1e3 * t
+    m = min(len(info["errors"]), len(info_o["errors"])) - 3          # the last entries sit at the rounding floor
+    assert rel(info["errors"][:m], info_o["errors"][:m]) < (1e-2 if P["dtype"] == torch.float32 else 1e-5)
+
+
+def test_eigmax_dispatch(golden, cb):
+    P = pb.problem("dense96_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    saved = cb.rng.PROBE_DEVICE
+    cb.rng.PROBE_DEVICE = "cpu"
+    try:
+        e = cb.linalg.eigmax(A, cb.linalg.PowerIteration(tol=1e-9, max_iter=400, key=cb.rng.PRNGKey(11)))
+        vals, vecs = cb.linalg.eig(A, 1, "LM", cb.linalg.PowerIteration(tol=1e-9, max_iter=400, key=cb.rng.PRNGKey(11)))
+    finally:
+        cb.rng.PROBE_DEVICE = saved
+    assert abs(float(e) - float(golden("eigmax_dense96_f64")["eigmax"])) < 1e-9
+    assert vals.shape == (1,) and vecs.shape == (96, 1)
+    with pytest.raises(AssertionError):
+        cb.linalg.eig(A, 2, "LM", cb.linalg.PowerIteration())
 
 
 # ------------------------------------------------------------------------------------------- GMRES (8f item 2)

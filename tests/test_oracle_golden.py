@@ -9,7 +9,7 @@ import torch
 
 from oracle import krylov_oracle as ko
 from tests import problems as pb
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, PCG_CASES
+from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, PCG_CASES, POWER_CASES
 
 
 def rel(a, b):
@@ -144,6 +144,19 @@ def test_pcg_nystrom(case, golden):
     assert rel(x, g["x"]) < 100 * t
     m = min(len(info["errors"]), 20)
     assert rel(info["errors"][:m], g["errors"][:m]) < 1e3 * t
+
+
+@pytest.mark.parametrize("case", sorted(POWER_CASES))
+def test_power_iteration(case, golden):
+    name, tol, iters = POWER_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    v, emax, info = ko.power_iteration(A, tol=tol, max_iter=iters, key=ko.PRNGKey(11))
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    assert info["iterations"] == int(g["iterations"])
+    assert abs(float(emax) - float(g["eigmax"])) <= 10 * t * abs(float(g["eigmax"]))
+    assert rel(v, g["v"]) < 1e3 * t and rel(info["errors"], g["errors"]) < 1e-3
 
 
 @pytest.mark.parametrize("case", sorted(GMRES_CASES))
