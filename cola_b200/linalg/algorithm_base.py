@@ -1,29 +1,41 @@
-"""Algorithm objects (cola/linalg/algorithm_base.py:11-34)."""
-from types import SimpleNamespace
+"""Algorithm objects of the dispatch surface (reference: cola/linalg/algorithm_base.py:11-34).
 
+Three names are part of the interface the Krylov path is called through:
+  Algorithm                marker base of CG / GMRES / Lanczos / Arnoldi / Hutch / PowerIteration / ...
+  Auto(**options)          "pick for me"; its options are forwarded to the algorithm the dispatch rules choose
+                           (`CG(**alg.__dict__)`, inv.py:72-92), so it is nothing but an attribute bag
+  IterativeOperatorWInfo   the lazy inverse returned by `inv(A, CG())` / `inv(A, GMRES())`: applying it runs the
+                           solver on the given right-hand sides and keeps the solver's `info` dict
+"""
 from ..ops import LinearOperator
 
 
 class Algorithm:
-    pass
+    """Marker base class; concrete algorithms are dataclasses whose fields are the solver options."""
 
 
-class Auto(SimpleNamespace, Algorithm):
-    pass
+class Auto(Algorithm):
+    def __init__(self, **options):
+        vars(self).update(options)
+
+    def __repr__(self):
+        return "Auto(" + ", ".join(f"{k}={v!r}" for k, v in vars(self).items()) + ")"
+
+    def __eq__(self, other):
+        return isinstance(other, Auto) and vars(self) == vars(other)
 
 
 class IterativeOperatorWInfo(LinearOperator):
-    """Lazy A^{-1}: `_matmat(X)` runs the solver and stores `info` (algorithm_base.py:16-29)."""
     def __init__(self, A, alg):
-        super().__init__(A.dtype, A.shape)
-        self.A = A
-        self.alg = alg
-        self.info = {}
+        LinearOperator.__init__(self, dtype=A.dtype, shape=A.shape)
+        self.A, self.alg = A, alg
+        self.info = {}              # filled by the most recent application
         self.device = A.device
 
     def _matmat(self, X):
-        Y, self.info = self.alg(self.A, X)
-        return Y
+        solution, info = self.alg(self.A, X)
+        self.info = info
+        return solution
 
     def __str__(self):
-        return f"{self.alg}({str(self.A)})"
+        return "%s(%s)" % (self.alg, self.A)
