@@ -98,12 +98,19 @@ def stream_ptr():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def require_cuda(t, what="operand"):
+    """The single device gate of the package: every loop and every matmat passes its operands through here, and a
+    CPU tensor raises (there is no CPU or eager-torch fallback)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"cola_b200 is a CUDA-only path: {what} is on the CPU (no CPU fallback); "
+                           "move the operator and the operand to a B200 with .to('cuda')")
+
+
 def ptr(t, dtype=None):
     """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
     if t is None:
         return None
-    if not t.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: got a CPU tensor (no CPU fallback)")
+    require_cuda(t, "a kernel operand")
     if not t.is_contiguous():
         raise RuntimeError("cola_b200 kernels need contiguous operands")
     if dtype is not None and t.dtype != dtype:
@@ -113,8 +120,9 @@ def ptr(t, dtype=None):
 
 def off_ptr(t, elem_offset):
     """Pointer to element `elem_offset` of contiguous CUDA tensor t."""
-    if not (t.is_cuda and t.is_contiguous()):
-        raise RuntimeError("cola_b200 kernels need contiguous CUDA operands")
+    require_cuda(t, "a kernel operand")
+    if not t.is_contiguous():
+        raise RuntimeError("cola_b200 kernels need contiguous operands")
     return ctypes.c_void_p(t.data_ptr() + elem_offset * t.element_size())
 
 

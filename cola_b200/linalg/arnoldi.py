@@ -20,8 +20,7 @@ from .lanczos import BatchedDense
 
 def arnoldi_fact(A: LinearOperator, rhs, max_iters, tol, pbar=False):
     """rhs (n, b) on the device -> (Q (m+1, n, b), H (b, m+1, m) in A.dtype, idx, info)."""
-    if not rhs.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: start vectors are on the CPU (no CPU fallback)")
+    be.require_cuda(rhs, "start vectors")
     dt = A.dtype
     rhs = rhs.to(dt).contiguous()
     n, b = rhs.shape

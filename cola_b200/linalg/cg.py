@@ -66,8 +66,7 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     """cola/linalg/inverse/cg.py:94-119 on the device.  b (n,k) -> (x (n,k), r (n,k), k_iters, info)."""
     if not isinstance(preconditioner, Identity):
         return _run_batched_pcg(A, b, x0, max_iters, tol, preconditioner, pbar)
-    if not b.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: right-hand side is on the CPU (no CPU fallback)")
+    be.require_cuda(b, "right-hand side")
     dt = A.dtype
     b = b.to(dt).contiguous()
     n, k = b.shape
@@ -201,8 +200,7 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
     batches between host polls are unchanged.  One deviation: the per-column `has_converged` mask inside the sweeps
     tests gamma = <r, P r> instead of ||r||^2 against 1e-80; both vanish together for a positive definite P, and
     the mask only matters for residuals that are exactly zero."""
-    if not b.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: right-hand side is on the CPU (no CPU fallback)")
+    be.require_cuda(b, "right-hand side")
     assert tuple(P.shape) == tuple(A.shape), "preconditioner shape mismatch"
     dt = A.dtype
     b = b.to(dt).contiguous()

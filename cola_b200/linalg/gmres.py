@@ -52,8 +52,7 @@ def gmres(A: LinearOperator, rhs, x0=None, max_iters=100, tol=1e-7, P=None, use_
 
 def gmres_fwd(A, rhs, x0, max_iters, tol, P=None, pbar=False):
     """cola/linalg/inverse/gmres.py:92-124.  rhs (n, b) -> (soln (n, b), info)."""
-    if not rhs.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: right-hand sides are on the CPU (no CPU fallback)")
+    be.require_cuda(rhs, "right-hand sides")
     dt = A.dtype
     rhs = rhs.to(dt).contiguous()
     n, b = rhs.shape

@@ -32,8 +32,7 @@ class LanczosState:
 
 def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
     """rhs (n, b) on the device.  Mirrors lanczos.py:235-284 (init_lanczos + lanczos_fact)."""
-    if not rhs.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: start vectors are on the CPU (no CPU fallback)")
+    be.require_cuda(rhs, "start vectors")
     dt = A.dtype
     rhs = rhs.to(dt).contiguous()
     n, b = rhs.shape

@@ -38,8 +38,7 @@ def power_iteration(A: LinearOperator, tol=1e-6, max_iter=1000, pbar=False, key=
     key = rng.PRNGKey(42) if key is None else key
     dt = A.dtype
     v = rng.randn(A.shape[-1], dtype=dt, device=A.device, key=key)
-    if not v.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: the operator lives on the CPU (no CPU fallback)")
+    be.require_cuda(v, "the operator")
     v = v.reshape(-1, 1).contiguous()                      # the start vector is NOT normalised (:56)
     p = torch.empty_like(v)
     acc = torch.zeros((2, 1), dtype=torch.float64, device=v.device)   # <v, A v>, ||A v||^2

@@ -206,9 +206,7 @@ class LinearOperator:
 def _as_operand(A, X):
     if not torch.is_tensor(X):
         raise TypeError("operand must be a torch tensor")
-    if not X.is_cuda:
-        raise RuntimeError("cola_b200 is a CUDA-only path: operand is on the CPU (no CPU fallback); "
-                           "move the operator and the operand to a B200 with .to('cuda')")
+    be.require_cuda(X, "operand")
     dt = torch.promote_types(A.dtype, X.dtype)
     if dt != A.dtype:
         raise TypeError(f"operand dtype {X.dtype} does not match operator dtype {A.dtype}")
@@ -694,8 +692,8 @@ class Plan:
         return " + ".join(parts)
 
     def apply(self, X, Y, dots=None, dots_row=None, gate=None):
-        if not (X.is_cuda and Y.is_cuda):
-            raise RuntimeError("cola_b200 is a CUDA-only path (no CPU fallback)")
+        be.require_cuda(X, "operand")
+        be.require_cuda(Y, "result buffer")
         if X.dtype != self.dtype or Y.dtype != self.dtype:
             raise TypeError(f"operand dtype {X.dtype}/{Y.dtype} does not match operator dtype {self.dtype}")
         assert X.shape[0] == self.shape[1] and Y.shape[0] == self.shape[0] and X.shape[1] == Y.shape[1]

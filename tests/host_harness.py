@@ -1,0 +1,201 @@
+"""TEST INFRASTRUCTURE ONLY -- a stand-in for libcola_b200.so's kernels so that the HOST orchestration of the
+Krylov loops (cola_b200/linalg/*.py, the operator plan compiler in cola_b200/ops.py) can be exercised in the
+`-m "not gpu"` suite, in a container without a GPU.
+
+`emulated_kernels()` replaces, for the duration of a `with` block, the tensor-level wrappers of
+cola_b200/backend.py by torch-CPU statements of the semantics written next to each entry point in
+include/cola_b200.h (same argument lists, same fp64 accumulators, same rounding points: coefficients are
+rounded to the path dtype before use, reductions are taken in double), and opens the package's single device
+gate (`backend.require_cuda`).  Nothing under cola_b200/ imports this module, the product has no switch that
+reaches it, and outside the `with` block CPU tensors raise as always
+(tests/test_abi_and_host.py::test_cpu_tensors_raise_no_fallback).  What it checks is loop logic -- stop rules,
+indexing of the accumulator rows, the assembly of T / H / info, chunking, dispatch -- against the golden vectors;
+the kernels themselves are only checked on the GPU (tests/test_gpu_parity.py, through the C ABI).  The CG loop
+drives its control block through raw C entry points and CUDA graphs and is not covered here.
+"""
+import contextlib
+
+import torch
+
+
+def _open(gate):
+    return gate is None or int(gate.reshape(-1)[0]) == 0
+
+
+def _flat(t, numel):
+    return t.reshape(-1)[:numel]
+
+
+def _add_dots(dots, dots_row, k, X, Y):
+    if dots is None:
+        return
+    r = 0 if dots_row is None else int(dots_row.reshape(-1)[0])
+    acc = dots.reshape(-1)
+    acc[r * k:(r + 1) * k] += (X.double() * Y.double()).sum(0)
+
+
+def _epilogue(KX, X, Y, alpha, shift, diag, accumulate, dots, dots_row):
+    """Y = alpha*KX + (shift + diag[i]) X (+Y); dots += <X, Y>."""
+    res = alpha * KX
+    if shift != 0.0:
+        res = res + shift * X
+    if diag is not None:
+        res = res + _flat(diag, X.shape[0])[:, None] * X
+    if accumulate:
+        res = res + Y
+    Y.copy_(res)
+    _add_dots(dots, dots_row, X.shape[1], X, Y)
+
+
+def col_dots(X, Y, dots, gate=None):
+    if _open(gate):
+        dots.reshape(-1)[:X.shape[1]] += (X.double() * Y.double()).sum(0)
+
+
+def col_scale(X, Y, sq, take_sqrt, mode, a=1.0, gate=None):
+    if not _open(gate):
+        return
+    s = sq.reshape(-1)[:X.shape[1]]
+    s = (torch.sqrt(s) if take_sqrt else s).to(X.dtype)
+    if mode == 0:
+        Y.copy_(X * (a * s))
+    elif mode == 1:
+        Y.copy_(X / torch.where(s.abs() < 1e-40, torch.full_like(s, 1e-40), s))
+    elif mode == 2:
+        Y.copy_(X / s)
+    else:
+        Y.copy_(X / torch.clamp(s, min=a))
+
+
+def axpby(X, Y, a, b, gate=None):
+    if _open(gate):
+        Y.copy_(a * X + b * Y if b != 0 else a * X)
+
+
+def diag_matmat(X, Y, shift, diag, accumulate, dots=None, dots_row=None, gate=None):
+    if _open(gate):
+        _epilogue(torch.zeros_like(X), X, Y, 0.0, shift, diag, accumulate, dots, dots_row)
+
+
+def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False,
+             dots=None, dots_row=None, gate=None):
+    if not _open(gate):
+        return
+    S = torch.sparse_csr_tensor(rowptr.long(), colidx.long(), vals, size=tuple(shape))
+    KX = S @ X
+    if shift == 0.0 and diag is None and dots is None:
+        Y.copy_(alpha * KX + Y if accumulate else alpha * KX)
+    else:
+        _epilogue(KX, X, Y, alpha, shift, diag, accumulate, dots, dots_row)
+
+
+def mode_contract(M, d_out, d_in, pre, post, inp, out, alpha=1.0, shift=0.0, diag=None, epi_x=None, accumulate=False,
+                  dots=None, dots_row=None, gate=None):
+    if not _open(gate):
+        return
+    src = _flat(inp, pre * d_in * post).reshape(pre, d_in, post)
+    dst = _flat(out, pre * d_out * post).reshape(pre * d_out, post)
+    KX = torch.einsum("aj,pjq->paq", M[:d_out, :d_in], src).reshape(pre * d_out, post)
+    if epi_x is None:
+        dst.copy_(alpha * KX + dst if accumulate else alpha * KX)
+        return
+    X = _flat(epi_x, pre * d_out * post).reshape(pre * d_out, post)
+    _epilogue(KX, X, dst, alpha, shift, diag, accumulate, dots, dots_row)
+
+
+def reorth_dots(V, j0, j1, W, C, gate=None):
+    if _open(gate) and j1 > j0:
+        C[j0:j1] += (V[j0:j1].double() * W.double()[None]).sum(1)
+
+
+def reorth_update(V, j0, j1, W, C, sign=-1.0, wnorm2=None, gate=None):
+    if not _open(gate):
+        return
+    if j1 > j0:
+        coef = C[j0:j1].to(W.dtype)
+        W += sign * (coef[:, None, :] * V[j0:j1]).sum(0)
+    if wnorm2 is not None:
+        wnorm2.reshape(-1)[:W.shape[1]] += (W.double() ** 2).sum(0)
+
+
+def lanczos_three_term(W, Vi, Vim1, alpha_acc, beta_prev_sq, gate=None):
+    if not _open(gate):
+        return
+    upd = alpha_acc.to(W.dtype) * Vi
+    if Vim1 is not None:
+        upd = upd + torch.sqrt(beta_prev_sq).to(W.dtype) * Vim1
+    W -= upd
+
+
+def tridiag_eig_first_row(d, e, z, status=None, gate=None):
+    if not _open(gate):
+        return
+    m, b = d.shape
+    T = torch.diag_embed(d.T.contiguous())
+    if m > 1:
+        off = e[:m - 1].T.contiguous()
+        T = T + torch.diag_embed(off, offset=1) + torch.diag_embed(off, offset=-1)
+    lam, P = torch.linalg.eigh(T)
+    d.copy_(lam.T)
+    z.copy_(P[:, 0, :].T)
+    if status is not None:
+        status.zero_()
+
+
+def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
+    if not _open(gate):
+        return
+    b = W.shape[1]
+    if Qprev is not None:
+        W -= hprev.reshape(-1)[:b].to(W.dtype) * Qprev
+    if Qcur is not None:
+        hcur.reshape(-1)[:b] += (Qcur.double() * W.double()).sum(0)
+    if wnorm2 is not None:
+        wnorm2.reshape(-1)[:b] += (W.double() ** 2).sum(0)
+
+
+class _Fused:
+    enabled = False
+
+
+def reorth_update_dots(V, j0, j1, W, C1, C2, sign=-1.0, gate=None):
+    """False = "shape outside the fused kernel's envelope" (the caller's two-kernel path); with
+    emulated_kernels(fused=True) the fused semantics are stated so both host branches are exercised."""
+    if not _Fused.enabled:
+        return False
+    reorth_update(V, j0, j1, W, C1, sign=sign, gate=gate)
+    reorth_dots(V, j0, j1, W, C2, gate=gate)
+    return True
+
+
+_WRAPPERS = dict(col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm,
+                 mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
+                 reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
+                 tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link)
+
+
+@contextlib.contextmanager
+def emulated_kernels(fused=False):
+    import cola_b200.backend as be
+    import cola_b200.ops as ops
+    import cola_b200.rng as rng
+    saved = {name: getattr(be, name) for name in _WRAPPERS}
+    saved_gate, saved_ptr, saved_off = be.require_cuda, be.ptr, be.off_ptr
+    saved_tc, saved_mem, saved_probe = ops._KronCore._tc_ok, torch.cuda.mem_get_info, rng.PROBE_DEVICE
+    try:
+        for name, fn in _WRAPPERS.items():
+            setattr(be, name, fn)
+        be.require_cuda = lambda t, what="operand": None
+        be.ptr = lambda t, dtype=None: t
+        be.off_ptr = lambda t, elem_offset: t.reshape(-1)[elem_offset:]
+        ops._KronCore._tc_ok = lambda self, X: False
+        torch.cuda.mem_get_info = lambda device=None: (64 << 30, 64 << 30)
+        rng.PROBE_DEVICE = "cpu"
+        _Fused.enabled = fused
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(be, name, fn)
+        be.require_cuda, be.ptr, be.off_ptr = saved_gate, saved_ptr, saved_off
+        ops._KronCore._tc_ok, torch.cuda.mem_get_info, rng.PROBE_DEVICE = saved_tc, saved_mem, saved_probe
+        _Fused.enabled = False

@@ -1,0 +1,99 @@
+"""Host-logic tests without a GPU: the bodies of the GPU parity tests (tests/test_gpu_parity.py) for everything
+that is orchestrated in Python -- plan compiler + matmat epilogues, Lanczos, Arnoldi, GMRES, power iteration,
+SLQ, Hutchinson, f(A)v -- are run on CPU tensors with the kernels replaced by tests/host_harness.py (statements
+of the header's semantics).  They check loop logic against the oracle and the reference's golden vectors; the
+kernels themselves are checked only on the GPU.  CG (raw C entry points + CUDA graphs) is not covered here."""
+import pytest
+import torch
+
+import cola_b200
+from tests import test_gpu_parity as gp
+from tests.golden_cases import ARNOLDI_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, POWER_CASES
+from tests.host_harness import emulated_kernels
+
+
+@pytest.fixture(params=[False, True], ids=["two-kernel-cgs2", "fused-cgs2"])
+def emu_both(request, monkeypatch):
+    monkeypatch.setattr(gp, "DEV", "cpu")
+    with emulated_kernels(fused=request.param):
+        yield cola_b200
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    monkeypatch.setattr(gp, "DEV", "cpu")
+    with emulated_kernels():
+        yield cola_b200
+
+
+def test_gate_is_closed_outside_the_harness():
+    A = cola_b200.ops.Dense(torch.eye(4))
+    with emulated_kernels():
+        assert torch.equal(A @ torch.ones(4, 2), torch.ones(4, 2))
+    with pytest.raises(RuntimeError, match="CUDA-only"):
+        A @ torch.ones(4, 2)
+
+
+@pytest.mark.parametrize("name", MATMAT_PROBLEMS)
+def test_matmat(name, golden, emu):
+    gp.test_matmat(name, golden, emu)
+
+
+def test_matmat_fused_dots_and_product_chain(emu):
+    gp.test_matmat_fused_dots_and_gate(emu)
+    # the Product-chain epilogue case of test_gpu_parity.test_product_chain_epilogue, without its CG tail
+    g = torch.Generator().manual_seed(2)
+    M = torch.randn(40, 24, dtype=torch.float64, generator=g)
+    d = torch.rand(40, dtype=torch.float64, generator=g) + 0.5
+    ops = emu.ops
+    A = emu.PSD(ops.Product(ops.Dense(M), ops.Dense(M.T.contiguous())) + ops.Diagonal(d) + 0.3 * ops.I_like(ops.Dense(M @ M.T)))
+    X = torch.randn(40, 5, dtype=torch.float64, generator=g)
+    ref = M @ (M.T @ X) + d[:, None] * X + 0.3 * X
+    dots = torch.zeros(5, dtype=torch.float64)
+    Y = torch.empty_like(X)
+    A.matmat_into(X, Y, dots=dots)
+    assert gp.rel(Y, ref) < 1e-13 and gp.rel(dots, (X * ref).sum(0)) < 1e-13
+
+
+@pytest.mark.parametrize("case", sorted(LANCZOS_CASES))
+def test_lanczos(case, golden, emu_both):
+    gp.test_lanczos_vs_oracle_and_golden(case, golden, emu_both)
+
+
+def test_lanczos_known_answers_and_eig(golden, emu):
+    gp.test_lanczos_known_answers_and_early_stop(golden, emu)
+    gp.test_eig_lanczos_default_start(golden, emu)
+
+
+@pytest.mark.parametrize("case", sorted(ARNOLDI_CASES))
+def test_arnoldi(case, golden, emu):
+    gp.test_arnoldi_vs_oracle_and_golden(case, golden, emu)
+
+
+def test_eig_arnoldi(golden, emu):
+    gp.test_eig_arnoldi(golden, emu)
+
+
+@pytest.mark.parametrize("case", sorted(POWER_CASES))
+def test_power_iteration(case, golden, emu):
+    gp.test_power_iteration_vs_oracle_and_golden(case, golden, emu)
+
+
+@pytest.mark.parametrize("case", sorted(GMRES_CASES))
+def test_gmres(case, golden, emu):
+    gp.test_gmres_vs_oracle_and_golden(case, golden, emu)
+
+
+@pytest.mark.parametrize("name,m,vtol", [("kron884_diag_f32", 25, 0.25), ("kron465_diag_f64", 30, 0.2),
+                                         ("lap24_f64", 40, 0.25)])
+def test_slq(name, m, vtol, golden, emu):
+    gp.test_slq_logdet_identical_probes(name, m, vtol, golden, emu)
+
+
+@pytest.mark.parametrize("name,m", [("kron884_diag_f32", 25), ("kron465_diag_f64", 30)])
+def test_log_matmat_and_hutch_logdet(name, m, golden, emu):
+    gp.test_log_matmat_and_hutch_logdet(name, m, golden, emu)
+
+
+def test_hutch_rademacher_and_errors(golden, emu):
+    gp.test_hutch_rademacher_and_errors(golden, emu)
