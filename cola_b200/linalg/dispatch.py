@@ -11,8 +11,8 @@ import numpy as np
 import torch
 
 from .. import rng
-from ..ops import (PSD, BlockDiag, Dense, Diagonal, Identity, Kronecker, LinearOperator, Product, ScalarMul,
-                   SelfAdjoint, Unitary, lazify)
+from ..ops import (PSD, BlockDiag, Dense, Diagonal, I_like, Identity, Kronecker, KronSum, LinearOperator, Product,
+                   ScalarMul, SelfAdjoint, Transpose, Unitary, lazify)
 from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
 from .arnoldi import arnoldi, arnoldi_eigs
 from .cg import CG
@@ -20,6 +20,7 @@ from .gmres import GMRES
 from .power_iteration import PowerIteration
 from .lanczos import lanczos, lanczos_eigs
 from .stochastic import Hutch, LanczosUnary, hutchinson_diag_estimate
+from .unary import ArnoldiUnary
 
 
 @dataclass
@@ -69,17 +70,22 @@ class Exact(Algorithm):
 
 
 def exact_diag(A, k, bs):
-    """diagonal_estimation.py:117-128 for k = 0: blocks of identity columns through the fused matmat."""
-    if k != 0:
-        raise NotImplementedError("off-diagonals (k != 0) are outside the Krylov hot path")
-    bs = min(100, A.shape[0])
+    """diagonal_estimation.py:84-128: blocks of 100 identity columns through the fused matmat.  Column c of A holds
+    entry (c - k, c) of the k-th diagonal, so each block is read off directly instead of being masked with a shifted
+    identity block and reduced over columns (the reference's form; it also fails on a ragged last block for k != 0,
+    this one does not)."""
     n = A.shape[0]
-    out = torch.empty(n, dtype=A.dtype, device=A.device)
+    bs = min(100, n)
+    out = torch.zeros(n - abs(k), dtype=A.dtype, device=A.device)
     for i in range(0, n, bs):
         w = min(bs, n - i)
         chunk = torch.zeros((n, w), dtype=A.dtype, device=A.device)
         chunk[i:i + w] = torch.eye(w, dtype=A.dtype, device=A.device)
-        out[i:i + w] = ((A @ chunk) * chunk).sum(-1)[i:i + w]
+        AE = A @ chunk
+        cols = torch.arange(i, i + w, device=A.device)
+        rows = cols - k
+        ok = (rows >= 0) & (rows < n)
+        out[(rows if k >= 0 else cols)[ok]] = AE[rows[ok], (cols - i)[ok]]
     return out
 
 
@@ -213,17 +219,87 @@ def trace(A: LinearOperator, alg: Algorithm = Auto()):
     return diag(A, 0, alg).sum()
 
 
-# ---------------------------------------------------------------------------------------------------- log / logdet
+# ---------------------------------------------------------------------------------------------------- f(A)
+def apply_unary(f, A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/unary/unary.py:94-212: structure rules first, then Auto / Lanczos / Arnoldi / Eigh."""
+    if isinstance(A, Diagonal):                      # unary.py:181-183
+        return Diagonal(f(A.diag))
+    if isinstance(A, BlockDiag):                     # :186-189
+        return BlockDiag(*[apply_unary(f, a, alg) for a in A.Ms], multiplicities=A.multiplicities)
+    if isinstance(A, Identity):                      # :192-195
+        return f(torch.ones((), dtype=A.dtype, device=A.device)) * A
+    if isinstance(A, ScalarMul):                     # :198-200
+        return f(A.c) * I_like(A)
+    if isinstance(A, Transpose):                     # :203-205
+        return Transpose(apply_unary(f, A.A, alg))
+    if isinstance(alg, Auto):                        # :113-131
+        psd, small = A.isa(PSD), bool(np.prod(A.shape) <= 1e6)
+        if psd:
+            alg = Eigh() if small else Lanczos(**alg.__dict__)
+        elif small:
+            raise NotImplementedError("small non-PSD operators route to a dense complex eig in the reference "
+                                      "(unary.py:171-178), which is outside the Krylov hot path")
+        else:
+            alg = Arnoldi(**alg.__dict__)
+    if isinstance(alg, Lanczos):                     # :134-137
+        assert A.isa(SelfAdjoint), "Lanczos only valid for SelfAdjoint, wrap in cola.SelfAdjoint if desired"
+        return LanczosUnary(A, f, **alg.__dict__)
+    if isinstance(alg, Arnoldi):                     # :140-142
+        return ArnoldiUnary(A, f, **alg.__dict__)
+    if isinstance(alg, Eigh):                        # :160-168: dense eigh (library), lazy V f(D) V^T
+        assert A.isa(SelfAdjoint), "Eigh only valid for SelfAdjoint, wrap in cola.SelfAdjoint if desired"
+        eigs, V = torch.linalg.eigh(A.to_dense())
+        V = lazify(V)
+        return V @ Diagonal(f(eigs)) @ V.H
+    raise NotImplementedError(f"apply_unary with {type(alg).__name__} is outside the Krylov hot path")
+
+
+def exp(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/unary/unary.py:229-246"""
+    if isinstance(A, KronSum):                       # exp(A (+) B) = exp(A) (x) exp(B)
+        return Kronecker(*[exp(a, alg) for a in A.Ms])
+    return apply_unary(torch.exp, A, alg)
+
+
 def log(A: LinearOperator, alg: Algorithm = Auto()):
-    """cola/linalg/unary/unary.py:249-262 + apply_unary rules :94-142 (Lanczos case)."""
-    if isinstance(A, Diagonal):
-        return Diagonal(torch.log(A.diag))
-    if isinstance(alg, Auto):
-        alg = Lanczos(**alg.__dict__)
-    if isinstance(alg, Lanczos):   # unary.py:134-137
-        assert A.isa(SelfAdjoint), "Lanczos unary functions need a SelfAdjoint operator"
-        return LanczosUnary(A, torch.log, **alg.__dict__)
-    raise NotImplementedError(f"log with {type(alg).__name__} is outside the Krylov hot path")
+    """cola/linalg/unary/unary.py:249-262"""
+    return apply_unary(torch.log, A, alg)
+
+
+def pow(A: LinearOperator, alpha, alg: Algorithm = Auto()):
+    """cola/linalg/unary/unary.py:265-305: integer powers are products / inverses, the rest is f(A) = A^alpha."""
+    if isinstance(A, Kronecker):                     # :303-305
+        return Kronecker(*[pow(a, alpha, alg) for a in A.Ms])
+    k = int(np.round(alpha))
+    if np.isclose(alpha, k):
+        if k == 0:
+            return I_like(A)
+        if 0 < k < 10:
+            out = A
+            for _ in range(k - 1):
+                out = out @ A
+            return out
+        if k == -1:
+            if isinstance(alg, Lanczos):
+                new_alg = CG(**{kk: v for kk, v in alg.__dict__.items() if kk in ("tol", "max_iters", "pbar")})
+            elif isinstance(alg, Arnoldi):
+                new_alg = GMRES(**{kk: v for kk, v in alg.__dict__.items() if kk in ("tol", "max_iters", "pbar")})
+            elif isinstance(alg, Eigh):
+                new_alg = Cholesky()
+            else:
+                new_alg = alg
+            return inv(A, new_alg)
+    return apply_unary(lambda x: x**alpha, A, alg)
+
+
+def sqrt(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/unary/unary.py:308-320"""
+    return pow(A, 0.5, alg)
+
+
+def isqrt(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/unary/unary.py:323-335"""
+    return pow(A, -0.5, alg)
 
 
 def slogdet(A: LinearOperator, log_alg: Algorithm = Auto(), trace_alg: Algorithm = Auto()):
@@ -253,13 +329,11 @@ def slogdet(A: LinearOperator, log_alg: Algorithm = Auto(), trace_alg: Algorithm
         if small:
             s, l = torch.linalg.slogdet(A.to_dense())
             return s, l
-        if not A.isa(PSD):
-            raise NotImplementedError("non-PSD logdet routes to Arnoldi in the reference (outside this path)")
-        log_alg = Lanczos(**log_alg.__dict__)
-    if isinstance(log_alg, Lanczos):   # logdet.py:111-117
-        logA = log(A, log_alg)
-        tr = trace(logA, trace_alg)
-        return one, tr
+        log_alg = Lanczos(**log_alg.__dict__) if A.isa(PSD) else Arnoldi(**log_alg.__dict__)
+    if isinstance(log_alg, (Lanczos, Arnoldi)):   # logdet.py:111-117
+        tr = trace(log(A, log_alg), trace_alg)
+        mag = torch.abs(tr)                        # the reference returns (phase, |tr log A|), restated as is
+        return tr / mag, mag
     raise NotImplementedError(f"slogdet with {type(log_alg).__name__} is outside the Krylov hot path")
 
 

@@ -122,12 +122,10 @@ class Hutch(Algorithm):
 
 def hutchinson_diag_estimate(A: LinearOperator, k=0, bs=100, tol=3e-2, max_iters=10000, pbar=False, rand='normal',
                              key=None, group=None):
-    """cola/linalg/trace/diagonal_estimation.py:158-210 (main diagonal, k = 0).  With `group`
+    """cola/linalg/trace/diagonal_estimation.py:158-210 (k-th diagonal, numpy offset convention).  With `group`
     (a torch.distributed process group) each rank handles a contiguous slice of every 100-probe block and the
     running sums are all-reduced once per block (the stopping rule needs the global statistics)."""
     import time
-    if k != 0:
-        raise NotImplementedError("off-diagonals (k != 0) are outside the Krylov hot path")
     bs = min(100, A.shape[0])
     assert tol > 1e-3, "tolerance chosen too high for stochastic diagonal estimation"
     assert rand in ['normal', 'rademacher'], "rand must be 'normal' or 'rademacher'"
@@ -138,7 +136,7 @@ def hutchinson_diag_estimate(A: LinearOperator, k=0, bs=100, tol=3e-2, max_iters
     if group is not None:
         import torch.distributed as dist
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-    sums = torch.zeros((2, n), dtype=A.dtype, device=dev)   # diag_sum, diag_sumsq
+    sums = torch.zeros((2, n - abs(k)), dtype=A.dtype, device=dev)   # diag_sum, diag_sumsq
 
     def err(i):
         mean = sums[0] / (i * bs)
@@ -159,7 +157,12 @@ def hutchinson_diag_estimate(A: LinearOperator, k=0, bs=100, tol=3e-2, max_iters
             z = torch.sign(z)
         lo, hi = (rank * bs) // world, ((rank + 1) * bs) // world
         zl = z[:, lo:hi].contiguous()
-        est = (A @ zl) * zl
+        if k == 0:
+            est = (A @ zl) * zl
+        elif k > 0:                                    # (A z)[r] * z[r + k]   (roll by -k, :190-194)
+            est = (A @ zl)[:n - k] * zl[k:]
+        else:                                          # (A z)[j + |k|] * z[j]
+            est = (A @ zl)[-k:] * zl[:n + k]
         part = torch.stack([est.sum(-1), (est**2).sum(-1)])
         if group is not None:
             dist.all_reduce(part, group=group)

@@ -374,6 +374,28 @@ class Kronecker(LinearOperator):
         return "⊗".join(str(M) for M in self.Ms)
 
 
+class KronSum(LinearOperator):
+    """operators.py:241-275: A (+) B (+) ... = A x I x .. + I x B x .. + ...  (square factors)."""
+    def __init__(self, *Ms):
+        self.Ms = tuple(lazify(M) for M in Ms)
+        shape = _prod([Mi.shape[-2] for Mi in Ms]), _prod([Mi.shape[-1] for Mi in Ms])
+        dtype = reduce(torch.promote_types, (M.dtype for M in self.Ms))
+        super().__init__(dtype, shape)
+
+    def _infer_annotations(self):  # annotations.py:91-93 (same intersection rule as Kronecker)
+        return _intersect(self.Ms)
+
+    def to_dense(self):
+        def ksum(A, B):
+            IA = torch.eye(A.shape[-2], dtype=A.dtype, device=A.device)
+            IB = torch.eye(B.shape[-2], dtype=B.dtype, device=B.device)
+            return torch.kron(A, IB) + torch.kron(IA, B)
+        return reduce(ksum, [M.to_dense() for M in self.Ms])
+
+    def __str__(self):
+        return "⊕ₖ".join(str(M) for M in self.Ms)
+
+
 class BlockDiag(LinearOperator):
     """operators.py:277-320"""
     def __init__(self, *Ms, multiplicities=None):
@@ -407,8 +429,10 @@ class Diagonal(LinearOperator):
 
 
 class Tridiagonal(LinearOperator):
-    """operators.py:351-372: the container Lanczos returns (alpha lower, beta diagonal, gamma upper band).
-    Tiny (m x m); its matmat is not on the hot path and stays a few elementwise torch ops on the device."""
+    """operators.py:351-372 (alpha lower, beta diagonal, gamma upper band): the container Lanczos returns, and an
+    operator in its own right.  With plain vector bands its matmat is the CSR kernel on a 3-entries-per-row matrix
+    (`as_sparse`), so shift / Diagonal / dots epilogues fuse as for any Sparse; batched bands (what a batched
+    Lanczos returns) keep the elementwise form below."""
     def __init__(self, alpha, beta, gamma):
         def col(v):
             return v.reshape(-1, 1) if v.dim() == 1 else v
@@ -416,11 +440,23 @@ class Tridiagonal(LinearOperator):
         super().__init__(dtype=beta.dtype, shape=(self.beta.shape[0], self.beta.shape[0]))
 
     def _matmat(self, X):
+        if self.beta.dim() == 2 and self.beta.shape[1] == 1:
+            return LinearOperator._matmat(self, X)         # compiled plan: CSR core
         out = self.beta * X
         zeros = torch.zeros((1, X.shape[-1]), dtype=X.dtype, device=X.device)
         up = torch.cat([self.gamma * X[1:], zeros], dim=0)
         lo = torch.cat([zeros, self.alpha * X[:-1]], dim=0)
         return out + lo + up
+
+    def as_sparse(self):
+        n = self.beta.shape[0]
+        dev = self.beta.device
+        i = torch.arange(n, device=dev)
+        rows = torch.cat([i, i[1:], i[:-1]])
+        cols = torch.cat([i, i[:-1], i[1:]])
+        data = torch.cat([self.beta[:, 0], self.alpha[:, 0], self.gamma[:, 0]])
+        order = torch.argsort(rows * n + cols)
+        return Sparse(data[order].contiguous(), rows[order], cols[order], (n, n))
 
     def to_dense(self):
         m = self.beta.shape[0]
@@ -508,6 +544,10 @@ def transpose(A):
         return A
     if isinstance(A, Kronecker):
         return Kronecker(*[transpose(M) for M in A.Ms])
+    if isinstance(A, KronSum):
+        return KronSum(*[transpose(M) for M in A.Ms])
+    if isinstance(A, Tridiagonal):
+        return Tridiagonal(A.gamma, A.beta, A.alpha)
     if isinstance(A, BlockDiag):
         return BlockDiag(*[transpose(M) for M in A.Ms], multiplicities=A.multiplicities)
     if isinstance(A, Sum):
@@ -609,6 +649,31 @@ class _KronCore:
                 dst = self._workspace(numel, X.dtype, X.device, i % 2)
                 be.mode_contract(F, d_out[i], d_in[i], pre, post, src, dst, gate=epi.gate)
                 src = dst
+
+
+class _KronSumCore:
+    """sum_i I x .. x F_i x .. x I as D mode contractions that accumulate into Y, in factor order like
+    operators.py:261-268 (no `0 * ev` initialisation pass, no moveaxis copies).  The last factor sees X as
+    (n / d_D, d_D, k), i.e. its flattened rows are the operator's rows, so it carries the fused epilogue."""
+    def __init__(self, factors):
+        self.Fs = [(f if f.is_contiguous() else f.contiguous()) for f in factors]
+        assert all(f.shape[0] == f.shape[1] for f in self.Fs), "KronSum factors are square"
+        self.shape = (_prod([f.shape[0] for f in self.Fs]), ) * 2
+
+    def apply(self, X, Y, epi):
+        k = X.shape[1]
+        dims = [f.shape[0] for f in self.Fs]
+        D = len(dims)
+        for i, F in enumerate(self.Fs):
+            pre = _prod(dims[:i]) if i > 0 else 1
+            post = (_prod(dims[i + 1:]) if i + 1 < D else 1) * k
+            acc = epi.accumulate or i > 0
+            if i == D - 1:
+                kw = epi.kw()
+                kw["accumulate"] = acc
+                be.mode_contract(F, dims[i], dims[i], pre, post, X, Y, epi_x=X if epi.needs_x() else None, **kw)
+            else:
+                be.mode_contract(F, dims[i], dims[i], pre, post, X, Y, alpha=epi.alpha, accumulate=acc, gate=epi.gate)
 
 
 class _BlockDiagCore:
@@ -733,6 +798,10 @@ def _core_of(op):
         return _CsrCore(op)
     if isinstance(op, Kronecker):
         return _KronCore([_dense_of(M) for M in op.Ms])
+    if isinstance(op, KronSum):
+        return _KronSumCore([_dense_of(M) for M in op.Ms])
+    if isinstance(op, Tridiagonal) and op.beta.dim() == 2 and op.beta.shape[1] == 1:
+        return _CsrCore(op.as_sparse())
     if isinstance(op, BlockDiag):
         return _BlockDiagCore([_dense_of(M) for M in op.Ms], op.multiplicities)
     return _OpaqueCore(op)

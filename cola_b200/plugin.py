@@ -9,18 +9,19 @@ The reference resolves its Krylov loops by module attribute at call time (`cg.py
     cola.linalg.decompositions.arnoldi.arnoldi_fact                (arnoldi.py:289-324)
     cola.linalg.trace.diagonal_estimation.hutchinson_diag_estimate (diagonal_estimation.py:158-210)
     cola.linalg.tbd.slq.slq_fwd                                    (slq.py:37-52)
-    Dense/Sparse/Kronecker/BlockDiag/Diagonal/Sum/Product/ScalarMul._matmat  (operators.py)
+    Dense/Sparse/Kronecker/KronSum/BlockDiag/Diagonal/Sum/Product/ScalarMul._matmat  (operators.py)
 
 to adapters that take the B200 path when the operator lives on a CUDA device in float32/float64 and its tree
 converts (`from_cola`), and call the saved reference function otherwise (CPU, complex, JAX/NumPy backends,
-preconditioners that do not convert, off-diagonal Hutchinson, exotic operators).  The adapters translate between the
+preconditioners that do not convert, exotic operators).  The adapters translate between the
 reference's state layouts and this package's: the reference keeps the Krylov basis as (b, n, m+2) with the
 vector index fastest, the kernels as (m+2, n, b); what is handed back is a strided view with the reference's
 logical shape.  `uninstall()` restores everything.
 
 The reference is not importable on the GPU box, so the adapters are exercised on CPU in
-tests/test_plugin_reference.py with oracle-backed stand-ins for the CUDA loops (FORCE_FAST_PATH), while the CUDA
-loops themselves are checked against the oracle in tests/test_gpu_parity.py.
+tests/test_plugin_reference.py (FORCE_FAST_PATH): once with oracle-backed stand-ins for the loops, and once with
+this package's own host loops running on the test-only kernel stand-ins of tests/host_harness.py, driven through
+the reference's public API; the CUDA kernels themselves are checked against the oracle in tests/test_gpu_parity*.py.
 """
 import importlib
 
@@ -33,6 +34,7 @@ b_cg = importlib.import_module(__package__ + ".linalg.cg")
 b_lanczos = importlib.import_module(__package__ + ".linalg.lanczos")
 b_arnoldi = importlib.import_module(__package__ + ".linalg.arnoldi")
 b_stoch = importlib.import_module(__package__ + ".linalg.stochastic")
+b_unary = importlib.import_module(__package__ + ".linalg.unary")
 
 FORCE_FAST_PATH = False      # tests only: route CPU operators through the adapters as well
 _SAVED = {}
@@ -84,6 +86,8 @@ def from_cola(A, cola):
         M = bops.Tridiagonal(A.alpha, A.beta, A.gamma)
     elif isinstance(A, R.Kronecker):
         M = bops.Kronecker(*[from_cola(m, cola) for m in A.Ms])
+    elif isinstance(A, R.KronSum):
+        M = bops.KronSum(*[from_cola(m, cola) for m in A.Ms])
     elif isinstance(A, R.BlockDiag):
         M = bops.BlockDiag(*[from_cola(m, cola) for m in A.Ms], multiplicities=list(A.multiplicities))
     elif isinstance(A, R.Sum):
@@ -99,6 +103,9 @@ def from_cola(A, cola):
                      bops.Identity(tuple(A.shape), A.dtype))
     elif unary is not None and isinstance(A, unary.LanczosUnary):
         M = b_stoch.LanczosUnary(from_cola(A.A, cola), A.f, **{k: v for k, v in getattr(A, "kwargs", {}).items()
+                                                                if k in ("max_iters", "tol", "pbar")})
+    elif unary is not None and isinstance(A, unary.ArnoldiUnary):
+        M = b_unary.ArnoldiUnary(from_cola(A.A, cola), A.f, **{k: v for k, v in getattr(A, "kwargs", {}).items()
                                                                 if k in ("max_iters", "tol", "pbar")})
     else:
         raise NotConvertible(type(A).__name__)
@@ -170,7 +177,7 @@ def _make_arnoldi_fact(cola, ref):
 
 def _make_hutch(cola, ref):
     def hutchinson_diag_estimate(A, k=0, bs=100, tol=3e-2, max_iters=10000, pbar=False, rand='normal', key=None):
-        M = _mirror_or_none(A, cola) if k == 0 else None
+        M = _mirror_or_none(A, cola)
         if M is None:
             return ref(A, k, bs, tol, max_iters, pbar, rand, key)
         return b_stoch.hutchinson_diag_estimate(M, k, bs, tol, max_iters, pbar, rand, key)
@@ -188,7 +195,8 @@ def _make_slq_fwd(cola, ref):
 
 def _make_matmat(cola, ref):
     def _matmat(self, X):
-        if torch.is_tensor(X) and (X.is_cuda or FORCE_FAST_PATH) and _is_fast_dtype(X.dtype) and X.dtype == self.dtype:
+        if torch.is_tensor(X) and (X.is_cuda or FORCE_FAST_PATH) and _is_fast_dtype(X.dtype) and X.dtype == self.dtype \
+                and not torch._C._functorch.is_batchedtensor(X):   # under vmap there is no pointer to hand over
             M = _mirror_or_none(self, cola)
             if M is not None:
                 return M._matmat(X.contiguous())
@@ -203,7 +211,10 @@ _LOOPS = (
     ("cola.linalg.trace.diagonal_estimation", "hutchinson_diag_estimate", _make_hutch),
     ("cola.linalg.tbd.slq", "slq_fwd", _make_slq_fwd),
 )
-_MATMAT_CLASSES = ("Dense", "Sparse", "Kronecker", "BlockDiag", "Diagonal", "Sum", "Product", "ScalarMul")
+# Tridiagonal is deliberately absent: the reference vmaps `Tridiagonal.to_dense` over the batched Lanczos output
+# (unary.py:52), and functorch-batched leaves cannot be handed to kernels by pointer.  Inside a tree handed to one
+# of the loops it still converts (from_cola) and runs on the CSR kernel.
+_MATMAT_CLASSES = ("Dense", "Sparse", "Kronecker", "KronSum", "BlockDiag", "Diagonal", "Sum", "Product", "ScalarMul")
 
 
 def install(cola=None, matmats=True):

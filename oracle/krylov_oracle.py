@@ -188,6 +188,36 @@ class BlockDiagOp(Op):  # operators.py:277-320
         return torch.cat(pieces, dim=0)
 
 
+class KronSumOp(Op):  # operators.py:241-275: out = sum_i (I x ... x M_i x ... x I) X, accumulated in factor order
+    def __init__(self, *Ms):
+        self.Ms = Ms
+        self.dtype = Ms[0].dtype
+        self.shape = (int(np.prod([M.shape[0] for M in Ms])), int(np.prod([M.shape[1] for M in Ms])))
+
+    def matmat(self, X):
+        ev = X.reshape(*[M.shape[1] for M in self.Ms], -1)
+        out = 0 * ev
+        for i, M in enumerate(self.Ms):
+            front = torch.moveaxis(ev, i, 0)
+            Mf = M.matmat(front.reshape(M.shape[1], -1)).reshape(M.shape[0], *front.shape[1:])
+            out += torch.moveaxis(Mf, 0, i)
+        return out.reshape(self.shape[0], ev.shape[-1])
+
+
+class TridiagonalOp(Op):  # operators.py:351-372 (alpha lower band, beta diagonal, gamma upper band)
+    def __init__(self, alpha, beta, gamma):
+        self.alpha, self.beta, self.gamma = alpha.reshape(-1, 1), beta.reshape(-1, 1), gamma.reshape(-1, 1)
+        self.dtype = beta.dtype
+        self.shape = (beta.shape[0], beta.shape[0])
+
+    def matmat(self, X):
+        out = self.beta * X
+        zeros = torch.zeros((1, X.shape[-1]), dtype=X.dtype)
+        up = torch.concat([self.gamma * X[1:], zeros], dim=0)
+        lo = torch.concat([zeros, self.alpha * X[:-1]], dim=0)
+        return out + lo + up
+
+
 # ----------------------------------------------------------------------------------
 # loop driver with the `info` contract  (cola/utils/torch_tqdm.py:7-71, 86-90)
 # ----------------------------------------------------------------------------------
@@ -474,11 +504,59 @@ def lanczos_unary_matmat(A, f, Vin, max_iters=100, tol=1e-7):
     out = (Q @ P @ (flam * coef)[..., None])[..., 0]
     return out.T, info
 
+# ----------------------------------------------------------------------------------
+# f(A) V through Arnoldi  (cola/linalg/unary/unary.py:63-91); the result is complex
+# ----------------------------------------------------------------------------------
+def arnoldi_unary_matmat(A, f, Vin, max_iters=100, tol=1e-7):
+    Q, H, info = arnoldi(A, Vin, max_iters, tol)          # batched: Q (b, n, m+1), H (b, m+1, m)
+    Q, H = Q[:, :, :-1], H[:, :-1]
+    lam, P = torch.linalg.eig(H)
+    norms = torch.linalg.norm(Vin, dim=0)
+    e0 = torch.zeros(P.shape[1], Vin.shape[-1], dtype=P.dtype)
+    e0[0] = 1.0
+    Pinv0 = torch.linalg.solve(P, e0.T[..., None]).squeeze(-1)
+    coef = Pinv0 * norms[:, None]
+    thresh = 10 * torch.finfo(A.dtype).eps * torch.max(torch.abs(lam), dim=1, keepdim=True)[0]
+    flam = torch.where(torch.abs(lam) > thresh, f(lam), torch.zeros_like(lam))
+    out = (Q.to(P.dtype) @ P @ (flam * coef)[..., None])[..., 0]
+    return out.T, info
+
 
 # ----------------------------------------------------------------------------------
-# Hutchinson diagonal / trace  (cola/linalg/trace/diagonal_estimation.py:158-210), k = 0 only
+# exp / log / sqrt / isqrt as lazy operators  (cola/linalg/unary/unary.py:37-91, 229-335)
 # ----------------------------------------------------------------------------------
-def hutchinson_diag(matmat, n, dtype, tol=3e-2, max_iters=10000, rand="normal", key=None):
+UNARY_FUNS = {"exp": torch.exp, "log": torch.log, "sqrt": lambda x: x**0.5, "isqrt": lambda x: x**-0.5}
+
+
+class LanczosUnaryOp(Op):                                  # unary.py:37-60
+    def __init__(self, A, f, max_iters, tol):
+        super().__init__(A.shape, A.dtype)
+        self.A, self.f, self.max_iters, self.tol = A, f, max_iters, tol
+
+    def matmat(self, X):
+        return lanczos_unary_matmat(self.A, self.f, X, self.max_iters, self.tol)[0]
+
+
+class ArnoldiUnaryOp(LanczosUnaryOp):                      # unary.py:63-91
+    def matmat(self, X):
+        return arnoldi_unary_matmat(self.A, self.f, X, self.max_iters, self.tol)[0]
+
+
+def unary_operator(fn, A, alg, max_iters, tol):
+    """The dispatch rules the fixtures exercise: exp(KronSum) = Kronecker of exp(factor) (unary.py:244-246),
+    pow(Kronecker, a) = Kronecker of pow(factor, a) (:303-305), otherwise LanczosUnary / ArnoldiUnary (:134-142)."""
+    if fn == "exp" and isinstance(A, KronSumOp):
+        return KroneckerOp(*[unary_operator(fn, M, alg, max_iters, tol) for M in A.Ms])
+    if fn in ("sqrt", "isqrt") and isinstance(A, KroneckerOp):
+        return KroneckerOp(*[unary_operator(fn, M, alg, max_iters, tol) for M in A.factors])
+    cls = LanczosUnaryOp if alg == "lanczos" else ArnoldiUnaryOp
+    return cls(A, UNARY_FUNS[fn], max_iters, tol)
+
+
+# ----------------------------------------------------------------------------------
+# Hutchinson / exact diagonals  (cola/linalg/trace/diagonal_estimation.py:84-128, 158-210)
+# ----------------------------------------------------------------------------------
+def hutchinson_diag(matmat, n, dtype, tol=3e-2, max_iters=10000, rand="normal", key=None, k=0):
     bs = min(100, n)
     assert tol > 1e-3, "tolerance chosen too high for stochastic diagonal estimation"
     assert rand in ["normal", "rademacher"], "rand must be 'normal' or 'rademacher'"
@@ -490,8 +568,10 @@ def hutchinson_diag(matmat, n, dtype, tol=3e-2, max_iters=10000, rand="normal", 
         z = keyed_randn(n, bs, dtype=dtype, key=key)
         if rand == "rademacher":
             z = torch.sign(z)
-        z2 = torch.roll(z, 0, 0)
-        est = (matmat(z) * z2)[slice(None, None)]
+        z2 = torch.roll(z, -k, 0)                                         # diagonal_estimation.py:190-193
+        z2[slice(0, abs(k)) if k <= 0 else slice(-abs(k), None)] = 0
+        slc = slice(abs(k), None) if -k > 0 else slice(None, -abs(k) or None)
+        est = (matmat(z) * z2)[slc]
         return i + 1, s1 + est.sum(-1), s2 + (est**2).sum(-1), key
 
     def err(s):
@@ -503,9 +583,33 @@ def hutchinson_diag(matmat, n, dtype, tol=3e-2, max_iters=10000, rand="normal", 
     def cond(s):
         return (s[0] == 0) | ((s[0] < max_iters) & (err(s) > tol))
 
-    zeros = torch.zeros(n, dtype=dtype)
+    zeros = torch.zeros(n - abs(k), dtype=dtype)
     (i, s1, _, _), info = _tracked_while(err, cond, body, (0, zeros, zeros, key))
     return s1 / (i * bs), info
+
+
+def exact_diag(matmat, n, dtype, k=0):
+    """cola/linalg/trace/diagonal_estimation.py:84-128: blocks of 100 identity columns, the k-th diagonal picked out
+    with a shifted copy of the block (get_I_chunk_like)."""
+    bs = min(100, n)
+    eye = torch.eye(n, dtype=dtype)
+    total = 0.
+    for i in range(0, n, bs):
+        if k == 0:
+            chunk = shifted = eye[:, i:i + bs]
+        elif k <= 0:
+            kk = abs(k)
+            I_chunk = eye[:, i:i + bs + kk]
+            padded = torch.zeros(n, bs + kk, dtype=dtype)
+            padded[:, :I_chunk.shape[-1]] = I_chunk
+            chunk, shifted = I_chunk[:, :bs], padded[:, kk:kk + bs]
+        else:
+            I_chunk = eye[:, max(i - k, 0):i + bs]
+            padded = torch.zeros(n, bs + k, dtype=dtype)
+            padded[:, -I_chunk.shape[-1]:] = I_chunk
+            chunk, shifted = I_chunk[:, -bs:], padded[:, :bs]
+        total = total + (matmat(chunk) * shifted).sum(-1)
+    return total[abs(k):] if k <= 0 else total[:(-k or None)]
 
 
 # ----------------------------------------------------------------------------------

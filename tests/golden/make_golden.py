@@ -35,8 +35,9 @@ from cola.linalg.unary.unary import LanczosUnary  # noqa: E402
 from cola.ops import operators as rops  # noqa: E402
 
 from tests import problems as pb  # noqa: E402
-from tests.golden_cases import (ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS,  # noqa: E402
-                                PCG_CASES, POWER_CASES)
+from tests.golden_cases import (ARNOLDI_CASES, CG_CASES, DIAG_CASES, GMRES_CASES, LANCZOS_CASES,  # noqa: E402
+                                MATMAT_PROBLEMS, NEXT_CG_CASES, NEXT_MATMAT_PROBLEMS, PCG_CASES, POWER_CASES,
+                                UNARY_CASES)
 
 assert cola.__file__.startswith("/root/reference"), cola.__file__
 
@@ -76,6 +77,12 @@ def to_reference(spec, ann=None):
             return rops.BlockDiag(*[rec(x) for x in s[1]], multiplicities=s[2])
         if k == "product":
             return rops.Product(*[rec(x) for x in s[1]])
+        if k == "psd":
+            return cola.PSD(rec(s[1]))
+        if k == "kronsum":
+            return rops.KronSum(*[rec(x) for x in s[1]])
+        if k == "tridiag":
+            return rops.Tridiagonal(*s[1:])
         if k == "sum":
             first = rec(s[1][0])
             out = first
@@ -264,17 +271,53 @@ def gen_stochastic():
     save("hutch_diag_dense96_f64", diag=dg)
 
 
+# --------------------------------------------------------------------------- SURVEY 8f items 3-4
+def gen_next():
+    from cola.linalg.trace.diagonal_estimation import Exact
+    for name in NEXT_MATMAT_PROBLEMS:
+        P = pb.problem(name)
+        A = to_reference(P["spec"], P["ann"])
+        X = pb.randn_np((A.shape[1], 6), P["dtype"], 100)
+        save("matmat_" + name, Y=A @ X, y=A @ X[:, 0].contiguous(), sum=checksum(P["spec"], P["B"]))
+    for case, (name, tol, iters) in NEXT_CG_CASES.items():
+        P = pb.problem(name)
+        A = to_reference(P["spec"], P["ann"])
+        x, info = CG(tol=tol, max_iters=iters)(A, P["B"])
+        save(case, x=x, errors=info["errors"], iterations=info["iterations"], sum=checksum(P["spec"], P["B"]))
+    for case, (name, fn, alg, m, tol) in UNARY_CASES.items():
+        P = pb.problem(name)
+        A = to_reference(P["spec"], P["ann"])
+        alg = (Arnoldi if alg == "arnoldi" else Lanczos)(max_iters=m, tol=tol)
+        F = getattr(cola.linalg, fn)(A, alg)
+        Y = F @ P["B"]
+        save(case, Y=Y, kind=type(F).__name__.split("[")[0])
+    for case, (name, k, alg) in DIAG_CASES.items():
+        P = pb.problem(name)
+        A = to_reference(P["spec"], P["ann"])
+        alg = Exact() if alg == "exact" else Hutch(tol=2e-2, max_iters=4, key=A.xnp.PRNGKey(9))
+        save(case, diag=cola.linalg.diag(A, k, alg), dense_diag=torch.diagonal(A.to_dense(), offset=k))
+    # the Lanczos | Arnoldi rule of slogdet returns (tr/|tr|, |tr|)  (logdet.py:111-117): an operator with det < 1
+    P = pb.problem("dense96_f64")
+    A = to_reference(P["spec"], P["ann"])
+    sign, mag = cola.linalg.slogdet(A, Lanczos(max_iters=40, tol=1e-12), Hutch(tol=2e-2, max_iters=2, key=A.xnp.PRNGKey(42)))
+    save("slogdet_lanczos_dense96_f64", sign=sign, logdet=mag, dense_logdet=torch.linalg.slogdet(A.to_dense())[1])
+
+
+GENERATORS = dict(matmat=gen_matmat, cg=gen_cg, lanczos=gen_lanczos, arnoldi=gen_arnoldi, gmres=gen_gmres, pcg=gen_pcg,
+                  power=gen_power, stochastic=gen_stochastic, next=gen_next)
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
-    gen_matmat()
-    gen_cg()
-    gen_lanczos()
-    gen_arnoldi()
-    gen_gmres()
-    gen_pcg()
-    gen_power()
-    gen_stochastic()
-    with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
+    which = sys.argv[1:] or list(GENERATORS)       # `make_golden.py next` regenerates one family only
+    manifest_path = os.path.join(HERE, "MANIFEST.json")
+    previous = json.load(open(manifest_path)) if (sys.argv[1:] and os.path.exists(manifest_path)) else {}
+    MANIFEST["cases"].update(previous.get("cases", {}))
+    repaired = dict(previous.get("sparse_instances_repaired", {}))
+    for name in which:
+        before = len(REPAIRED)
+        GENERATORS[name]()
+        repaired[name] = len(REPAIRED) - before
+    MANIFEST["sparse_instances_repaired"] = repaired     # per generator family
+    with open(manifest_path, "w") as fh:
         json.dump(MANIFEST, fh, indent=1, sort_keys=True)
-    MANIFEST["sparse_instances_repaired"] = len(REPAIRED)
     print("wrote", len(MANIFEST["cases"]), "cases;", len(REPAIRED), "Sparse instances repaired")

@@ -55,3 +55,33 @@ POWER_CASES = {  # case -> (problem, tol, max_iter)   power_iteration(A, key=PRN
     "power_kron465_diag_f64": ("kron465_diag_f64", 1e-8, 300),
     "power_lap24_f64_capped": ("lap24_f64", 1e-12, 25),
 }
+
+# ---- f(A)v operators, exact / off-diagonal estimators, KronSum and Tridiagonal matmats
+NEXT_MATMAT_PROBLEMS = ["kronsum465_f64", "kronsum884_f32", "tridiag200_f64", "tridiag200_shift_f32"]
+
+NEXT_CG_CASES = {  # case -> (problem, tol, max_iters)
+    "cg_kronsum465_f64": ("kronsum465_f64", 1e-10, 200),
+    "cg_kronsum884_f32": ("kronsum884_f32", 1e-6, 200),
+    "cg_tridiag200_shift_f32": ("tridiag200_shift_f32", 1e-6, 200),
+}
+
+UNARY_CASES = {  # case -> (problem, function, algorithm, max_iters, tol)   F = cola.linalg.<function>(A, alg); Y = F @ B
+    "expA_arnoldi_nonsym48_f64": ("nonsym48_f64", "exp", "arnoldi", 20, 1e-12),
+    "logA_arnoldi_nonsym48_f64": ("nonsym48_f64", "log", "arnoldi", 48, 1e-12),
+    "sqrtA_arnoldi_nonsym48_f32": ("nonsym48_f32", "sqrt", "arnoldi", 20, 1e-7),
+    "expA_arnoldi_tridiag200_f64": ("tridiag200_f64", "exp", "arnoldi", 30, 1e-12),
+    "sqrtA_lanczos_kron465_diag_f64": ("kron465_diag_f64", "sqrt", "lanczos", 30, 1e-7),
+    "isqrtA_lanczos_kron884_diag_f32": ("kron884_diag_f32", "isqrt", "lanczos", 25, 1e-7),
+    "expA_lanczos_kronsum465_f64": ("kronsum465_f64", "exp", "lanczos", 8, 1e-12),   # exp(KronSum) -> Kronecker of exp(factor); full Krylov spaces
+    "sqrtA_lanczos_kron888_pure_f32": ("kron888_pure_f32", "sqrt", "lanczos", 8, 1e-7),   # full Krylov spaces (d = 8)   # pow(Kronecker) -> Kronecker of pow(factor)
+}
+
+DIAG_CASES = {  # case -> (problem, k, algorithm)   cola.linalg.diag(A, k, alg)
+    "diag_exact_tridiag200_f64_k0": ("tridiag200_f64", 0, "exact"),
+    "diag_exact_tridiag200_f64_k1": ("tridiag200_f64", 1, "exact"),
+    "diag_exact_tridiag200_f64_km1": ("tridiag200_f64", -1, "exact"),
+    "diag_exact_lap16_shift_f32_k0": ("lap16_shift_f32", 0, "exact"),     # ragged last block (n = 256)
+    "diag_exact_kron465_diag_f64_k0": ("kron465_diag_f64", 0, "exact"),
+    "diag_hutch_product_f64_k2": ("product_f64", 2, "hutch"),
+    "diag_hutch_product_f64_km3": ("product_f64", -3, "hutch"),
+}

@@ -130,6 +130,25 @@ def problem(name):
     if name == "graph2k_f64":         # BASELINE config 5, scaled down
         return dict(spec=("csr", *graph_laplacian_coo(2048, 8, f64, 7)), ann="sa", dtype=f64,
                     B=randn_np((2048, ), f64, 19))
+    if name == "kron888_pure_f32":    # a bare Kronecker product: the structure rules of pow / inv / logdet apply
+        fs = [("psd", ("dense", kron_factor(8, f32, i))) for i in range(3)]
+        return dict(spec=("kron", fs), ann="psd", dtype=f32, B=randn_np((512, 16), f32, 0))
+    if name in ("kronsum465_f64", "kronsum884_f32"):   # KronSum (operators.py:241-275)
+        dt = f64 if name.endswith("f64") else f32
+        dims = (4, 6, 5) if dt == f64 else (8, 8, 4)
+        fs = [("psd", ("dense", kron_factor(d, dt, 20 + i))) for i, d in enumerate(dims)]   # annotated factors
+        n = int(np.prod(dims))
+        return dict(spec=("kronsum", fs), ann="psd", dtype=dt, B=randn_np((n, 7 if dt == f64 else 16), dt, 21))
+    if name == "tridiag200_f64":      # non-symmetric Tridiagonal (operators.py:351-372)
+        g = rs(22)
+        spec = ("tridiag", t(g.normal(size=199), f64), t(g.normal(size=200) + 3.0, f64), t(g.normal(size=199), f64))
+        return dict(spec=spec, ann=None, dtype=f64, B=randn_np((200, 5), f64, 23))
+    if name == "tridiag200_shift_f32":   # symmetric Tridiagonal + c*I + Diagonal: the CSR core with a fused epilogue
+        g = rs(24)
+        off = t(g.uniform(-1.0, 1.0, size=199), f32)
+        spec = ("sum", [("tridiag", off, t(g.uniform(2.5, 3.5, size=200), f32), off), ("scaled_identity", 0.5, 200),
+                        ("diag", t(g.uniform(0.0, 1.0, size=200), f32))])
+        return dict(spec=spec, ann="psd", dtype=f32, B=randn_np((200, 6), f32, 25))
     raise KeyError(name)
 
 
@@ -183,6 +202,12 @@ def to_oracle(spec):
         return ko.BlockDiagOp(*[to_oracle(s) for s in spec[1]], multiplicities=spec[2])
     if kind == "product":
         return ko.ProductOp(*[to_oracle(s) for s in spec[1]])
+    if kind == "psd":
+        return to_oracle(spec[1])
+    if kind == "kronsum":
+        return ko.KronSumOp(*[to_oracle(s) for s in spec[1]])
+    if kind == "tridiag":
+        return ko.TridiagonalOp(*spec[1:])
     if kind == "sum":
         terms = [to_oracle(s) for s in spec[1]]
         dtype = next(tm.dtype for tm in terms if not isinstance(tm, tuple))
@@ -216,6 +241,12 @@ def to_b200(spec, device, ann=None):
             return ops.BlockDiag(*[rec(x) for x in s[1]], multiplicities=s[2])
         if k == "product":
             return ops.Product(*[rec(x) for x in s[1]])
+        if k == "psd":
+            return cb.PSD(rec(s[1]))
+        if k == "kronsum":
+            return ops.KronSum(*[rec(x) for x in s[1]])
+        if k == "tridiag":
+            return ops.Tridiagonal(*[v.to(device) for v in s[1:]])
         if k == "sum":
             first = rec(s[1][0])
             out = first

@@ -1,0 +1,172 @@
+"""GPU parity tests for the SURVEY 8f rows built after the main path: f(A)v through Lanczos / Arnoldi with the
+exp / log / sqrt / isqrt / pow dispatch surface, exact and off-diagonal estimators, KronSum and Tridiagonal
+matmats (and CG on them).  Same bar as tests/test_gpu_parity.py: the CUDA path through the C ABI against the CPU
+oracle on identical inputs and against fixtures the real reference produced; 1e-5 (fp32) / 1e-10 (fp64)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import problems as pb
+from tests import test_gpu_parity as gp
+from tests.golden_cases import DIAG_CASES, NEXT_CG_CASES, NEXT_MATMAT_PROBLEMS, UNARY_CASES
+from tests.test_gpu_parity import rel, tol_of
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import cola_b200
+    assert torch.cuda.is_available()
+    cola_b200.backend.lib()  # fails loudly if the extension is missing
+    cola_b200.rng.PROBE_DEVICE = "cpu"
+    return cola_b200
+
+
+def crel(a, b):
+    """Relative distance that also takes complex arrays."""
+    a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+# ------------------------------------------------------------------------------------------- KronSum / Tridiagonal
+@pytest.mark.parametrize("name", NEXT_MATMAT_PROBLEMS)
+def test_matmat_kronsum_tridiagonal(name, golden, cb):
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    O = pb.to_oracle(P["spec"])
+    t = tol_of(P["dtype"])
+    X = pb.randn_np((A.shape[1], 6), P["dtype"], 100)
+    g = golden("matmat_" + name)
+    assert rel(A @ X.to(DEV), g["Y"]) < t
+    assert rel(A @ X[:, 0].contiguous().to(DEV), g["y"]) < t
+    X2 = pb.randn_np((A.shape[1], 33), P["dtype"], 101)          # ragged RHS count
+    assert rel(A @ X2.to(DEV), O.matmat(X2)) < t
+    # fused <x, y> dots, and the transpose (KronSum of transposed factors / swapped bands)
+    Xd = X2.to(DEV)
+    Y = torch.empty_like(Xd)
+    dots = torch.zeros(33, dtype=torch.float64, device=DEV)
+    A.matmat_into(Xd, Y, dots=dots)
+    assert rel(Y, O.matmat(X2)) < t and rel(dots, (X2.double() * O.matmat(X2).double()).sum(0)) < t
+    dense = O.matmat(torch.eye(A.shape[1], dtype=P["dtype"]))
+    assert rel(A.T @ Xd, dense.T @ X2) < 10 * t
+    assert rel(A.to_dense(), dense) < t
+
+
+@pytest.mark.parametrize("case", sorted(NEXT_CG_CASES))
+def test_cg_on_kronsum_and_tridiagonal(case, golden, cb, monkeypatch):
+    monkeypatch.setitem(gp.CG_CASES, case, NEXT_CG_CASES[case])
+    gp.test_cg_vs_oracle_and_golden(case, golden, cb)
+
+
+# ------------------------------------------------------------------------------------------- f(A) v
+@pytest.mark.parametrize("case", sorted(UNARY_CASES))
+def test_unary_functions(case, golden, cb):
+    from oracle import krylov_oracle as ko
+    name, fn, alg, m, tol = UNARY_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    L = cb.linalg
+    algo = (L.Arnoldi if alg == "arnoldi" else L.Lanczos)(max_iters=m, tol=tol)
+    F = getattr(L, fn)(A, algo)
+    g = golden(case)
+    assert type(F).__name__ == str(g["kind"])
+    Y = F @ P["B"].to(DEV)
+    assert tuple(Y.shape) == tuple(g["Y"].shape) and Y.cpu().numpy().dtype == g["Y"].dtype
+    Yo = ko.unary_operator(fn, pb.to_oracle(P["spec"]), alg, m, tol).matmat(P["B"])
+    # f(A)v inherits the conditioning of the small eigenproblem (eig(H) / eigh(T)): 100x the strict bar, as for
+    # the log(A) V fixtures of the main path
+    t = 100 * tol_of(P["dtype"])
+    assert crel(Y, Yo) < t, crel(Y, Yo)
+    assert crel(Y, g["Y"]) < t, crel(Y, g["Y"])
+    if alg == "arnoldi":
+        # identity that does not depend on any implementation: exp/log/sqrt of the dense matrix
+        import scipy.linalg as sl
+        Ad = pb.to_oracle(P["spec"]).matmat(torch.eye(A.shape[0], dtype=P["dtype"])).double().numpy()
+        dense = {"exp": sl.expm, "log": sl.logm, "sqrt": sl.sqrtm}[fn](Ad) @ P["B"].double().numpy()
+        assert crel(Y.to(torch.complex128), dense) < (1e-4 if P["dtype"] == torch.float32 else 1e-6)
+
+
+def test_unary_structure_rules(cb):
+    """unary.py:181-205 and the integer cases of pow (:265-300) that need no solver."""
+    L, ops = cb.linalg, cb.ops
+    d = torch.linspace(0.5, 2.0, 12, dtype=torch.float64, device=DEV)
+    alg = L.Lanczos(max_iters=12, tol=1e-12)
+    assert rel(L.exp(ops.Diagonal(d), alg).diag, torch.exp(d)) == 0.0
+    assert rel(L.isqrt(ops.Diagonal(d), alg).diag, d**-0.5) < 1e-15
+    I = ops.I_like(ops.Diagonal(d))
+    X = torch.ones(12, 2, dtype=torch.float64, device=DEV)
+    assert rel(L.exp(I, alg) @ X, np.e * np.ones((12, 2))) < 1e-15
+    assert rel(L.log(3.0 * I, alg) @ X, np.log(3.0) * np.ones((12, 2))) < 1e-15
+    M = pb.spd_dense(6, torch.float64, 31).to(DEV)
+    B = ops.BlockDiag(cb.PSD(ops.Dense(M)), ops.Diagonal(d[:4]), multiplicities=[2, 1])
+    FB = L.sqrt(B, L.Lanczos(max_iters=6, tol=1e-12))
+    assert isinstance(FB, ops.BlockDiag) and FB.multiplicities == [2, 1]
+    w, V = torch.linalg.eigh(M)
+    sq = (V * w.sqrt()) @ V.T
+    ref = torch.block_diag(sq, sq, torch.diag(d[:4].sqrt()))
+    Xb = torch.randn(16, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0)).to(DEV)
+    assert rel(FB @ Xb, ref @ Xb) < 1e-9
+    A = cb.PSD(ops.Dense(M))
+    assert rel(L.pow(A, 2, alg) @ Xb[:6], M @ (M @ Xb[:6])) < 1e-13
+    assert isinstance(L.pow(A, 0, alg), ops.Identity)
+    with pytest.raises(AssertionError, match="SelfAdjoint"):
+        L.sqrt(ops.Dense(M), alg)
+    # small PSD operators with Auto take the dense eigh (unary.py:113-131,160-168)
+    assert rel(L.sqrt(A) @ Xb[:6], sq @ Xb[:6]) < 1e-12
+
+
+def test_pow_minus_one_is_a_solve(cb):
+    """pow(A, -1, Lanczos) -> inv(A, CG) and pow(A, -1, Arnoldi) -> inv(A, GMRES)  (unary.py:283-297)."""
+    L = cb.linalg
+    P = pb.problem("dense96_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    B = P["B"].to(DEV)
+    X = L.pow(A, -1, L.Lanczos(max_iters=500, tol=1e-11)) @ B
+    assert rel(A @ X, B) < 1e-8
+    P = pb.problem("nonsym48_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    B = P["B"].to(DEV)
+    X = L.pow(A, -1, L.Arnoldi(max_iters=48, tol=1e-12)) @ B
+    assert rel(A @ X, B) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------- diagonals
+@pytest.mark.parametrize("case", sorted(DIAG_CASES))
+def test_exact_and_offset_diagonals(case, golden, cb):
+    name, k, alg = DIAG_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    L = cb.linalg
+    g = golden(case)
+    t = tol_of(P["dtype"])
+    if alg == "exact":
+        d = L.diag(A, k, L.Exact())
+        assert rel(d, g["dense_diag"]) < t
+    else:
+        d = L.diag(A, k, L.Hutch(tol=2e-2, max_iters=4, key=cb.rng.PRNGKey(9)))
+    assert tuple(d.shape) == tuple(g["diag"].shape) and rel(d, g["diag"]) < t
+
+
+def test_exact_diag_ragged_blocks_and_trace(cb):
+    """n = 250 is not a multiple of the 100-column block: every offset still comes out exact; trace = sum diag."""
+    L, ops = cb.linalg, cb.ops
+    M = pb.randn_np((250, 250), torch.float64, 41)
+    A = ops.Product(ops.Dense(M.to(DEV)), ops.Dense(torch.eye(250, dtype=torch.float64, device=DEV)))
+    for k in (0, 1, -1, 7, -120):
+        assert rel(L.diag(A, k, L.Exact()), torch.diagonal(M, offset=k)) < 1e-13
+    assert abs(float(L.trace(A, L.Exact())) - float(torch.trace(M))) < 1e-10
+
+
+def test_slogdet_lanczos_rule(golden, cb):
+    """logdet.py:111-117 returns (tr/|tr|, |tr log A|); restated as is (det < 1 here, so the sign is -1)."""
+    L = cb.linalg
+    P = pb.problem("dense96_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    g = golden("slogdet_lanczos_dense96_f64")
+    sign, mag = L.slogdet(A, L.Lanczos(max_iters=40, tol=1e-12), L.Hutch(tol=2e-2, max_iters=2, key=cb.rng.PRNGKey(42)))
+    assert float(sign) == float(g["sign"]) == -1.0
+    assert abs(float(mag) - float(g["logdet"])) < 1e-8 * float(g["logdet"])

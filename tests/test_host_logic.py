@@ -8,13 +8,16 @@ import torch
 
 import cola_b200
 from tests import test_gpu_parity as gp
-from tests.golden_cases import ARNOLDI_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, POWER_CASES
+from tests import test_gpu_parity_next as gn
+from tests.golden_cases import (ARNOLDI_CASES, DIAG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, NEXT_MATMAT_PROBLEMS,
+                                POWER_CASES, UNARY_CASES)
 from tests.host_harness import emulated_kernels
 
 
 @pytest.fixture(params=[False, True], ids=["two-kernel-cgs2", "fused-cgs2"])
 def emu_both(request, monkeypatch):
     monkeypatch.setattr(gp, "DEV", "cpu")
+    monkeypatch.setattr(gn, "DEV", "cpu")
     with emulated_kernels(fused=request.param):
         yield cola_b200
 
@@ -22,6 +25,7 @@ def emu_both(request, monkeypatch):
 @pytest.fixture
 def emu(monkeypatch):
     monkeypatch.setattr(gp, "DEV", "cpu")
+    monkeypatch.setattr(gn, "DEV", "cpu")
     with emulated_kernels():
         yield cola_b200
 
@@ -97,3 +101,28 @@ def test_log_matmat_and_hutch_logdet(name, m, golden, emu):
 
 def test_hutch_rademacher_and_errors(golden, emu):
     gp.test_hutch_rademacher_and_errors(golden, emu)
+
+
+# ---- SURVEY 8f rows (tests/test_gpu_parity_next.py bodies; the CG-based ones stay GPU-only)
+@pytest.mark.parametrize("name", NEXT_MATMAT_PROBLEMS)
+def test_matmat_kronsum_tridiagonal(name, golden, emu):
+    gn.test_matmat_kronsum_tridiagonal(name, golden, emu)
+
+
+@pytest.mark.parametrize("case", sorted(UNARY_CASES))
+def test_unary_functions(case, golden, emu):
+    gn.test_unary_functions(case, golden, emu)
+
+
+def test_unary_structure_rules(emu):
+    gn.test_unary_structure_rules(emu)
+
+
+@pytest.mark.parametrize("case", sorted(DIAG_CASES))
+def test_exact_and_offset_diagonals(case, golden, emu):
+    gn.test_exact_and_offset_diagonals(case, golden, emu)
+
+
+def test_exact_diag_ragged_and_slogdet_rule(golden, emu):
+    gn.test_exact_diag_ragged_blocks_and_trace(emu)
+    gn.test_slogdet_lanczos_rule(golden, emu)

@@ -9,7 +9,8 @@ import torch
 
 from oracle import krylov_oracle as ko
 from tests import problems as pb
-from tests.golden_cases import ARNOLDI_CASES, CG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, PCG_CASES, POWER_CASES
+from tests.golden_cases import (ARNOLDI_CASES, CG_CASES, DIAG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS,
+                                NEXT_CG_CASES, NEXT_MATMAT_PROBLEMS, PCG_CASES, POWER_CASES, UNARY_CASES)
 
 
 def rel(a, b):
@@ -22,7 +23,7 @@ def tol_of(dtype):
     return 2e-6 if dtype == torch.float32 else 1e-12
 
 
-@pytest.mark.parametrize("name", MATMAT_PROBLEMS)
+@pytest.mark.parametrize("name", MATMAT_PROBLEMS + NEXT_MATMAT_PROBLEMS)
 def test_matmat(name, golden):
     P = pb.problem(name)
     A = pb.to_oracle(P["spec"])
@@ -32,9 +33,9 @@ def test_matmat(name, golden):
     assert rel(A @ X[:, 0].contiguous(), g["y"]) < tol_of(P["dtype"])
 
 
-@pytest.mark.parametrize("case", sorted(CG_CASES))
+@pytest.mark.parametrize("case", sorted(CG_CASES) + sorted(NEXT_CG_CASES))
 def test_cg(case, golden):
-    name, tol, iters = CG_CASES[case]
+    name, tol, iters = {**CG_CASES, **NEXT_CG_CASES}[case]
     P = pb.problem(name)
     A = pb.to_oracle(P["spec"])
     x, r, k, info = ko.cg(A, P["B"], tol=tol, max_iters=iters)
@@ -212,6 +213,54 @@ def test_hutch_rademacher(golden):
     A = pb.to_oracle(P["spec"])
     mean, info = ko.hutchinson_diag(A.matmat, 96, A.dtype, tol=5e-2, max_iters=4, rand="rademacher", key=ko.PRNGKey(7))
     assert rel(mean, golden("hutch_diag_dense96_f64")["diag"]) < 1e-12
+
+
+@pytest.mark.parametrize("case", sorted(UNARY_CASES))
+def test_unary_functions(case, golden):
+    """exp / log / sqrt / isqrt through LanczosUnary, ArnoldiUnary (complex result) and the KronSum / Kronecker rules."""
+    name, fn, alg, m, tol = UNARY_CASES[case]
+    P = pb.problem(name)
+    F = ko.unary_operator(fn, pb.to_oracle(P["spec"]), alg, m, tol)
+    g = golden(case)
+    Y = F.matmat(P["B"])
+    assert Y.numpy().dtype == g["Y"].dtype and tuple(Y.shape) == tuple(g["Y"].shape)
+    d = np.linalg.norm(Y.numpy() - g["Y"]) / np.linalg.norm(g["Y"])
+    assert d < 100 * tol_of(P["dtype"]), d
+
+
+@pytest.mark.parametrize("case", sorted(DIAG_CASES))
+def test_exact_and_offset_diagonals(case, golden):
+    name, k, alg = DIAG_CASES[case]
+    P = pb.problem(name)
+    A = pb.to_oracle(P["spec"])
+    g = golden(case)
+    if alg == "exact":
+        d = ko.exact_diag(A.matmat, A.shape[0], A.dtype, k)
+        assert rel(d, g["dense_diag"]) < tol_of(P["dtype"])
+    else:
+        d, _ = ko.hutchinson_diag(A.matmat, A.shape[0], A.dtype, tol=2e-2, max_iters=4, key=ko.PRNGKey(9), k=k)
+    assert tuple(d.shape) == tuple(g["diag"].shape) and rel(d, g["diag"]) < tol_of(P["dtype"])
+
+
+def test_exact_diag_reference_limit():
+    """The reference's shifted-identity blocks (diagonal_estimation.py:84-128) do not line up on a ragged last
+    block when k != 0 (n = 250, bs = 100); the restatement inherits that, the product path does not."""
+    M = torch.eye(250, dtype=torch.float64)
+    assert rel(ko.exact_diag(lambda X: M @ X, 250, torch.float64, 0), np.ones(250)) == 0.0
+    with pytest.raises(RuntimeError):
+        ko.exact_diag(lambda X: M @ X, 250, torch.float64, 1)
+
+
+def test_slogdet_lanczos_rule_returns_magnitude(golden):
+    """logdet.py:111-117 returns (tr/|tr|, |tr log A|): for det(A) < 1 the 'logdet' is the magnitude."""
+    P = pb.problem("dense96_f64")
+    A = pb.to_oracle(P["spec"])
+    g = golden("slogdet_lanczos_dense96_f64")
+    mean, _ = ko.hutchinson_diag(lambda Z: ko.lanczos_unary_matmat(A, torch.log, Z, 40, 1e-12)[0], 96, A.dtype,
+                                 tol=2e-2, max_iters=2, key=ko.PRNGKey(42))
+    tr = mean.sum()
+    assert float(g["sign"]) == -1.0 and float(g["dense_logdet"]) < 0
+    assert abs(float(abs(tr)) - float(g["logdet"])) < 1e-9 * float(g["logdet"]) and float(tr / abs(tr)) == -1.0
 
 
 def test_rng_key_chain():
