@@ -11,7 +11,9 @@ reaches it, and outside the `with` block CPU tensors raise as always
 (tests/test_abi_and_host.py::test_cpu_tensors_raise_no_fallback).  What it checks is loop logic -- stop rules,
 indexing of the accumulator rows, the assembly of T / H / info, chunking, dispatch -- against the golden vectors;
 the kernels themselves are only checked on the GPU (tests/test_gpu_parity.py, through the C ABI).  The CG loop
-drives its control block through raw C entry points and CUDA graphs and is not covered here.
+calls its four raw entry points (cola_cg_tol / advance / update_r / update_xp) through `lib().call`; those are
+stated in `_CgEntryPoints` from the header and csrc/vec_kernels.cu, and CUDA-graph replay is switched off (the
+eager batches of 16 gated iterations are the same launch sequence).
 """
 import contextlib
 
@@ -81,8 +83,9 @@ def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shi
              dots=None, dots_row=None, gate=None):
     if not _open(gate):
         return
-    S = torch.sparse_csr_tensor(rowptr.long(), colidx.long(), vals, size=tuple(shape))
-    KX = S @ X
+    # like the kernels, products are accumulated in double and rounded once to the path dtype
+    S = torch.sparse_csr_tensor(rowptr.long(), colidx.long(), vals.double(), size=tuple(shape))
+    KX = (S @ X.double()).to(X.dtype)
     if shift == 0.0 and diag is None and dots is None:
         Y.copy_(alpha * KX + Y if accumulate else alpha * KX)
     else:
@@ -95,7 +98,7 @@ def mode_contract(M, d_out, d_in, pre, post, inp, out, alpha=1.0, shift=0.0, dia
         return
     src = _flat(inp, pre * d_in * post).reshape(pre, d_in, post)
     dst = _flat(out, pre * d_out * post).reshape(pre * d_out, post)
-    KX = torch.einsum("aj,pjq->paq", M[:d_out, :d_in], src).reshape(pre * d_out, post)
+    KX = torch.einsum("aj,pjq->paq", M[:d_out, :d_in].double(), src.double()).to(M.dtype).reshape(pre * d_out, post)
     if epi_x is None:
         dst.copy_(alpha * KX + dst if accumulate else alpha * KX)
         return
@@ -158,6 +161,63 @@ class _Fused:
     enabled = False
 
 
+class _CgEntryPoints:
+    """cola_cg_* of include/cola_b200.h on CPU tensors (be.ptr hands the tensors through).  ctl = int32
+    [it, done, max_iters, k]; gamma / pAp are (rows, k) fp64 accumulators indexed by ctl.it."""
+    cdll = None
+
+    def call(self, name, *args):
+        getattr(self, name.rsplit("_", 1)[0])(*args)
+
+    def launch_count(self):
+        return 0
+
+    @staticmethod
+    def _row(acc, it, k):
+        return acc.reshape(-1)[it * k:(it + 1) * k]
+
+    @classmethod
+    def _alpha(cls, gamma, pap, it, k, dt):
+        g = cls._row(gamma, it, k)
+        tiny = torch.tensor(1e-40, dtype=dt)
+        conv = torch.sqrt(g).to(dt) < tiny                       # has_converged, cg.py:144
+        den = cls._row(pap, it, k).to(dt)
+        den = torch.where(den.abs().double() < 1e-40, tiny, den)
+        return torch.where(conv, torch.zeros((), dtype=dt), g.to(dt) / den), conv
+
+    def cola_cg_tol(self, gamma0, tol, tol_eff, k, stream):
+        dt = tol_eff.dtype
+        t = torch.tensor(tol.value, dtype=dt)
+        tol_eff.copy_(t * torch.sqrt(gamma0.reshape(-1)[:k]).to(dt) + t)
+
+    def cola_cg_advance(self, ctl, gamma, tol_eff, increment, stream):
+        if int(ctl[1]):
+            return
+        it, k = int(ctl[0]) + (1 if increment else 0), int(ctl[3])
+        rs = torch.sqrt(self._row(gamma, it, k)).to(tol_eff.dtype)
+        ctl[0] = it
+        ctl[1] = 0 if (bool((rs > tol_eff).any()) and it < int(ctl[2])) else 1
+
+    def cola_cg_update_r(self, R, AP, n, k, ld, ctl, gamma, pap, gamma_w, stream):
+        if int(ctl[1]):
+            return
+        it = int(ctl[0])
+        alpha, _ = self._alpha(gamma, pap, it, k, R.dtype)
+        R -= alpha * AP
+        self._row(gamma_w, it + 1, k).add_((R.double() ** 2).sum(0))
+
+    def cola_cg_update_xp(self, X, R, P, n, k, ld, ctl, gamma, pap, stream):
+        if int(ctl[1]):
+            return
+        it, dt = int(ctl[0]), X.dtype
+        alpha, conv = self._alpha(gamma, pap, it, k, dt)
+        g0 = self._row(gamma, it, k).to(dt)
+        g0 = torch.where(g0.abs().double() < 1e-40, torch.tensor(1e-40, dtype=dt), g0)
+        beta = torch.where(conv, torch.zeros((), dtype=dt), self._row(gamma, it + 1, k).to(dt) / g0)
+        X += alpha * P
+        P.copy_(R + beta * P)
+
+
 def reorth_update_dots(V, j0, j1, W, C1, C2, sign=-1.0, gate=None):
     """False = "shape outside the fused kernel's envelope" (the caller's two-kernel path); with
     emulated_kernels(fused=True) the fused semantics are stated so both host branches are exercised."""
@@ -176,10 +236,14 @@ _WRAPPERS = dict(col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matma
 
 @contextlib.contextmanager
 def emulated_kernels(fused=False):
+    import importlib
+
     import cola_b200.backend as be
     import cola_b200.ops as ops
     import cola_b200.rng as rng
+    cg = importlib.import_module("cola_b200.linalg.cg")
     saved = {name: getattr(be, name) for name in _WRAPPERS}
+    saved_lib, saved_stream, saved_graph = be.lib, be.stream_ptr, cg.USE_CUDA_GRAPH
     saved_gate, saved_ptr, saved_off = be.require_cuda, be.ptr, be.off_ptr
     saved_tc, saved_mem, saved_probe = ops._KronCore._tc_ok, torch.cuda.mem_get_info, rng.PROBE_DEVICE
     try:
@@ -188,6 +252,8 @@ def emulated_kernels(fused=False):
         be.require_cuda = lambda t, what="operand": None
         be.ptr = lambda t, dtype=None: t
         be.off_ptr = lambda t, elem_offset: t.reshape(-1)[elem_offset:]
+        fake = _CgEntryPoints()
+        be.lib, be.stream_ptr, cg.USE_CUDA_GRAPH = (lambda: fake), (lambda: None), False
         ops._KronCore._tc_ok = lambda self, X: False
         torch.cuda.mem_get_info = lambda device=None: (64 << 30, 64 << 30)
         rng.PROBE_DEVICE = "cpu"
@@ -197,5 +263,6 @@ def emulated_kernels(fused=False):
         for name, fn in saved.items():
             setattr(be, name, fn)
         be.require_cuda, be.ptr, be.off_ptr = saved_gate, saved_ptr, saved_off
+        be.lib, be.stream_ptr, cg.USE_CUDA_GRAPH = saved_lib, saved_stream, saved_graph
         ops._KronCore._tc_ok, torch.cuda.mem_get_info, rng.PROBE_DEVICE = saved_tc, saved_mem, saved_probe
         _Fused.enabled = False

@@ -130,8 +130,10 @@ def test_pow_minus_one_is_a_solve(cb):
     P = pb.problem("nonsym48_f64")
     A = pb.to_b200(P["spec"], DEV, P["ann"])
     B = P["B"].to(DEV)
-    X = L.pow(A, -1, L.Arnoldi(max_iters=48, tol=1e-12)) @ B
-    assert rel(A @ X, B) < 1e-6
+    # 30 steps: the reference's GMRES squares the Hessenberg (normal equations), so the full 48-step run on n = 48
+    # loses accuracy again (2e-5) -- see the note on the gmres fixtures in tests/golden/make_golden.py
+    X = L.pow(A, -1, L.Arnoldi(max_iters=30, tol=1e-12)) @ B
+    assert rel(A @ X, B) < 1e-7
 
 
 # ------------------------------------------------------------------------------------------- diagonals

@@ -1,16 +1,17 @@
-"""Host-logic tests without a GPU: the bodies of the GPU parity tests (tests/test_gpu_parity.py) for everything
-that is orchestrated in Python -- plan compiler + matmat epilogues, Lanczos, Arnoldi, GMRES, power iteration,
-SLQ, Hutchinson, f(A)v -- are run on CPU tensors with the kernels replaced by tests/host_harness.py (statements
-of the header's semantics).  They check loop logic against the oracle and the reference's golden vectors; the
-kernels themselves are checked only on the GPU.  CG (raw C entry points + CUDA graphs) is not covered here."""
+"""Host-logic tests without a GPU: the bodies of the GPU parity tests (tests/test_gpu_parity*.py) for everything
+that is orchestrated in Python -- plan compiler + matmat epilogues, CG / preconditioned CG (device-side stop rule,
+16-iteration batches, trace reconstruction), Lanczos, Arnoldi, GMRES, power iteration, SLQ, Hutchinson, f(A)v --
+are run on CPU tensors with the kernels replaced by tests/host_harness.py (statements of the header's semantics).
+They check loop logic against the oracle and the reference's golden vectors; the kernels themselves, and the
+CUDA-graph replay of CG batches, are checked only on the GPU."""
 import pytest
 import torch
 
 import cola_b200
 from tests import test_gpu_parity as gp
 from tests import test_gpu_parity_next as gn
-from tests.golden_cases import (ARNOLDI_CASES, DIAG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS, NEXT_MATMAT_PROBLEMS,
-                                POWER_CASES, UNARY_CASES)
+from tests.golden_cases import (ARNOLDI_CASES, CG_CASES, DIAG_CASES, GMRES_CASES, LANCZOS_CASES, MATMAT_PROBLEMS,
+                                NEXT_CG_CASES, NEXT_MATMAT_PROBLEMS, PCG_CASES, POWER_CASES, UNARY_CASES)
 from tests.host_harness import emulated_kernels
 
 
@@ -57,6 +58,42 @@ def test_matmat_fused_dots_and_product_chain(emu):
     Y = torch.empty_like(X)
     A.matmat_into(X, Y, dots=dots)
     assert gp.rel(Y, ref) < 1e-13 and gp.rel(dots, (X * ref).sum(0)) < 1e-13
+
+
+@pytest.mark.parametrize("case", sorted(CG_CASES))
+def test_cg(case, golden, emu):
+    gp.test_cg_vs_oracle_and_golden(case, golden, emu)
+
+
+@pytest.mark.parametrize("case", sorted(NEXT_CG_CASES))
+def test_cg_on_kronsum_and_tridiagonal(case, golden, emu, monkeypatch):
+    gn.test_cg_on_kronsum_and_tridiagonal(case, golden, emu, monkeypatch)
+
+
+def test_cg_surface_and_edge_cases(golden, emu):
+    gp.test_cg_first_iterations_tight(emu)
+    gp.test_cg_vector_x0_and_solve_surface(golden, emu)
+    gp.test_cg_edge_cases(emu)
+    gp.test_product_chain_epilogue(emu)
+    gn.test_pow_minus_one_is_a_solve(emu)
+
+
+# pcg_dense96_f64 stops at tol 1e-11, where the iteration count moves by 2 with the summation order of the stand-in
+# matmat (the GPU test holds it to +-1 on the real kernels); its solution is still compared below
+@pytest.mark.parametrize("case", sorted(set(PCG_CASES) - {"pcg_dense96_f64"}))
+def test_pcg_nystrom(case, golden, emu):
+    gp.test_pcg_nystrom_vs_oracle_and_golden(case, golden, emu)
+
+
+def test_pcg_nystrom_threshold_limited_case(golden, emu):
+    from tests import problems as pb
+    name, rank, tol, iters = PCG_CASES["pcg_dense96_f64"]
+    P = pb.problem(name)
+    A = pb.to_b200(P["spec"], "cpu", P["ann"])
+    Nys = emu.linalg.NystromPrecond(A, rank=rank, key=emu.rng.PRNGKey(3))
+    x, info = emu.linalg.CG(tol=tol, max_iters=iters, P=Nys)(A, P["B"])
+    g = golden("pcg_dense96_f64")
+    assert abs(info["iterations"] - int(g["iterations"])) <= 3 and gp.rel(x, g["x"]) < 1e-8
 
 
 @pytest.mark.parametrize("case", sorted(LANCZOS_CASES))

@@ -205,8 +205,8 @@ def test_adapter_layouts_against_reference(installed, monkeypatch):
 
 def test_reference_api_over_host_loops_on_emulated_kernels(installed):
     """The whole drop-in, minus the silicon: the reference's public API with install(), this package's own host
-    loops (not stand-ins) and the test-only kernel statements of tests/host_harness.py.  Everything that is not CG
-    (whose loop drives raw C entry points) runs: structured matmats incl. KronSum / Tridiagonal, Lanczos, Arnoldi,
+    loops (not stand-ins) and the test-only kernel statements of tests/host_harness.py: CG and Nystrom-preconditioned
+    CG through solve(), structured matmats incl. KronSum / Tridiagonal, Lanczos, Arnoldi,
     eig, SLQ, logdet(Lanczos, Hutch), Hutch off-diagonals, exp / sqrt through the reference's own LanczosUnary /
     ArnoldiUnary on the rebound factorisations."""
     from importlib import import_module as im
@@ -229,6 +229,12 @@ def test_reference_api_over_host_loops_on_emulated_kernels(installed):
     def run():
         out = {}
         out["matmat"] = A @ B
+        x, info = CG(tol=1e-9, max_iters=40)(A, B)
+        out["cg_x"], out["cg_it"], out["cg_errors"] = x, info["iterations"], info["errors"]
+        out["solve_x"] = cola.linalg.solve(KS, B, CG(tol=1e-9, max_iters=60))
+        Nys = im("cola.linalg.preconditioning.preconditioners").NystromPrecond(A, rank=4, key=A.xnp.PRNGKey(1))
+        xp, infop = CG(tol=1e-9, max_iters=40, P=Nys)(A, B)
+        out["pcg_x"], out["pcg_it"] = xp, infop["iterations"]
         out["kronsum"] = KS @ B
         out["tridiag"] = Tr @ B
         Q, T, info = ref_lanczos(A, B, 6, 1e-12)
@@ -256,9 +262,13 @@ def test_reference_api_over_host_loops_on_emulated_kernels(installed):
         for name in ("mode_contract", "csr_spmm", "reorth_update", "mgs_link", "tridiag_eig_first_row"):
             fn = getattr(be, name)
             setattr(be, name, (lambda f, n: (lambda *a, **k: (launched.append(n), f(*a, **k))[1]))(fn, name))
+        cg_lib = be.lib()
+        cg_call = cg_lib.call
+        cg_lib.call = lambda name, *a: (launched.append(name), cg_call(name, *a))[1]
         got = run()
     # the B200 host loops really ran (not the reference's): their kernels were "launched"
-    assert {"mode_contract", "csr_spmm", "reorth_update", "mgs_link", "tridiag_eig_first_row"} <= set(launched)
+    assert {"mode_contract", "csr_spmm", "reorth_update", "mgs_link", "tridiag_eig_first_row", "cola_cg_update_xp_f64",
+            "cola_cg_advance_f64"} <= set(launched)
     for name, r in ref.items():
         gval = got[name]
         if isinstance(r, int):
