@@ -325,9 +325,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (xin != nullptr) {
               if (a.shift != 0.f) y += a.shift * xv[i];
               if (dg != nullptr) y += dv[i] * xv[i];
-              if (a.dots != nullptr) dacc += (double)xv[i] * (double)y;
             }
             if (a.accumulate) y += ov[i];
+            // <x, y> of the value that is stored, earlier terms of a Sum included (same contract as the SIMT and CSR
+            // epilogues: the dots are those of the whole operator)
+            if (xin != nullptr && a.dots != nullptr) dacc += (double)xv[i] * (double)y;
           }
           outp[o] = y;
         }
@@ -635,8 +637,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
                 float y = alpha * __uint_as_float(v[c * 16 + i]);
                 if (a.shift != 0.f) y += a.shift * xv[i];
                 if (dg != nullptr) y += dg[((p * kD + h * 32 + c * 16 + i) << lsh) + l] * xv[i];
-                dacc += (double)xv[i] * (double)y;
                 if (accumulate) y += outp[o];
+                dacc += (double)xv[i] * (double)y;     // of the stored value: earlier terms of a Sum included
                 outp[o] = y;
               }
             }
@@ -836,6 +838,63 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
       rc = cuda_status("kron_mode_tc");
       if (rc) return rc;
       src = dst; src_k = a.out_k; src_r0 = a.out_r0;
+    }
+  }
+  return COLA_OK;
+}
+
+int cola_kronsum_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
+                               float* Y, int64_t k, float alpha, float shift, const float* diag, int accumulate,
+                               double* dots, const int32_t* dots_row, const int32_t* gate, void* stream) {
+  COLA_REQUIRE(factors && ldf && X && Y, "kronsum_tc: null pointer");
+  COLA_REQUIRE(X != Y, "kronsum_tc: X and Y must not alias");
+  COLA_REQUIRE(n_factors >= 2 && n_factors <= 8, "kronsum_tc: 2..8 factors of 64x64");
+  COLA_REQUIRE(k >= 32 && k % 32 == 0, "kronsum_tc: k must be a multiple of 32");
+  COLA_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0), "kronsum_tc: X/Y must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int64_t n = 1;
+  for (int64_t i = 0; i < n_factors; ++i) n *= kD;
+  COLA_REQUIRE((n / kD) % 4 == 0, "kronsum_tc: n / 64 must be a multiple of 4");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kron_mode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    attr_set = true;
+  }
+  CUtensorMap fac_maps[8], in_maps[8];
+  int64_t pres[8], Ls[8];
+  for (int64_t i = 0; i < n_factors; ++i) {
+    COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kronsum_tc: factor alignment");
+    int rc = make_map_fac(&fac_maps[i], factors[i], ldf[i]);
+    if (rc) return rc;
+    pres[i] = 1; Ls[i] = 1;
+    for (int64_t j = 0; j < i; ++j) pres[i] *= kD;
+    for (int64_t j = i + 1; j < n_factors; ++j) Ls[i] *= kD;
+    rc = make_map_in(&in_maps[i], X, pres[i], Ls[i], k);      // every mode contracts X itself
+    if (rc) return rc;
+  }
+  const int grid_max = sm_count();
+  const bool epi = (shift != 0.f) || diag || dots;
+  // A 32-column chunk of right-hand sides goes through ALL modes before the next one starts: its slice of X
+  // (n*32 floats) is fetched from HBM by the first mode and found in L2 by the others, its slice of Y is
+  // read-modified in L2, so the sum of D contractions moves about what one does.
+  for (int64_t r0 = 0; r0 < k; r0 += 32) {
+    for (int64_t i = 0; i < n_factors; ++i) {
+      const bool last = (i == n_factors - 1);
+      TcArgs a;
+      a.out = Y; a.L = Ls[i]; a.pre = pres[i];
+      a.in_r0 = r0; a.out_k = k; a.out_r0 = r0;
+      a.n_tiles = pres[i] * Ls[i] / 4; a.alpha = alpha;
+      a.last_mode = 1;                                         // epilogue indexing is mode-independent
+      a.accumulate = (i > 0 || accumulate) ? 1 : 0;
+      a.epi_x = (last && epi) ? X : nullptr;
+      a.shift = last ? shift : 0.f; a.diag = last ? diag : nullptr;
+      a.dots = last ? dots : nullptr; a.dots_row = dots_row; a.gate = gate;
+      static const int dbg = getenv("COLA_KRON_DBG") ? atoi(getenv("COLA_KRON_DBG")) : 0;
+      a.dbg = dbg;
+      const int64_t grid = a.n_tiles < grid_max ? a.n_tiles : grid_max;
+      kron_mode_tc_kernel<<<(unsigned)grid, kTcThreads, kSmemBytes, st>>>(in_maps[i], fac_maps[i], a);
+      int rc = cuda_status("kronsum_mode_tc");
+      if (rc) return rc;
     }
   }
   return COLA_OK;

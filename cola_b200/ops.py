@@ -659,8 +659,27 @@ class _KronSumCore:
         self.Fs = [(f if f.is_contiguous() else f.contiguous()) for f in factors]
         assert all(f.shape[0] == f.shape[1] for f in self.Fs), "KronSum factors are square"
         self.shape = (_prod([f.shape[0] for f in self.Fs]), ) * 2
+        self.use_tensor_cores = True   # set False to force the exact-fp32 SIMT contractions (A/B checks)
+
+    def _tc_ok(self, X):
+        """fp32, every factor 64x64, k % 32 == 0: the tcgen05 per-mode kernel (csrc/kron_tc.cu)."""
+        if X.dtype != torch.float32 or len(self.Fs) < 2 or any(tuple(f.shape) != (64, 64) for f in self.Fs):
+            return False
+        dims = (ctypes.c_int64 * len(self.Fs))(*[64] * len(self.Fs))
+        return bool(be.lib().cdll.cola_kron_tc_supported(len(self.Fs), dims, X.shape[1]))
+
+    def _apply_tc(self, X, Y, epi):
+        D = len(self.Fs)
+        facs = (ctypes.c_void_p * D)(*[f.data_ptr() for f in self.Fs])
+        ldf = (ctypes.c_int64 * D)(*[f.stride(0) for f in self.Fs])
+        be.lib().call("cola_kronsum_matmat_tc_f32", D, facs, ldf, be.ptr(X), be.ptr(Y), X.shape[1],
+                      ctypes.c_float(epi.alpha), ctypes.c_float(epi.shift),
+                      be.ptr(epi.diag) if epi.diag is not None else None, int(epi.accumulate), be.ptr(epi.dots),
+                      be.ptr(epi.dots_row), be.ptr(epi.gate), be.stream_ptr())
 
     def apply(self, X, Y, epi):
+        if self.use_tensor_cores and self._tc_ok(X):
+            return self._apply_tc(X, Y, epi)
         k = X.shape[1]
         dims = [f.shape[0] for f in self.Fs]
         D = len(dims)

@@ -109,6 +109,15 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
                             int accumulate, double* dots, const int32_t* dots_row, const int32_t* gate,
                             void* stream);
 
+/* Kronecker SUM on the tensor cores: Y = alpha * (F_1 (+) ... (+) F_D) X (+ epilogue), same shapes and arithmetic as
+ * cola_kron_matmat_tc_f32 (64x64 fp32 factors, k a multiple of 32, 3xTF32).  Each mode contracts X itself and
+ * accumulates into Y, one 32-column chunk of right-hand sides through all modes at a time (X chunk and Y chunk stay
+ * in L2 between modes); the last mode carries shift / diag / dots.  Replaces KronSum._matmat (operators.py:261-268:
+ * a zero-initialised accumulator, D GEMMs and 2D moveaxis copies).  No workspace.  X and Y must not alias. */
+int cola_kronsum_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
+                               float* Y, int64_t k, float alpha, float shift, const float* diag, int accumulate,
+                               double* dots, const int32_t* dots_row, const int32_t* gate, void* stream);
+
 /* Operators with no core (Diagonal, ScalarMul*Identity, sums of those):
  *   Y = (shift + diag[i]) * X  (+Y).   Diagonal._matmat / ScalarMul._matmat (operators.py:97-98,338-339). */
 int cola_diag_matmat_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n, int64_t k, float shift,

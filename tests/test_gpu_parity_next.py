@@ -172,3 +172,60 @@ def test_slogdet_lanczos_rule(golden, cb):
     sign, mag = L.slogdet(A, L.Lanczos(max_iters=40, tol=1e-12), L.Hutch(tol=2e-2, max_iters=2, key=cb.rng.PRNGKey(42)))
     assert float(sign) == float(g["sign"]) == -1.0
     assert abs(float(mag) - float(g["logdet"])) < 1e-8 * float(g["logdet"])
+
+
+# ------------------------------------------------------------------------------------------- tensor-core paths
+def test_kronsum_tensor_core_path(cb):
+    """KronSum with 64x64 fp32 factors runs on the tcgen05 per-mode kernel (3xTF32), every mode contracting X and
+    accumulating into Y: fp32-grade accuracy against an fp64 reference, agreement with the exact SIMT contractions,
+    fused shift / diagonal / dots, and accumulation behind another core of a Sum."""
+    ops = cb.ops
+    for D, k in [(2, 32), (2, 96), (3, 64)]:
+        Fs = [pb.kron_factor(64, torch.float32, 60 + i) for i in range(D)]
+        n = 64**D
+        dg = pb.t(pb.rs(10).uniform(size=n) + 0.5, torch.float32)
+        KS = ops.KronSum(*[ops.Dense(F.to(DEV)) for F in Fs])
+        A = cb.PSD(KS + 0.1 * ops.I_like(KS) + ops.Diagonal(dg.to(DEV)))
+        core = A.plan().terms[0][1][0]
+        X = pb.randn_np((n, k), torch.float32, 4).to(DEV)
+        assert type(core).__name__ == "_KronSumCore" and core._tc_ok(X)
+        Y = torch.empty_like(X)
+        dots = torch.zeros(k, dtype=torch.float64, device=DEV)
+        A.matmat_into(X, Y, dots=dots)
+        E = X.double().reshape(*([64] * D), k)
+        ref = torch.zeros_like(E)
+        for i, F in enumerate(Fs):
+            ref = ref + torch.moveaxis(torch.tensordot(F.double().to(DEV), torch.moveaxis(E, i, 0), dims=1), 0, i)
+        ref = ref.reshape(n, k) + (0.1 + dg.double().to(DEV))[:, None] * X.double()
+        assert rel(Y, ref) < 2e-6, (D, k, rel(Y, ref))
+        assert rel(dots, (X.double() * Y.double()).sum(0)) < 1e-12
+        core.use_tensor_cores = False
+        Y2 = torch.empty_like(X)
+        A.matmat_into(X, Y2)
+        core.use_tensor_cores = True
+        assert rel(Y, Y2) < 2e-6
+        Y3 = torch.full_like(X, 7.0)                             # closed gate: no launch touches Y
+        A.matmat_into(X, Y3, gate=torch.tensor([1], dtype=torch.int32, device=DEV))
+        assert bool((Y3 == 7.0).all())
+
+
+def test_tensor_core_epilogue_dots_cover_earlier_terms(cb):
+    """Sum[CSR core, Kronecker or KronSum on the tensor cores]: the tensor-core term is applied last with
+    accumulate, and its fused <x, y> must be that of the whole operator (what CG's p^T A p needs)."""
+    ops = cb.ops
+    n, k = 4096, 64
+    g = pb.rs(12)
+    off = pb.t(g.uniform(-1.0, 1.0, size=n - 1), torch.float32).to(DEV)
+    Tri = ops.Tridiagonal(off, pb.t(g.uniform(2.5, 3.5, size=n), torch.float32).to(DEV), off)   # CSR core
+    Fs = [ops.Dense(pb.kron_factor(64, torch.float32, 70 + i).to(DEV)) for i in range(2)]
+    X = pb.randn_np((n, k), torch.float32, 5).to(DEV)
+    for last in (ops.Kronecker(*Fs), ops.KronSum(*Fs)):
+        A = Tri + last + 0.25 * ops.I_like(last)
+        plan = A.plan()
+        assert len(plan.terms) == 2 and plan.terms[1][1][0]._tc_ok(X)
+        Y = torch.empty_like(X)
+        dots = torch.zeros(k, dtype=torch.float64, device=DEV)
+        A.matmat_into(X, Y, dots=dots)
+        ref = (Tri.to_dense().double() + last.to_dense().double()) @ X.double() + 0.25 * X.double()
+        assert rel(Y, ref) < 2e-6
+        assert rel(dots, (X.double() * Y.double()).sum(0)) < 1e-12
