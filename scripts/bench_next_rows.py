@@ -51,8 +51,13 @@ def kronsum_matmat():
     alg = sum(d * d for d in dims) * 4 + 2 * n * k * 4
     emit(row="KronSum matmat (operators.py:261-268)", workload="KronSum(64,64,64) fp32, 128 RHS", ms=ms,
          algorithmic_GB=alg / 1e9, achieved_GBps=alg / ms / 1e6, frac_of_hbm=alg / ms / 1e6 / HBM,
-         note="3 accumulating mode contractions: X read 3x, Y written once and read-modified twice (6 passes vs 2 "
-              "algorithmic); operand 134 MB > L2")
+         note="tcgen05 per-mode kernel (3xTF32), 4 chunks of 32 RHS x 3 modes = 12 launches; a chunk of X / Y stays in L2 "
+              "between modes; operand 134 MB > L2")
+    core = A.plan().terms[0][1][0]
+    core.use_tensor_cores = False
+    ms = time_kernel(lambda: A.matmat_into(X, Y), reps=10)
+    emit(row="KronSum matmat, exact-fp32 SIMT contractions (A/B)", workload="same", ms=ms, achieved_GBps=alg / ms / 1e6,
+         frac_of_hbm=alg / ms / 1e6 / HBM, note="3 accumulating mode_contract launches: X read 3x, Y read-modified twice")
 
 
 def tridiagonal_matmat():
