@@ -21,6 +21,7 @@ from .lanczos import BatchedDense
 def arnoldi_fact(A: LinearOperator, rhs, max_iters, tol, pbar=False):
     """rhs (n, b) on the device -> (Q (m+1, n, b), H (b, m+1, m) in A.dtype, idx, info)."""
     be.require_cuda(rhs, "start vectors")
+    A.plan()                                               # validate / compile once; the loop uses matmat_into
     dt = A.dtype
     rhs = rhs.to(dt).contiguous()
     n, b = rhs.shape

@@ -202,6 +202,7 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
     the mask only matters for residuals that are exactly zero."""
     be.require_cuda(b, "right-hand side")
     assert tuple(P.shape) == tuple(A.shape), "preconditioner shape mismatch"
+    A.plan(), P.plan()                                         # validate / compile once; the loop uses matmat_into
     dt = A.dtype
     b = b.to(dt).contiguous()
     n, k = b.shape

@@ -53,6 +53,7 @@ def gmres(A: LinearOperator, rhs, x0=None, max_iters=100, tol=1e-7, P=None, use_
 def gmres_fwd(A, rhs, x0, max_iters, tol, P=None, pbar=False):
     """cola/linalg/inverse/gmres.py:92-124.  rhs (n, b) -> (soln (n, b), info)."""
     be.require_cuda(rhs, "right-hand sides")
+    A.plan()                                               # validate / compile once
     dt = A.dtype
     rhs = rhs.to(dt).contiguous()
     n, b = rhs.shape

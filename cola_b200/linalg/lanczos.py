@@ -33,6 +33,7 @@ class LanczosState:
 def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
     """rhs (n, b) on the device.  Mirrors lanczos.py:235-284 (init_lanczos + lanczos_fact)."""
     be.require_cuda(rhs, "start vectors")
+    A.plan()                                               # validate / compile once; the loop uses matmat_into
     dt = A.dtype
     rhs = rhs.to(dt).contiguous()
     n, b = rhs.shape

@@ -39,6 +39,7 @@ def power_iteration(A: LinearOperator, tol=1e-6, max_iter=1000, pbar=False, key=
     dt = A.dtype
     v = rng.randn(A.shape[-1], dtype=dt, device=A.device, key=key)
     be.require_cuda(v, "the operator")
+    A.plan()                                               # validate / compile once; the loop uses matmat_into
     v = v.reshape(-1, 1).contiguous()                      # the start vector is NOT normalised (:56)
     p = torch.empty_like(v)
     acc = torch.zeros((2, 1), dtype=torch.float64, device=v.device)   # <v, A v>, ||A v||^2

@@ -111,8 +111,15 @@ class LinearOperator:
 
     # ---- application ---------------------------------------------------------------------------------
     def plan(self):
-        if self._plan is None:
+        """The compiled plan, recompiled when a leaf tensor was replaced or written in place since the last
+        compile (an optimizer step on a parameter): plans hold derived copies (scaled diagonals, folded scalars,
+        densified factors, the CSR form of a Tridiagonal) that would otherwise go stale.  The Krylov loops validate
+        once at entry and then use `matmat_into`, which does not re-check."""
+        token = _version_token(self)
+        if self._plan is None or self.__dict__.get("_plan_token") != token:
             self._plan = compile_plan(self)
+            self._plan_token = token
+            self.__dict__.pop("_cg_workspace", None)   # a captured CG batch points at the old plan's buffers
         return self._plan
 
     def _matmat(self, X):
@@ -129,7 +136,7 @@ class LinearOperator:
     def matmat_into(self, X, Y, dots=None, dots_row=None, gate=None):
         """Fused form used by the Krylov loops: Y = A X and, if given, dots[row] += colsum(X * Y) in the same
         kernel; `gate`/`dots_row` are device int32 scalars (see include/cola_b200.h)."""
-        self.plan().apply(X, Y, dots=dots, dots_row=dots_row, gate=gate)
+        (self._plan or self.plan()).apply(X, Y, dots=dots, dots_row=dots_row, gate=gate)
 
     def __matmul__(self, X):
         assert X.shape[0] == self.shape[-1], f"dimension mismatch {self.shape} vs {X.shape}"
@@ -201,6 +208,19 @@ class LinearOperator:
 
     def __repr__(self):
         return "<%dx%d %s with dtype=%s>" % (self.shape[0], self.shape[1], self.__class__.__name__, self.dtype)
+
+
+def _version_token(op):
+    """(id, in-place version counter) of every tensor in the operator tree."""
+    tok = []
+    for val in vars(op).values():
+        if torch.is_tensor(val):
+            tok.append((id(val), val._version))
+        elif isinstance(val, LinearOperator):
+            tok.append(_version_token(val))
+        elif isinstance(val, (tuple, list)) and val and all(isinstance(v, LinearOperator) for v in val):
+            tok.append(tuple(_version_token(v) for v in val))
+    return tuple(tok)
 
 
 def _as_operand(A, X):

@@ -63,9 +63,10 @@ def from_cola(A, cola):
     """Reference operator tree -> mirror classes, one to one (same constructor arguments); annotations are
     carried over by name.  Leaves that are not on the hot path raise NotConvertible (the caller then stays on
     the reference path), except plain `LinearOperator`s with a matmat closure, which are wrapped as opaque."""
+    token = _leaf_token(A)
     cached = getattr(A, "_b200_mirror", None)
-    if cached is not None:
-        return cached
+    if cached is not None and cached[0] == token:
+        return cached[1]
     R = cola.ops
     if not _is_fast_dtype(A.dtype):
         raise NotConvertible(f"dtype {A.dtype}")
@@ -114,14 +115,41 @@ def from_cola(A, cola):
         if name in ref_names:
             M.annotations = set(M.annotations) | {getattr(bops, name)}
     try:
-        A._b200_mirror = M
+        A._b200_mirror = (token, M)
     except (AttributeError, TypeError):
         pass
     return M
 
 
-def _mirror_or_none(A, cola):
-    if not (_on_fast_device(A) and _is_fast_dtype(A.dtype)):
+def _leaf_token(A):
+    """(id, in-place version) of the operator's parameter tensors: a cached mirror is reused only while none of them
+    was replaced or written in place (mirrors and their plans hold derived copies: folded scalars, CSR index arrays)."""
+    try:
+        leaves = A.flatten()[0]
+    except Exception:
+        return None
+    return tuple((id(t), t._version) if torch.is_tensor(t) else repr(t) for t in leaves)
+
+
+def _needs_autograd(A, *tensors):
+    """True when autograd is recording and an operand or a parameter of the operator requires grad.  The kernels are
+    not differentiable, so those calls stay on the reference's eager code: that is what runs when the reference
+    differentiates `A(theta) @ v` inside its custom backward rules (cg.py:72-86, slq.py:10-31).  The solver loops
+    themselves are invoked inside `torch.autograd.Function.forward` (custom_autodiff.py:44-49), where recording is off,
+    and keep the fast path."""
+    if not torch.is_grad_enabled():
+        return False
+    if any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        return True
+    try:
+        leaves = A.flatten()[0]
+    except Exception:
+        return False
+    return any(torch.is_tensor(t) and t.requires_grad for t in leaves)
+
+
+def _mirror_or_none(A, cola, *tensors):
+    if not (_on_fast_device(A) and _is_fast_dtype(A.dtype)) or _needs_autograd(A, *tensors):
         return None
     try:
         return from_cola(A, cola)
@@ -132,7 +160,7 @@ def _mirror_or_none(A, cola):
 # ------------------------------------------------------------------------------------------------ adapters
 def _make_run_batched_cg(cola, ref):
     def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar):
-        M = _mirror_or_none(A, cola)
+        M = _mirror_or_none(A, cola, b, x0)
         if M is None:
             return ref(A, b, x0, max_iters, tol, preconditioner, pbar)
         if isinstance(preconditioner, cola.ops.Identity):
@@ -147,7 +175,8 @@ def _make_run_batched_cg(cola, ref):
 
 def _make_lanczos_fact(cola, ref):
     def lanczos_fact(A, init_val, max_iters=100, tol=1e-7, pbar=False):
-        M = _mirror_or_none(A, cola)
+        # a state that is not a fresh start is the implicitly restarted variant (lanczos.py:111): reference path
+        M = _mirror_or_none(A, cola, init_val[0]) if int(init_val[3]) == 1 else None
         if M is None:
             return ref(A, init_val, max_iters, tol, pbar)
         V0, diag0, _, _ = init_val                               # init_lanczos (lanczos.py:275-284): V0[..., 1] = rhs/|rhs|
@@ -165,7 +194,8 @@ def _make_lanczos_fact(cola, ref):
 
 def _make_arnoldi_fact(cola, ref):
     def arnoldi_fact(A, init_val, max_iters, tol, pbar):
-        M = _mirror_or_none(A, cola)
+        # idx > 0: a restart of implicitly restarted Arnoldi on a partly filled basis (arnoldi.py:99): reference path
+        M = _mirror_or_none(A, cola, init_val[0]) if int(init_val[2]) == 0 else None
         if M is None:
             return ref(A, init_val, max_iters, tol, pbar)
         Q0 = init_val[0]                                         # init_arnoldi (arnoldi.py:327-335): Q0[..., 0] = rhs/|rhs|
@@ -185,19 +215,29 @@ def _make_hutch(cola, ref):
 
 
 def _make_slq_fwd(cola, ref):
+    """`slq_fwd` carries the reference's custom autograd rule (`@iterative_autograd(slq_bwd)`, slq.py:37): the
+    replacement is wrapped the same way, so the forward runs here (inside Function.forward, recording off) and the
+    backward stays the reference's slq_bwd -- whose CG solve comes back through the rebound run_batched_cg."""
+    inner_ref = getattr(ref, "__wrapped__", None)
+
     def slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key):
         M = _mirror_or_none(A, cola)
         if M is None:
-            return ref(A, fun, num_samples, max_iters, tol, pbar, key)
+            return (inner_ref or ref)(A, fun, num_samples, max_iters, tol, pbar, key)
         return b_stoch.slq_fwd(M, fun, num_samples, max_iters, tol, pbar, key)
-    return slq_fwd
+
+    if inner_ref is None:
+        return slq_fwd
+    autodiff = importlib.import_module("cola.utils.custom_autodiff")
+    slq_mod = importlib.import_module("cola.linalg.tbd.slq")
+    return autodiff.iterative_autograd(slq_mod.slq_bwd)(slq_fwd)
 
 
 def _make_matmat(cola, ref):
     def _matmat(self, X):
         if torch.is_tensor(X) and (X.is_cuda or FORCE_FAST_PATH) and _is_fast_dtype(X.dtype) and X.dtype == self.dtype \
                 and not torch._C._functorch.is_batchedtensor(X):   # under vmap there is no pointer to hand over
-            M = _mirror_or_none(self, cola)
+            M = _mirror_or_none(self, cola, X)
             if M is not None:
                 return M._matmat(X.contiguous())
         return ref(self, X)

@@ -163,3 +163,24 @@ def test_exact_and_offset_diagonals(case, golden, emu):
 def test_exact_diag_ragged_and_slogdet_rule(golden, emu):
     gn.test_exact_diag_ragged_blocks_and_trace(emu)
     gn.test_slogdet_lanczos_rule(golden, emu)
+
+
+def test_plan_follows_in_place_parameter_updates(emu):
+    """Plans hold derived copies (scaled diagonals, folded scalars, the CSR form of a Tridiagonal): an in-place write
+    to a leaf (an optimizer step) or a replaced leaf must recompile, an untouched operator must not."""
+    ops = emu.ops
+    d = torch.linspace(1.0, 2.0, 8, dtype=torch.float64)
+    band = torch.full((7, ), 0.5, dtype=torch.float64)
+    A = 2.0 * ops.Diagonal(d) + ops.Tridiagonal(band, d.clone(), band)
+    X = torch.ones(8, 2, dtype=torch.float64)
+    ref = lambda: 2.0 * d[:, None] * X + A.Ms[1].to_dense() @ X   # noqa: E731
+    assert torch.allclose(A @ X, ref())
+    first = A.plan()
+    assert A.plan() is first                                   # unchanged leaves: cached
+    d.mul_(3.0)                                                # in place, like optimizer.step()
+    assert torch.allclose(A @ X, ref()) and A.plan() is not first
+    second = A.plan()
+    A.Ms[1].beta.add_(1.0)                                     # a leaf of a nested operator (feeds the CSR copy)
+    assert torch.allclose(A @ X, ref()) and A.plan() is not second
+    Q, T, info = emu.linalg.Lanczos(start_vector=X[:, 0].contiguous() + d, max_iters=4, tol=1e-12)(emu.SelfAdjoint(A))
+    assert torch.allclose(T.beta[0, 0], ((X[:, 0] + d) @ (A.to_dense() @ (X[:, 0] + d))) / ((X[:, 0] + d) @ (X[:, 0] + d)))

@@ -278,3 +278,27 @@ def test_reference_api_over_host_loops_on_emulated_kernels(installed):
         assert gval.shape == r.shape and gval.dtype == r.dtype, name
         err = float((gval - r).abs().max() / r.abs().max())
         assert err < 1e-9, (name, err)
+
+
+def test_reference_own_suite_over_host_loops(tmp_path):
+    """The reference's OWN test suite (/root/reference/tests, its non-JAX default selection: 290 tests) run with
+    install() active, CPU operators routed through the adapters and the kernels replaced by the test-only statements
+    (tests/ref_suite_plugin.py): every torch fp32/fp64 case that reaches CG, Lanczos, Arnoldi, SLQ, Hutchinson or a
+    structured matmat executes this package's host loops, everything else (complex, NumPy backend, autograd
+    recordings, implicitly restarted variants) must fall through to the reference code.  All of them have to pass."""
+    import json
+    import subprocess
+    stats = tmp_path / "stats.json"
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", COLA_B200_REF_SUITE_STATS=str(stats),
+               PYTHONPATH=os.pathsep.join([os.path.join(HERE, "golden", "refshim"), REF, os.path.dirname(HERE)]))
+    cmd = [sys.executable, "-m", "pytest", os.path.join(REF, "tests"), "-q", "-p", "no:cacheprovider", "-p",
+           "tests.ref_suite_plugin", "-m", "not big and not tricky and not market and not jax", "--tb=line"]
+    out = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=900)
+    tail = out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-2000:]
+    assert out.returncode == 0, out.stdout[-4000:]
+    assert " passed" in tail and "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 290, tail
+    calls = json.load(open(stats))
+    # the fast path was really taken: every loop family launched its kernels
+    for name in ("cola_cg_*", "mode_contract", "lanczos_three_term", "reorth_update", "mgs_link", "tridiag_eig_first_row",
+                 "diag_matmat", "col_scale"):
+        assert calls.get(name, 0) > 0, (name, calls)
