@@ -61,6 +61,53 @@ def test_sharded_slq_and_hutch_match_unsharded():
     assert results[0][0] == results[1][0]
 
 
+def _worker_host_loops(rank, world, port, results):
+    """Same checks with the package's own operators and host loops (kernels replaced by tests/host_harness.py), plus
+    the RHS-sharded CG solve of cola_b200.sharding.solve_sharded."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cola_b200 as cb
+    from cola_b200.linalg import stochastic
+    from tests import problems as pb
+    from tests.host_harness import emulated_kernels
+    P = pb.problem("kron465_diag_f64")
+    with emulated_kernels():
+        A = pb.to_b200(P["spec"], "cpu", P["ann"])
+        key = cb.rng.PRNGKey(42)
+        kw = dict(num_samples=25, max_iters=20, tol=1e-12, pbar=False, key=key, probe_chunk_size=4)
+        val = stochastic.slq_fwd(A, torch.log, group=dist.group.WORLD, **kw)
+        ref = stochastic.slq_fwd(A, torch.log, **kw)
+        F = cb.linalg.LanczosUnary(A, torch.log, max_iters=20, tol=1e-12)
+        dg, info = stochastic.hutchinson_diag_estimate(F, 0, tol=2e-2, max_iters=2, key=key, group=dist.group.WORLD)
+        dref, iref = stochastic.hutchinson_diag_estimate(F, 0, tol=2e-2, max_iters=2, key=key)
+        alg = cb.linalg.CG(tol=1e-30, max_iters=15)             # fixed budget: iterates identical to the unsharded solve
+        xs, _ = cb.sharding.solve_sharded(A, P["B"], alg, group=dist.group.WORLD)
+        xl, _ = cb.sharding.solve_sharded(A, P["B"], alg, group=dist.group.WORLD, gather=False)
+        xref, _ = alg(A, P["B"])
+    lo, hi = cb.sharding.column_range(P["B"].shape[1], rank, world)
+    results[rank] = (float(val), float(ref), float((dg - dref).abs().max() / dref.abs().max()), info["iterations"],
+                     iref["iterations"], float((xs - xref).abs().max() / xref.abs().max()),
+                     float((xl - xref[:, lo:hi]).abs().max()), tuple(xl.shape))
+    dist.destroy_process_group()
+
+
+def test_sharded_host_loops_match_unsharded():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_worker_host_loops, args=(world, port, results), nprocs=world, join=True)
+    assert len(results) == world
+    for r in range(world):
+        val, ref, derr, it, itref, xerr, xlerr, shape = results[r]
+        assert abs(val - ref) <= 1e-12 * abs(ref)      # 25 probes, 13 + 12 by rank, chunks of 4: one all-reduce
+        assert derr < 1e-12 and it == itref
+        assert xerr < 1e-12 and xlerr < 1e-12 and shape[1] in (3, 4)
+    assert results[0][0] == results[1][0]
+
+
 def test_column_range_covers_everything():
     from cola_b200.sharding import column_range
     for total in (1, 7, 64, 100, 1024):
