@@ -32,6 +32,59 @@ _small_value = 1e-40
 CHECK_EVERY = 16  # iterations enqueued between polls of the device-side stop flag
 USE_CUDA_GRAPH = True  # replay batches of iterations as a CUDA graph once the loop is warm
 GRAPH_MAX_ELEMS = 64 * 1024 * 1024
+# Set by cola_b200.sharding.solve_sharded for the duration of a RHS-sharded solve: the process group over which the
+# stopping rule `any(||r|| > tol_eff)` (cg.py:133-138) and the error trace are global, as in the unsharded solve.
+STOP_RULE_GROUP = None
+
+
+def _world(group):
+    if group is None:
+        return 1
+    import torch.distributed as dist
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def _global_stop_rule(group, it, drive, reevaluate, ctl, tol_eff, max_iters):
+    """Reproduces the reference's stopping rule over ALL right-hand sides when they are sharded over ranks.
+
+    The reference stops at the first iteration K at which every column satisfies ||r|| <= tol_eff (or at
+    max_iters) and all columns are iterated up to K.  Each rank's device-side rule stops at the first iteration
+    K_r at which ITS columns are satisfied, so K >= max_r K_r.  Protocol (one 16-byte all-reduce per round, usually
+    one or two rounds, nothing inside the iterations): agree on K* = max_r K_r; ranks that stopped earlier advance
+    to K* with the rule switched off (tol_eff = -1, iteration cap K*), then re-evaluate the real rule at K*; ranks
+    whose residuals rose above tolerance again continue to their next stop; repeat until every rank stands at the
+    same iteration."""
+    import torch.distributed as dist
+    dev = ctl.device
+    while True:
+        ks = torch.tensor([it, -it], dtype=torch.int64, device=dev)
+        dist.all_reduce(ks, op=dist.ReduceOp.MAX, group=group)
+        k_max, k_min = int(ks[0]), -int(ks[1])
+        if k_max == k_min:
+            return it
+        if it < k_max:
+            saved = tol_eff.clone()
+            tol_eff.fill_(-1.0)                                 # rs > -1 for every finite residual: rule off
+            ctl[2:3].fill_(k_max)
+            ctl[1:2].zero_()
+            advanced = drive(k_max)
+            tol_eff.copy_(saved)
+            ctl[2:3].fill_(max_iters)
+            ctl[1:2].zero_()
+            reevaluate()                                        # the real cond_fun at the current iteration
+            if advanced == it:                                  # no progress (all residuals NaN): give up agreeing
+                return drive(max_iters)
+            it = advanced
+        it = drive(max_iters)                                   # no-op when the rule is satisfied at K*
+
+
+def _global_error_trace(group, col_norms):
+    """info['errors'] tracks mean_columns ||r|| (cg.py:103-105): over all ranks' columns it is the all-reduced column
+    sum divided by the all-reduced column count.  col_norms: (iterations + 1, k_local)."""
+    import torch.distributed as dist
+    packed = torch.cat([col_norms.sum(dim=1), col_norms.new_tensor([col_norms.shape[1]])])
+    dist.all_reduce(packed, group=group)
+    return packed[:-1] / packed[-1]
 
 
 @dataclass
@@ -140,45 +193,55 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
             lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
 
     t0 = time.time()
-    it, done = 0, 0
     if ws and ws["graph"] is not None and ws.get("token") != A.plan().graph_token():
         ws["graph"] = None                                       # the operator's scratch buffers moved: recapture
-    graph, batches = (ws["graph"] if ws else None), 0
-    while True:
-        c = ctl.cpu()
-        it, done = int(c[0]), int(c[1])
-        if done:
-            break
-        remaining = max_iters - it
-        if graph_ok and graph is None and batches >= 1 and remaining >= 2 * CHECK_EVERY:
-            # Every kernel reads the iteration index and the stop flag from the device control block, so a batch of
-            # iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
-            # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
-            graph = torch.cuda.CUDAGraph()
-            # No garbage collection while the stream is capturing: a cyclic collection can finalise another
-            # operator's cached CUDAGraph (cudaGraphExecDestroy / cudaFree), which invalidates the capture in progress
-            # (seen as cudaErrorStreamCaptureInvalidated, depending on test order).  torch.cuda.graph() itself runs
-            # gc.collect() just before capture begins.
-            gc_on = gc.isenabled()
-            gc.disable()
-            try:
-                with torch.cuda.graph(graph):
-                    enqueue(CHECK_EVERY)
-            finally:
-                if gc_on:
-                    gc.enable()
-            ws["graph"], ws["token"] = graph, A.plan().graph_token()
-            # capture does not execute: fall through to the replay below
-        if graph is not None:
-            graph.replay()
-        else:
-            enqueue(min(CHECK_EVERY, remaining))
-        batches += 1
+    loop = {"graph": ws["graph"] if ws else None, "batches": 0}
+
+    def drive(limit):
+        """Enqueue gated batches until the device-side rule (or the iteration cap `limit`) stops the loop."""
+        while True:
+            c = ctl.cpu()
+            it, done = int(c[0]), int(c[1])
+            if done:
+                return it
+            remaining = limit - it
+            if graph_ok and loop["graph"] is None and loop["batches"] >= 1 and remaining >= 2 * CHECK_EVERY:
+                # Every kernel reads the iteration index and the stop flag from the device control block, so a batch
+                # of iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
+                # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
+                graph = torch.cuda.CUDAGraph()
+                # No garbage collection while the stream is capturing: a cyclic collection can finalise another
+                # operator's cached CUDAGraph (cudaGraphExecDestroy / cudaFree), which invalidates the capture in
+                # progress (seen as cudaErrorStreamCaptureInvalidated, depending on test order).  torch.cuda.graph()
+                # itself runs gc.collect() just before capture begins.
+                gc_on = gc.isenabled()
+                gc.disable()
+                try:
+                    with torch.cuda.graph(graph):
+                        enqueue(CHECK_EVERY)
+                finally:
+                    if gc_on:
+                        gc.enable()
+                loop["graph"] = graph
+                ws["graph"], ws["token"] = graph, A.plan().graph_token()
+                # capture does not execute: fall through to the replay below
+            if loop["graph"] is not None:
+                loop["graph"].replay()
+            else:
+                enqueue(min(CHECK_EVERY, remaining))
+            loop["batches"] += 1
+
+    it = drive(max_iters)
+    group = STOP_RULE_GROUP if _world(STOP_RULE_GROUP) > 1 else None
+    if group is not None:
+        it = _global_stop_rule(group, it, drive, lambda: lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma),
+                                                                    be.ptr(tol_eff), 0, st()), ctl, tol_eff, max_iters)
     elapsed = time.time() - t0
 
     # ---- info dict exactly as while_loop_winfo builds it (torch_tqdm.py:35-62): the tracked error is sampled
     # before every cond evaluation (it+1 of them) and once more after the loop; the first two are dropped.
-    trace = torch.sqrt(gamma[:it + 1]).mean(dim=1).cpu().numpy()
+    col_norms = torch.sqrt(gamma[:it + 1])
+    trace = (col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).cpu().numpy()
     samples = np.concatenate([trace, trace[-1:]])
     info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
     if ws:                                                       # hand back copies: the workspace is reused
@@ -250,15 +313,23 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
             lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(rnorm2), be.ptr(tol_eff), 1, st())
 
     t0 = time.time()
-    it = 0
-    while True:
-        c = ctl.cpu()
-        it, done = int(c[0]), int(c[1])
-        if done:
-            break
-        enqueue(min(CHECK_EVERY, max_iters - it))
+
+    def drive(limit):
+        while True:
+            c = ctl.cpu()
+            it, done = int(c[0]), int(c[1])
+            if done:
+                return it
+            enqueue(min(CHECK_EVERY, limit - it))
+
+    it = drive(max_iters)
+    group = STOP_RULE_GROUP if _world(STOP_RULE_GROUP) > 1 else None
+    if group is not None:
+        it = _global_stop_rule(group, it, drive, lambda: lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(rnorm2),
+                                                                    be.ptr(tol_eff), 0, st()), ctl, tol_eff, max_iters)
     elapsed = time.time() - t0
-    trace = torch.sqrt(rnorm2[:it + 1]).mean(dim=1).cpu().numpy()
+    col_norms = torch.sqrt(rnorm2[:it + 1])
+    trace = (col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).cpu().numpy()
     samples = np.concatenate([trace, trace[-1:]])
     info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
     be.col_scale(x, x, mult_sq, take_sqrt=True, mode=0)          # x * ||b||  (cg.py:119)

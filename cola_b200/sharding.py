@@ -2,8 +2,8 @@
 
 One process per GPU (`torch.distributed`); the operator is replicated, columns are split contiguously by rank and
 there is no data-path collective inside the Krylov loops: SLQ ends with ONE all-reduce of (sum, count), Hutchinson
-all-reduces its two running sums once per 100-probe block (its stopping rule is global), fixed-length CG needs
-none.  The reference has no multi-device code at all; this module is new."""
+all-reduces its two running sums once per 100-probe block (its stopping rule is global), CG agrees on the global
+stopping iteration after the local loops end (a 16-byte all-reduce) and all-reduces its error trace once.  The reference has no multi-device code at all; this module is new."""
 import torch
 
 
@@ -21,13 +21,24 @@ def shard_columns(X, group=None):
 
 
 def solve_sharded(A, B, alg, group=None, gather=True):
-    """CG solve with the RHS columns sharded over ranks.  Each rank solves its block independently (the stopping
-    rule `any(||r|| > tol)` is evaluated per rank: with a fixed iteration budget the iterates are identical to the
-    unsharded solve; with a tolerance a rank may stop a few iterations earlier than the slowest column elsewhere
-    would force, never later).  Returns the full solution on every rank if `gather`."""
+    """CG solve with the RHS columns sharded over ranks.  There is no collective inside the iterations.  The
+    reference's stopping rule `any(||r|| > tol_eff)` runs over ALL columns (cg.py:133-138), so after its own columns
+    have converged a rank agrees with the others on the common iteration count (one 16-byte all-reduce per round,
+    cola_b200/linalg/cg.py:_global_stop_rule) and `info` -- iterations and the mean-residual trace -- is the unsharded
+    solve's; with a fixed iteration budget that exchange is a single all-reduce confirming the same count.  Returns
+    the full solution on every rank if `gather`."""
+    import importlib
+
     import torch.distributed as dist
+    cg = importlib.import_module(__package__ + ".linalg.cg")
     Bl, (lo, hi) = shard_columns(B, group)
-    xl, info = alg(A, Bl)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    saved = cg.STOP_RULE_GROUP
+    cg.STOP_RULE_GROUP = (group if group is not None else dist.group.WORLD) if world > 1 else None
+    try:
+        xl, info = alg(A, Bl)
+    finally:
+        cg.STOP_RULE_GROUP = saved
     if not gather or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return xl, info
     world = dist.get_world_size(group)

@@ -86,10 +86,25 @@ def _worker_host_loops(rank, world, port, results):
         xs, _ = cb.sharding.solve_sharded(A, P["B"], alg, group=dist.group.WORLD)
         xl, _ = cb.sharding.solve_sharded(A, P["B"], alg, group=dist.group.WORLD, gather=False)
         xref, _ = alg(A, P["B"])
+        # tolerance-limited solve whose ranks stop at very different iterations: rank 0 gets two eigenvectors
+        # (converged after one step), rank 1 three generic columns.  The global rule must give the unsharded count,
+        # trace and solution (rank 0 is advanced with its rule switched off, cg.py:_global_stop_rule)
+        Pd = pb.problem("dense96_f64")
+        Ad = pb.to_b200(Pd["spec"], "cpu", Pd["ann"])
+        Bd = Pd["B"].clone()
+        Bd[:, :2] = torch.linalg.eigh(Pd["spec"][1])[1][:, [3, 40]]
+        tol_alg = cb.linalg.CG(tol=1e-9, max_iters=500)
+        xt, info_t = cb.sharding.solve_sharded(Ad, Bd, tol_alg, group=dist.group.WORLD)
+        xt_ref, info_ref = tol_alg(Ad, Bd)
+        xloc, info_loc = tol_alg(Ad, cb.sharding.shard_columns(Bd, dist.group.WORLD)[0])   # what a local rule would do
     lo, hi = cb.sharding.column_range(P["B"].shape[1], rank, world)
     results[rank] = (float(val), float(ref), float((dg - dref).abs().max() / dref.abs().max()), info["iterations"],
                      iref["iterations"], float((xs - xref).abs().max() / xref.abs().max()),
-                     float((xl - xref[:, lo:hi]).abs().max()), tuple(xl.shape))
+                     float((xl - xref[:, lo:hi]).abs().max()), tuple(xl.shape),
+                     dict(it=info_t["iterations"], it_ref=info_ref["iterations"], it_local=info_loc["iterations"],
+                          xerr=float((xt - xt_ref).abs().max() / xt_ref.abs().max()),
+                          trace_err=float(abs(info_t["errors"] - info_ref["errors"]).max() / info_ref["errors"].max()),
+                          n_err=(len(info_t["errors"]), len(info_ref["errors"]))))
     dist.destroy_process_group()
 
 
@@ -101,11 +116,15 @@ def test_sharded_host_loops_match_unsharded():
     mp.spawn(_worker_host_loops, args=(world, port, results), nprocs=world, join=True)
     assert len(results) == world
     for r in range(world):
-        val, ref, derr, it, itref, xerr, xlerr, shape = results[r]
+        val, ref, derr, it, itref, xerr, xlerr, shape, tl = results[r]
         assert abs(val - ref) <= 1e-12 * abs(ref)      # 25 probes, 13 + 12 by rank, chunks of 4: one all-reduce
         assert derr < 1e-12 and it == itref
         assert xerr < 1e-12 and xlerr < 1e-12 and shape[1] in (3, 4)
+        assert tl["it"] == tl["it_ref"] and tl["n_err"][0] == tl["n_err"][1], tl
+        assert tl["xerr"] < 1e-10 and tl["trace_err"] < 1e-10, tl
     assert results[0][0] == results[1][0]
+    # the scenario really exercises the protocol: left alone, rank 0 would have stopped long before rank 1
+    assert results[0][8]["it_local"] < results[1][8]["it_local"] == results[1][8]["it_ref"]
 
 
 def test_column_range_covers_everything():
