@@ -104,6 +104,11 @@ def require_cuda(t, what="operand"):
     if not t.is_cuda:
         raise RuntimeError(f"cola_b200 is a CUDA-only path: {what} is on the CPU (no CPU fallback); "
                            "move the operator and the operand to a B200 with .to('cuda')")
+    # kernels are enqueued on the CURRENT device's current stream (one process per GPU): an operand that lives on
+    # another device of the same process would be dereferenced by the wrong GPU
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{what} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "run the call under torch.cuda.device(...) (cola_b200 launches on the current device)")
 
 
 def ptr(t, dtype=None):

@@ -139,3 +139,18 @@ def test_preconditioned_cg_and_gmres_are_cuda_only():
         cb.linalg.GMRES(max_iters=3)(A, torch.ones(4, 2))
     with pytest.raises(RuntimeError, match="CUDA-only"):
         cb.linalg.CG(P=ops.Diagonal(torch.ones(4)))(A, torch.ones(4, 2))
+
+
+def test_operand_on_another_device_is_refused(monkeypatch):
+    """Kernels launch on the current device's stream; an operand on a different GPU of the same process must raise
+    instead of being dereferenced by the wrong device (checked with a stand-in tensor: there is no GPU here)."""
+    import types
+
+    import torch
+
+    from cola_b200 import backend as be
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    other = types.SimpleNamespace(is_cuda=True, device=types.SimpleNamespace(index=1))
+    with pytest.raises(RuntimeError, match="current CUDA device"):
+        be.require_cuda(other, "operand")
+    be.require_cuda(types.SimpleNamespace(is_cuda=True, device=types.SimpleNamespace(index=0)), "operand")
