@@ -12,7 +12,7 @@ import torch
 
 from .. import rng
 from ..ops import (PSD, BlockDiag, Dense, Diagonal, I_like, Identity, Kronecker, KronSum, LinearOperator, Product,
-                   ScalarMul, SelfAdjoint, Transpose, Unitary, lazify)
+                   ScalarMul, SelfAdjoint, Transpose, Triangular, Unitary, lazify)
 from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
 from .arnoldi import arnoldi, arnoldi_eigs
 from .cg import CG
@@ -95,6 +95,22 @@ def solve(A, b, alg=Auto()):
     return inv(A, alg) @ b
 
 
+class TriangularInv(LinearOperator):
+    """cola/linalg/inverse/inv.py:154-165: a triangular solve per application (library trsm on the device, as the
+    reference's xnp.solvetri); inside an operator tree it is an opaque core of the plan."""
+    def __init__(self, A: Triangular):
+        super().__init__(A.dtype, A.shape)
+        self.A = A.to_dense()
+        self.lower = A.lower
+        self.device = A.device
+
+    def _matmat(self, X):
+        return torch.linalg.solve_triangular(self.A, X, upper=not self.lower)
+
+    def _rmatmat(self, X):
+        return torch.linalg.solve_triangular(self.A.T, X.T, upper=self.lower).T
+
+
 class _DenseInverse(LinearOperator):
     """inv(A, Cholesky) for small PSD operators: torch.linalg.cholesky on the dense matrix (library, as in the
     reference: decompositions.py:147-175 + TriangularInv)."""
@@ -124,6 +140,8 @@ def inv(A: LinearOperator, alg: Algorithm = Auto()):
         return Kronecker(*[inv(M, alg) for M in A.Ms])
     if isinstance(A, Diagonal):
         return Diagonal(1. / A.diag)
+    if isinstance(A, Triangular):   # inv.py:149-151
+        return TriangularInv(A)
     # base cases
     if isinstance(alg, Auto):   # inv.py:72-92
         small = bool(np.prod(A.shape) <= 1e6)

@@ -251,6 +251,13 @@ class Dense(LinearOperator):
         return self.A
 
 
+class Triangular(Dense):
+    """operators.py:41-45"""
+    def __init__(self, A, lower=True):
+        super().__init__(A)
+        self.lower = lower
+
+
 class Sparse(LinearOperator):
     """operators.py:48-81.  Same COO constructor; the CSR arrays (int32 indices) are built on the device with a
     STABLE row sort, i.e. what the reference constructor means (its own non-stable argsort can misalign
@@ -556,6 +563,8 @@ def transpose(A):
         return A
     if isinstance(A, Transpose):
         return A.A
+    if isinstance(A, Triangular):
+        return Triangular(A.A.T.contiguous(), lower=not A.lower)
     if isinstance(A, Dense):
         return Dense(A.A.T.contiguous())
     if isinstance(A, Sparse):

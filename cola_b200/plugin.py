@@ -74,8 +74,13 @@ def from_cola(A, cola):
     if isinstance(A, R.Sparse):
         csr = A.A
         M = bops.Sparse.from_csr(csr.crow_indices(), csr.col_indices(), csr.values(), tuple(A.shape))
-    elif isinstance(A, R.Dense) and type(A).__name__.startswith(("Dense", "Triangular")):
+    elif isinstance(A, R.Triangular):
+        M = bops.Triangular(A.A, lower=A.lower)
+    elif isinstance(A, R.Dense) and type(A).__name__.startswith("Dense"):
         M = bops.Dense(A.A)
+    elif type(A).__name__.startswith("TriangularInv") and hasattr(A, "lower"):
+        b_dispatch = importlib.import_module(__package__ + ".linalg.dispatch")
+        M = b_dispatch.TriangularInv(bops.Triangular(A.A, lower=A.lower))
     elif isinstance(A, R.Identity):
         M = bops.Identity(tuple(A.shape), A.dtype)
         M.device = torch.device(A.device) if getattr(A, "device", None) is not None else M.device

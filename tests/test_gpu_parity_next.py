@@ -229,3 +229,27 @@ def test_tensor_core_epilogue_dots_cover_earlier_terms(cb):
         ref = (Tri.to_dense().double() + last.to_dense().double()) @ X.double() + 0.25 * X.double()
         assert rel(Y, ref) < 2e-6
         assert rel(dots, (X.double() * Y.double()).sum(0)) < 1e-12
+
+
+def test_triangular_inverse(cb):
+    """inv(Triangular) -> TriangularInv (inv.py:149-165): a triangular solve per application, its transpose, and its
+    use as an opaque core inside a fused plan (shift + dots epilogue as a separate sweep)."""
+    L, ops = cb.linalg, cb.ops
+    g = torch.Generator().manual_seed(0)
+    M = (torch.tril(torch.randn(40, 40, dtype=torch.float64, generator=g)) + 4 * torch.eye(40, dtype=torch.float64)).to(DEV)
+    X = torch.randn(40, 5, dtype=torch.float64, generator=g).to(DEV)
+    T = ops.Triangular(M, lower=True)
+    Ti = L.inv(T)
+    assert type(Ti).__name__ == "TriangularInv"
+    assert rel(M @ (Ti @ X), X) < 1e-13 and rel((X.T @ Ti) @ M, X.T) < 1e-13
+    assert T.T.lower is False and rel(M.T @ (L.inv(T.T) @ X), X) < 1e-13
+    A = Ti + 0.5 * ops.I_like(Ti)
+    ref = torch.linalg.solve_triangular(M, X, upper=False) + 0.5 * X
+    dots = torch.zeros(5, dtype=torch.float64, device=DEV)
+    Y = torch.empty_like(X)
+    A.matmat_into(X, Y, dots=dots)
+    assert rel(Y, ref) < 1e-13 and rel(dots, (X * ref).sum(0)) < 1e-13
+    # inv(L L^T) = L^-T L^-1, the Cholesky-style inverse of the reference (decompositions.py:147-175)
+    S = M @ M.T
+    Sinv = L.inv(T.T) @ Ti
+    assert rel(S @ (Sinv @ X), X) < 1e-11

@@ -165,6 +165,10 @@ def test_exact_diag_ragged_and_slogdet_rule(golden, emu):
     gn.test_slogdet_lanczos_rule(golden, emu)
 
 
+def test_triangular_inverse(emu):
+    gn.test_triangular_inverse(emu)
+
+
 def test_plan_follows_in_place_parameter_updates(emu):
     """Plans hold derived copies (scaled diagonals, folded scalars, the CSR form of a Tridiagonal): an in-place write
     to a leaf (an optimizer step) or a replaced leaf must recompile, an untouched operator must not."""

@@ -249,6 +249,10 @@ def test_reference_api_over_host_loops_on_emulated_kernels(installed):
         out["logdet"] = cola.linalg.logdet(A, Lanczos(max_iters=12, tol=1e-10), Hutch(tol=2e-2, max_iters=2, key=key))
         out["hutch_k1"] = Hutch(tol=2e-2, max_iters=2, key=key)(A, 1)
         out["sqrtA"] = cola.linalg.sqrt(A, Lanczos(max_iters=12, tol=1e-12)) @ B
+        Lc = R.Triangular(torch.linalg.cholesky(A.to_dense()), lower=True)       # Cholesky-style inverse as an operator
+        Ainv = cola.linalg.inv(Lc.T) @ cola.linalg.inv(Lc)
+        Q, T, info = ref_lanczos(cola.SelfAdjoint(Ainv), v, 6, 1e-12)             # TriangularInv cores inside a loop
+        out["lanczos_trinv_beta"] = T.beta
         out["expN"] = cola.linalg.exp(N, Arnoldi(max_iters=12, tol=1e-12)) @ B
         return out
 
