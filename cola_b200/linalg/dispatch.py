@@ -69,15 +69,23 @@ class Exact(Algorithm):
         return exact_diag(A, k, self.bs)
 
 
-def exact_diag(A, k, bs):
+def exact_diag(A, k, bs, group=None):
     """diagonal_estimation.py:84-128: blocks of 100 identity columns through the fused matmat.  Column c of A holds
     entry (c - k, c) of the k-th diagonal, so each block is read off directly instead of being masked with a shifted
     identity block and reduced over columns (the reference's form; it also fails on a ragged last block for k != 0,
-    this one does not)."""
+    this one does not).  With `group` (a torch.distributed process group) the column blocks are dealt round-robin
+    to the ranks and the disjoint pieces are combined by one all-reduce (independent units, operator
+    replicated)."""
     n = A.shape[0]
     bs = min(100, n)
     out = torch.zeros(n - abs(k), dtype=A.dtype, device=A.device)
-    for i in range(0, n, bs):
+    rank, world = 0, 1
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    for b, i in enumerate(range(0, n, bs)):
+        if b % world != rank:
+            continue
         w = min(bs, n - i)
         chunk = torch.zeros((n, w), dtype=A.dtype, device=A.device)
         chunk[i:i + w] = torch.eye(w, dtype=A.dtype, device=A.device)
@@ -86,6 +94,8 @@ def exact_diag(A, k, bs):
         rows = cols - k
         ok = (rows >= 0) & (rows < n)
         out[(rows if k >= 0 else cols)[ok]] = AE[rows[ok], (cols - i)[ok]]
+    if world > 1:
+        dist.all_reduce(out, group=group)              # every entry was written by exactly one rank
     return out
 
 

@@ -97,6 +97,12 @@ def _worker_host_loops(rank, world, port, results):
         xt, info_t = cb.sharding.solve_sharded(Ad, Bd, tol_alg, group=dist.group.WORLD)
         xt_ref, info_ref = tol_alg(Ad, Bd)
         xloc, info_loc = tol_alg(Ad, cb.sharding.shard_columns(Bd, dist.group.WORLD)[0])   # what a local rule would do
+        # exact diagonals: 100-column identity blocks dealt round-robin, one all-reduce (n = 576: 6 blocks, ragged)
+        Pl = pb.problem("lap24_f64")
+        Al = pb.to_b200(Pl["spec"], "cpu", Pl["ann"])
+        dense = pb.to_oracle(Pl["spec"]).matmat(torch.eye(576, dtype=torch.float64))
+        diag_err = max(float((cb.linalg.exact_diag(Al, kk, 100, group=dist.group.WORLD)
+                              - torch.diagonal(dense, offset=kk)).abs().max()) for kk in (0, 1, -24))
     lo, hi = cb.sharding.column_range(P["B"].shape[1], rank, world)
     results[rank] = (float(val), float(ref), float((dg - dref).abs().max() / dref.abs().max()), info["iterations"],
                      iref["iterations"], float((xs - xref).abs().max() / xref.abs().max()),
@@ -104,7 +110,7 @@ def _worker_host_loops(rank, world, port, results):
                      dict(it=info_t["iterations"], it_ref=info_ref["iterations"], it_local=info_loc["iterations"],
                           xerr=float((xt - xt_ref).abs().max() / xt_ref.abs().max()),
                           trace_err=float(abs(info_t["errors"] - info_ref["errors"]).max() / info_ref["errors"].max()),
-                          n_err=(len(info_t["errors"]), len(info_ref["errors"]))))
+                          n_err=(len(info_t["errors"]), len(info_ref["errors"])), diag_err=diag_err))
     dist.destroy_process_group()
 
 
@@ -122,6 +128,7 @@ def test_sharded_host_loops_match_unsharded():
         assert xerr < 1e-12 and xlerr < 1e-12 and shape[1] in (3, 4)
         assert tl["it"] == tl["it_ref"] and tl["n_err"][0] == tl["n_err"][1], tl
         assert tl["xerr"] < 1e-10 and tl["trace_err"] < 1e-10, tl
+        assert tl["diag_err"] < 1e-13, tl
     assert results[0][0] == results[1][0]
     # the scenario really exercises the protocol: left alone, rank 0 would have stopped long before rank 1
     assert results[0][8]["it_local"] < results[1][8]["it_local"] == results[1][8]["it_ref"]
