@@ -12,7 +12,7 @@ import torch
 
 from .. import rng
 from ..ops import (PSD, BlockDiag, Dense, Diagonal, I_like, Identity, Kronecker, KronSum, LinearOperator, Product,
-                   ScalarMul, SelfAdjoint, Transpose, Triangular, Unitary, lazify)
+                   ScalarMul, SelfAdjoint, Sum, Transpose, Triangular, Unitary, lazify)
 from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
 from .arnoldi import arnoldi, arnoldi_eigs
 from .cg import CG
@@ -194,6 +194,16 @@ def eigmax(A: LinearOperator, alg: Algorithm = Auto()):
 def eig(A: LinearOperator, k: int, which: str = "LM", alg: Algorithm = Auto()):
     """cola/linalg/eig/eigs.py:19-182 (Lanczos, Arnoldi and Auto/Eigh rules)."""
     eig_slice = get_slice(k, which)
+    # closed forms (eigs.py:143-149, 175-182).  With an explicit Lanczos / Arnoldi / ... the reference's rules for
+    # (LinearOperator, that algorithm) and (Identity | Diagonal, Algorithm) are ambiguous; the algorithm is honoured.
+    if isinstance(A, Identity) and isinstance(alg, Auto):
+        vals = torch.ones(A.shape[0], dtype=A.dtype, device=A.device)
+        vecs = torch.eye(A.shape[0], dtype=A.dtype, device=A.device)
+        return vals[eig_slice], Unitary(lazify(vecs[:, eig_slice]))
+    if isinstance(A, Diagonal) and isinstance(alg, Auto):
+        order = torch.argsort(A.diag)
+        vecs = torch.eye(A.shape[0], dtype=A.dtype, device=A.device)[:, order]
+        return A.diag[order][eig_slice], Unitary(lazify(vecs[:, eig_slice]))
     if isinstance(alg, Auto):   # eigs.py:76-96
         small = bool(np.prod(A.shape) <= 1e6)
         if k == 1 and which == "LM":
@@ -221,16 +231,32 @@ def eig(A: LinearOperator, k: int, which: str = "LM", alg: Algorithm = Auto()):
 
 # ---------------------------------------------------------------------------------------------------- trace / diag
 def diag(A: LinearOperator, k: int = 0, alg: Algorithm = Auto()):
-    """cola/linalg/trace/diag_trace.py:22-120"""
-    if isinstance(A, Dense):
+    """cola/linalg/trace/diag_trace.py:22-120: the structure rules come first (a Sum is estimated term by term, so
+    Dense / Diagonal / Identity / Kronecker-of-those terms contribute their exact diagonals whatever `alg` is)."""
+    if isinstance(A, Dense):                         # :58-61
         return torch.diagonal(A.A, offset=k)
-    if isinstance(A, Identity) and k == 0:
-        return torch.ones(A.shape[0], dtype=A.dtype, device=A.device)
-    if isinstance(A, Diagonal) and k == 0:
-        return A.diag
+    if isinstance(A, (Identity, Diagonal)):          # :64-78
+        if k == 0:
+            return A.diag if isinstance(A, Diagonal) else torch.ones(A.shape[0], dtype=A.dtype, device=A.device)
+        return torch.zeros(A.shape[0] - abs(k), dtype=A.dtype, device=A.device)
+    if type(A) is Sum:                               # :81-84
+        return sum(diag(M, k, alg) for M in A.Ms)
+    if isinstance(A, BlockDiag):                     # :87-91
+        assert k == 0, "Havent filled this case yet, need to pad with 0s"
+        return torch.cat([d for M, m in zip(A.Ms, A.multiplicities) for d in [diag(M, k, alg)] * m])
+    if isinstance(A, ScalarMul):                     # :94-96
+        return A.c * diag(I_like(A), k, alg)
+    if isinstance(A, (Kronecker, KronSum)):          # :103-119: outer product / outer sum of the factors' diagonals
+        assert k == 0, "Need to verify correctness of rule for off diagonal case"
+        ds = [diag(M, k, alg) for M in A.Ms]
+        out = None
+        for i, d in enumerate(ds):
+            d = d.reshape([-1 if j == i else 1 for j in range(len(ds))])
+            out = d if out is None else (out * d if isinstance(A, Kronecker) else out + d)
+        return out.reshape(-1)
     if isinstance(alg, Auto):   # diag_trace.py:43-50
         tol = alg.__dict__.get("tol", 1e-6)
-        use_exact = bool(tol < 1 / np.sqrt(10 * A.shape[-1]))
+        use_exact = bool(tol < 1 / np.sqrt(10 * np.prod(A.shape)))
         alg = Exact(**{kk: v for kk, v in alg.__dict__.items() if kk in ("bs", "pbar")}) if use_exact else \
             Hutch(**alg.__dict__)
     return alg(A, k)
@@ -337,6 +363,17 @@ def slogdet(A: LinearOperator, log_alg: Algorithm = Auto(), trace_alg: Algorithm
         return one, torch.zeros((), dtype=A.dtype, device=A.device)
     if isinstance(A, Diagonal):
         return torch.prod(torch.sign(A.diag)), torch.sum(torch.log(torch.abs(A.diag)))
+    if type(A) is Product and all(M.shape[-2] == M.shape[-1] for M in A.Ms):   # logdet.py:121-125
+        signs, logdets = zip(*[slogdet(M, log_alg, trace_alg) for M in A.Ms])
+        sg = one
+        for sgn in signs:
+            sg = sg * sgn
+        return sg, sum(logdets)
+    if isinstance(A, ScalarMul):   # logdet.py:134-139, restated as it is: log|c|, not n log|c|
+        return A.c / torch.abs(A.c), torch.log(torch.abs(A.c))
+    if isinstance(A, Triangular):  # logdet.py:170-176
+        d = torch.diagonal(A.A)
+        return torch.prod(d / torch.abs(d)), torch.sum(torch.log(torch.abs(d)))
     if isinstance(A, Kronecker):   # logdet.py:147-160
         n = A.shape[0]
         signs, logdets = zip(*[slogdet(M, log_alg, trace_alg) for M in A.Ms])

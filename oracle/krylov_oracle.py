@@ -612,6 +612,37 @@ def exact_diag(matmat, n, dtype, k=0):
     return total[abs(k):] if k <= 0 else total[:(-k or None)]
 
 
+def diag(A, k=0, alg="hutch", **hutch_kw):
+    """cola/linalg/trace/diag_trace.py:56-119: structure rules first -- a Sum is taken term by term, so Dense /
+    Diagonal / Kronecker-of-those terms give exact diagonals whatever the algorithm -- then Hutch or Exact on what is
+    left (here: CSR, Product, scaled operators; `c * Identity` is a Product[ScalarMul, Identity] in the reference and
+    has no rule of its own)."""
+    if isinstance(A, DenseOp):
+        return torch.diag(A.M, diagonal=k)
+    if isinstance(A, (IdentityOp, DiagonalOp)):
+        if k == 0:
+            return A.d if isinstance(A, DiagonalOp) else torch.ones(A.shape[0], dtype=A.dtype)
+        return torch.zeros(A.shape[0] - abs(k), dtype=A.dtype)
+    if isinstance(A, SumOp):
+        return sum(diag(M, k, alg, **hutch_kw) for M in A.terms)
+    if isinstance(A, BlockDiagOp):
+        assert k == 0
+        return torch.concat([d for M, m in zip(A.blocks, A.mult) for d in [diag(M, k, alg, **hutch_kw)] * m])
+    if isinstance(A, (KroneckerOp, KronSumOp)):
+        assert k == 0
+        Ms = A.factors if isinstance(A, KroneckerOp) else A.Ms
+        ds = [diag(M, k, alg, **hutch_kw) for M in Ms]
+        slices = [[None] * i + [slice(None)] + [None] * (len(ds) - i - 1) for i in range(len(ds))]
+        parts = [d[tuple(sl)] for d, sl in zip(ds, slices)]
+        out = parts[0]
+        for p in parts[1:]:
+            out = out * p if isinstance(A, KroneckerOp) else out + p
+        return out.reshape(-1)
+    if alg == "exact":
+        return exact_diag(A.matmat, A.shape[0], A.dtype, k)
+    return hutchinson_diag(A.matmat, A.shape[0], A.dtype, k=k, **hutch_kw)[0]
+
+
 # ----------------------------------------------------------------------------------
 # SLQ  (cola/linalg/tbd/slq.py:37-75)
 # ----------------------------------------------------------------------------------

@@ -82,6 +82,12 @@ DIAG_CASES = {  # case -> (problem, k, algorithm)   cola.linalg.diag(A, k, alg)
     "diag_exact_tridiag200_f64_km1": ("tridiag200_f64", -1, "exact"),
     "diag_exact_lap16_shift_f32_k0": ("lap16_shift_f32", 0, "exact"),     # ragged last block (n = 256)
     "diag_exact_kron465_diag_f64_k0": ("kron465_diag_f64", 0, "exact"),
+    # structure rules (diag_trace.py:56-119): with Hutch these are exact or partly exact, term by term
+    "diag_hutch_kron465_diag_f64_k0": ("kron465_diag_f64", 0, "hutch"),      # Sum[Kronecker, Diagonal]: exact
+    "diag_hutch_blockdiag_f32_k0": ("blockdiag_f32", 0, "hutch"),            # BlockDiag of Dense: exact
+    "diag_hutch_kronsum465_f64_k0": ("kronsum465_f64", 0, "hutch"),          # KronSum of Dense: exact
+    "diag_hutch_lap16_shift_f32_k0": ("lap16_shift_f32", 0, "hutch"),        # Sum[CSR (Hutch), c*I (Hutch), Diagonal (exact)]
+    "diag_hutch_kron888_f32_k0": ("kron888_f32", 0, "hutch"),                # Sum[Kronecker (exact), c*I (Hutch)]
     "diag_hutch_product_f64_k2": ("product_f64", 2, "hutch"),
     "diag_hutch_product_f64_km3": ("product_f64", -3, "hutch"),
 }
