@@ -494,13 +494,40 @@ class Tridiagonal(LinearOperator):
 
 
 class Transpose(LinearOperator):
-    """operators.py:381-396 (only as the result of .T on a non-symmetric hot-path operator)."""
+    """operators.py:381-396.  Lazy, like the reference's (`.T` of a Sum / Product / Kronecker / ... is a
+    `Transpose[...]` there, and dispatch rules see it as such); what is applied is the transpose pushed down to
+    the leaves (`_push_transpose`: transposed Dense / CSR cores, reversed Products), so it runs on the same fused
+    kernels as the operator itself."""
     def __init__(self, A):
         super().__init__(dtype=A.dtype, shape=(A.shape[1], A.shape[0]))
         self.A = A
+        self.device = A.device
 
     def _infer_annotations(self):
         return set()
+
+    def pushed(self):
+        """The operator tree of A^T, or None when A is an opaque operator without a transpose of its own."""
+        token = _version_token(self.A)
+        cached = self.__dict__.get("_pushed_cache")
+        if cached is None or cached[0] != token:               # transposed leaf copies follow in-place updates
+            P = _push_transpose(self.A)
+            cached = (token, None if isinstance(P, Transpose) else P)
+            self.__dict__["_pushed_cache"] = cached
+        return cached[1]
+
+    def _matmat(self, X):
+        if self.pushed() is None:
+            if type(self.A)._rmatmat is LinearOperator._rmatmat:
+                raise NotImplementedError(f"{type(self.A).__name__} has no transposed matmat on this path")
+            return self.A._rmatmat(X.T.contiguous()).T.contiguous()
+        return LinearOperator._matmat(self, X)                 # plan of the pushed tree
+
+    def _rmatmat(self, X):
+        return self.A._matmat(X.T.contiguous()).T
+
+    def __str__(self):
+        return f"{str(self.A)}ᵀ"
 
 
 class Sliced(LinearOperator):
@@ -559,6 +586,24 @@ def mul(A, c):
 
 
 def transpose(A):
+    """cola/fns.py:140-168: SelfAdjoint -> itself, Transpose -> its operand, Dense / Triangular / Sparse -> the
+    transposed leaf, everything else -> a lazy Transpose."""
+    if A.isa(SelfAdjoint):
+        return A
+    if isinstance(A, Transpose):
+        return A.A
+    if isinstance(A, Triangular):
+        return Triangular(A.A.T.contiguous(), lower=not A.lower)
+    if isinstance(A, Dense):
+        return Dense(A.A.T.contiguous())
+    if isinstance(A, Sparse):
+        return A._transpose()
+    return Transpose(A)
+
+
+def _push_transpose(A):
+    """A^T as a tree of hot-path operators: the transpose distributed over Sum / Product / Kronecker / KronSum /
+    BlockDiag / Tridiagonal down to transposed leaves.  Returns Transpose(A) for operators it cannot open."""
     if A.isa(SelfAdjoint):
         return A
     if isinstance(A, Transpose):
@@ -572,17 +617,17 @@ def transpose(A):
     if isinstance(A, (Diagonal, Identity, ScalarMul)):
         return A
     if isinstance(A, Kronecker):
-        return Kronecker(*[transpose(M) for M in A.Ms])
+        return Kronecker(*[_push_transpose(M) for M in A.Ms])
     if isinstance(A, KronSum):
-        return KronSum(*[transpose(M) for M in A.Ms])
+        return KronSum(*[_push_transpose(M) for M in A.Ms])
     if isinstance(A, Tridiagonal):
         return Tridiagonal(A.gamma, A.beta, A.alpha)
     if isinstance(A, BlockDiag):
-        return BlockDiag(*[transpose(M) for M in A.Ms], multiplicities=A.multiplicities)
-    if isinstance(A, Sum):
-        return Sum(*[transpose(M) for M in A.Ms])
-    if isinstance(A, Product):
-        return Product(*[transpose(M) for M in reversed(A.Ms)])
+        return BlockDiag(*[_push_transpose(M) for M in A.Ms], multiplicities=A.multiplicities)
+    if type(A) is Sum:
+        return Sum(*[_push_transpose(M) for M in A.Ms])
+    if type(A) is Product:
+        return Product(*[_push_transpose(M) for M in reversed(A.Ms)])
     return Transpose(A)
 
 
@@ -874,6 +919,8 @@ def compile_plan(A):
             plan.shift += scale * float(op.c)
         elif isinstance(op, Diagonal):
             add_diag(op.diag if scale == 1.0 else scale * op.diag)
+        elif isinstance(op, Transpose) and op.pushed() is not None:
+            visit(op.pushed(), scale)
         elif type(op) is Sum:
             for M in op.Ms:
                 visit(M, scale)
