@@ -60,6 +60,11 @@ class Eigh(Algorithm):
 
 
 @dataclass
+class LU(Algorithm):
+    pass
+
+
+@dataclass
 class Exact(Algorithm):
     """cola/linalg/trace/diagonal_estimation.py:13-31"""
     bs: int = 100
@@ -133,6 +138,21 @@ class _DenseInverse(LinearOperator):
         return torch.cholesky_solve(X, self.L)
 
 
+class _DenseLUInverse(LinearOperator):
+    """inv(A, LU) for small general operators: torch.linalg.lu_factor / lu_solve on the dense matrix (library, as in
+    the reference: decompositions.py:178-186 + TriangularInv / Permutation products, inv.py:102-105)."""
+    def __init__(self, A):
+        super().__init__(A.dtype, A.shape)
+        self.LU, self.piv = torch.linalg.lu_factor(A.to_dense())
+        self.device = A.device
+
+    def _matmat(self, X):
+        return torch.linalg.lu_solve(self.LU, self.piv, X)
+
+    def _rmatmat(self, X):
+        return torch.linalg.lu_solve(self.LU, self.piv, X.T.contiguous(), adjoint=True).T
+
+
 def inv(A: LinearOperator, alg: Algorithm = Auto()):
     """cola/linalg/inverse/inv.py:42-151"""
     # structure rules first (inv.py:108-151)
@@ -158,8 +178,7 @@ def inv(A: LinearOperator, alg: Algorithm = Auto()):
         if A.isa(PSD):
             alg = Cholesky() if small else CG(**alg.__dict__)
         elif small:
-            raise NotImplementedError("small non-PSD operators route to a dense LU in the reference (inv.py:84-85), "
-                                      "which is outside the Krylov hot path")
+            alg = LU()
         else:
             alg = GMRES(**alg.__dict__)
     if isinstance(alg, CG):     # inv.py:66-69
@@ -170,6 +189,8 @@ def inv(A: LinearOperator, alg: Algorithm = Auto()):
     if isinstance(alg, Cholesky):
         assert A.isa(PSD), "Cholesky only valid for PSD matrices, wrap in cola.PSD if desired"
         return _DenseInverse(A)
+    if isinstance(alg, LU):         # inv.py:102-105
+        return _DenseLUInverse(A)
     raise NotImplementedError(f"inv with {type(alg).__name__} is outside the Krylov hot path")
 
 
@@ -308,8 +329,11 @@ def apply_unary(f, A: LinearOperator, alg: Algorithm = Auto()):
     raise NotImplementedError(f"apply_unary with {type(alg).__name__} is outside the Krylov hot path")
 
 
-def exp(A: LinearOperator, alg: Algorithm = Auto()):
-    """cola/linalg/unary/unary.py:229-246"""
+def exp(A: LinearOperator, alg: Algorithm = None):
+    """cola/linalg/unary/unary.py:229-246.  The KronSum rule is declared on (KronSum, Algorithm) without a default,
+    so it only applies when an algorithm is passed; `exp(A)` is the generic rule with Auto."""
+    if alg is None:
+        return apply_unary(torch.exp, A, Auto())
     if isinstance(A, KronSum):                       # exp(A (+) B) = exp(A) (x) exp(B)
         return Kronecker(*[exp(a, alg) for a in A.Ms])
     return apply_unary(torch.exp, A, alg)
@@ -320,9 +344,13 @@ def log(A: LinearOperator, alg: Algorithm = Auto()):
     return apply_unary(torch.log, A, alg)
 
 
-def pow(A: LinearOperator, alpha, alg: Algorithm = Auto()):
-    """cola/linalg/unary/unary.py:265-305: integer powers are products / inverses, the rest is f(A) = A^alpha."""
-    if isinstance(A, Kronecker):                     # :303-305
+def pow(A: LinearOperator, alpha, alg: Algorithm = None):
+    """cola/linalg/unary/unary.py:265-305: integer powers are products / inverses, the rest is f(A) = A^alpha.  The
+    Kronecker rule (:303-305) is declared without a default algorithm: it applies to the three-argument call only
+    (which is what sqrt / isqrt make)."""
+    if alg is None:
+        alg = Auto()
+    elif isinstance(A, Kronecker):
         return Kronecker(*[pow(a, alpha, alg) for a in A.Ms])
     k = int(np.round(alpha))
     if np.isclose(alpha, k):

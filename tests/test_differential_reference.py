@@ -211,3 +211,43 @@ def test_operator_algebra(name, emu):
     assert type(A.T).__name__ == type(Ar.T).__name__.split("[")[0], (type(A.T).__name__, type(Ar.T).__name__)
     assert close(L.diag(A.T, 0, L.Hutch(tol=2e-2, max_iters=2, key=key)),
                  cola.linalg.diag(Ar.T, 0, RHutch(tol=2e-2, max_iters=2, key=key)))
+
+
+@pytest.mark.parametrize("name", ["kron_dense_diag", "blockdiag_of_kron", "product_scalar_inside", "div",
+                                  "kronsum_of_diag_dense", "product_of_diagonals", "scalar_times_sum"])
+def test_inverse_and_power_rules(name, emu):
+    """inv structure rules (inv.py:108-151: Product reversed, BlockDiag / Kronecker factor-wise, Diagonal, ScalarMul)
+    with Auto on the small leaves, and the integer cases of pow (unary.py:265-300)."""
+    A, Ar = _expressions(cb.ops, cb.PSD)[name], _expressions(cola.ops, cola.PSD)[name]
+    n = A.shape[0]
+    B = pb.randn_np((n, 3), f64, 71)
+    if name in ("div", "kronsum_of_diag_dense"):                             # no structure rule: Auto on the whole operator
+        A, Ar = cb.PSD(A), cola.PSD(Ar)
+    Ai, Air = L.inv(A), cola.linalg.inv(Ar)
+    assert type(Ai).__name__ == type(Air).__name__.split("[")[0] or type(Ai).__name__.startswith("_Dense")
+    assert close(Ai @ B, Air @ B, 1e-8)
+    assert close(A @ (Ai @ B), B, 1e-8)
+    assert close(L.pow(A, 2) @ B, cola.linalg.pow(Ar, 2) @ B, 1e-9)
+    assert type(L.pow(A, 0)).__name__ == type(cola.linalg.pow(Ar, 0)).__name__.split("[")[0] == "Identity"
+
+
+def test_auto_picks_the_krylov_algorithms_for_large_operators(emu):
+    """BASELINE config 1 (dense SPD, n = 1024, so prod(shape) > 1e6 and Auto leaves the dense algorithms):
+    solve -> CG with its defaults (inv.py:72-92), eigmax -> power iteration, eig -> Lanczos from the default keyed
+    start vector (eigs.py:76-96), sqrt -> LanczosUnary (unary.py:113-131); non-PSD -> GMRES."""
+    P = pb.problem("cfg1_dense1024")
+    A, Ar = pb.to_b200(P["spec"], "cpu", P["ann"]), mg.to_reference(P["spec"], P["ann"])
+    b = P["B"]
+    x, xr = L.solve(A, b), cola.linalg.solve(Ar, b)
+    assert type(L.inv(A).alg).__name__ == type(cola.linalg.inv(Ar).alg).__name__ == "CG"
+    assert close(x, xr, 1e-4)                                                # fp32, tol-limited (1e-6 relative residual)
+    assert abs(float(L.eigmax(A)) - float(cola.linalg.eigmax(Ar))) < 1e-5 * float(cola.linalg.eigmax(Ar))
+    S, Sr = L.sqrt(A, L.Auto(max_iters=20)), cola.linalg.sqrt(Ar, cola.linalg.Auto(max_iters=20))
+    assert type(S).__name__ == type(Sr).__name__.split("[")[0] == "LanczosUnary"
+    assert close(S @ b, Sr @ b, 1e-4)
+    N = cb.ops.Dense(P["spec"][1] + torch.triu(torch.ones(1024, 1024), 1) * 1e-3)
+    Nr = cola.ops.Dense(N.A)
+    assert type(L.inv(N).alg).__name__ == type(cola.linalg.inv(Nr).alg).__name__ == "GMRES"
+    vals, _ = L.eig(A, 2, "LM", L.Auto(max_iters=30))
+    vals_r, _ = cola.linalg.eig(Ar, 2, "LM", cola.linalg.Auto(max_iters=30))
+    assert close(vals, vals_r, 1e-4)
