@@ -109,6 +109,11 @@ def require_cuda(t, what="operand"):
     if t.device.index != torch.cuda.current_device():
         raise RuntimeError(f"{what} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
                            "run the call under torch.cuda.device(...) (cola_b200 launches on the current device)")
+    # the kernels do not record autograd: returning a result without grad_fn would silently cut a training graph
+    if getattr(t, "requires_grad", False) and torch.is_grad_enabled():
+        raise RuntimeError(f"{what} requires grad, but cola_b200's native API is not differentiable: detach it / use "
+                           "torch.no_grad(), or keep the reference's operators and call cola_b200.install(), under which "
+                           "the reference's custom backward rules run with the solves on the kernels")
 
 
 def ptr(t, dtype=None):

@@ -116,6 +116,11 @@ class LinearOperator:
         densified factors, the CSR form of a Tridiagonal) that would otherwise go stale.  The Krylov loops validate
         once at entry and then use `matmat_into`, which does not re-check."""
         token = _version_token(self)
+        if torch.is_grad_enabled() and _token_requires_grad(token):
+            raise RuntimeError("a parameter of this operator requires grad, but cola_b200's native API is not "
+                               "differentiable: detach it / use torch.no_grad(), or keep the reference's operators and "
+                               "call cola_b200.install() (the reference's backward rules then run with the solves on "
+                               "the kernels)")
         if self._plan is None or self.__dict__.get("_plan_token") != token:
             self._plan = compile_plan(self)
             self._plan_token = token
@@ -211,16 +216,27 @@ class LinearOperator:
 
 
 def _version_token(op):
-    """(id, in-place version counter) of every tensor in the operator tree."""
+    """(id, in-place version counter, requires_grad) of every tensor in the operator tree."""
     tok = []
     for val in vars(op).values():
         if torch.is_tensor(val):
-            tok.append((id(val), val._version))
+            tok.append((id(val), val._version, bool(val.requires_grad)))
         elif isinstance(val, LinearOperator):
             tok.append(_version_token(val))
         elif isinstance(val, (tuple, list)) and val and all(isinstance(v, LinearOperator) for v in val):
             tok.append(tuple(_version_token(v) for v in val))
     return tuple(tok)
+
+
+def _token_requires_grad(tok):
+    for item in tok:
+        if isinstance(item, tuple):
+            if len(item) == 3 and isinstance(item[2], bool) and not isinstance(item[0], tuple):
+                if item[2]:
+                    return True
+            elif _token_requires_grad(item):
+                return True
+    return False
 
 
 def _as_operand(A, X):

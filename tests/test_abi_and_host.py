@@ -154,3 +154,9 @@ def test_operand_on_another_device_is_refused(monkeypatch):
     with pytest.raises(RuntimeError, match="current CUDA device"):
         be.require_cuda(other, "operand")
     be.require_cuda(types.SimpleNamespace(is_cuda=True, device=types.SimpleNamespace(index=0)), "operand")
+    # an operand that requires grad is refused while autograd records (no silent cut of the graph), accepted otherwise
+    wants_grad = types.SimpleNamespace(is_cuda=True, device=types.SimpleNamespace(index=0), requires_grad=True)
+    with pytest.raises(RuntimeError, match="not differentiable"):
+        be.require_cuda(wants_grad, "operand")
+    with torch.no_grad():
+        be.require_cuda(wants_grad, "operand")

@@ -188,3 +188,15 @@ def test_plan_follows_in_place_parameter_updates(emu):
     assert torch.allclose(A @ X, ref()) and A.plan() is not second
     Q, T, info = emu.linalg.Lanczos(start_vector=X[:, 0].contiguous() + d, max_iters=4, tol=1e-12)(emu.SelfAdjoint(A))
     assert torch.allclose(T.beta[0, 0], ((X[:, 0] + d) @ (A.to_dense() @ (X[:, 0] + d))) / ((X[:, 0] + d) @ (X[:, 0] + d)))
+
+
+def test_native_api_refuses_parameters_that_require_grad(emu):
+    """The kernels do not record autograd: a leaf that requires grad raises while recording is on (instead of handing
+    back a result without grad_fn), and is accepted under torch.no_grad()."""
+    W = torch.eye(4, dtype=torch.float64, requires_grad=True)
+    A = emu.ops.Dense(W) + emu.ops.Diagonal(torch.ones(4, dtype=torch.float64))
+    X = torch.ones(4, 2, dtype=torch.float64)
+    with pytest.raises(RuntimeError, match="not differentiable"):
+        A @ X
+    with torch.no_grad():
+        assert torch.equal(A @ X, 2 * X)
