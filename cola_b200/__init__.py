@@ -14,9 +14,10 @@ float32/float64 operators (cola_b200/plugin.py), which makes it a drop-in inside
 program.
 """
 from . import backend, linalg, ops, plugin, rng, sharding
-from .ops import (PSD, Hermitian, LinearOperator, SelfAdjoint, Stiefel, Unitary, block_diag, kron, lazify)
+from .ops import (PSD, Hermitian, LinearOperator, SelfAdjoint, Stiefel, Unitary, block_diag, densify, kron, kronsum,
+                  lazify)
 
 from .plugin import from_cola, install, uninstall
 
 __all__ = ["backend", "linalg", "ops", "plugin", "rng", "sharding", "install", "uninstall", "from_cola", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
-           "LinearOperator", "lazify", "kron", "block_diag"]
+           "LinearOperator", "lazify", "kron", "kronsum", "densify", "block_diag"]

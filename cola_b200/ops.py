@@ -653,6 +653,18 @@ def kron(A, B):
     return Kronecker(*(a + b))
 
 
+def kronsum(A, B):
+    """cola/fns.py:224-242"""
+    a = A.Ms if isinstance(A, KronSum) else (lazify(A), )
+    b = B.Ms if isinstance(B, KronSum) else (lazify(B), )
+    return KronSum(*(a + b))
+
+
+def densify(A):
+    """cola/fns.py:41-47"""
+    return A.to_dense() if isinstance(A, LinearOperator) else A
+
+
 def block_diag(*ops, multiplicities=None):
     return BlockDiag(*ops, multiplicities=multiplicities)
 
