@@ -194,6 +194,46 @@ def inv(A: LinearOperator, alg: Algorithm = Auto()):
     raise NotImplementedError(f"inv with {type(alg).__name__} is outside the Krylov hot path")
 
 
+# ---------------------------------------------------------------------------------------------------- pseudo-inverse
+@dataclass
+class LSTSQ(Algorithm):
+    """cola/linalg/inverse/pinv.py:14-19"""
+    def __call__(self, A: LinearOperator):
+        return LSTSQSolve(A)
+
+
+class LSTSQSolve(LinearOperator):
+    """cola/linalg/inverse/pinv.py:22-28: dense least squares (library), for small operators."""
+    def __init__(self, A: LinearOperator):
+        super().__init__(A.dtype, (A.shape[-1], A.shape[-2]))
+        self.A = A.to_dense()
+        self.device = A.device
+
+    def _matmat(self, X):
+        return torch.linalg.lstsq(self.A, X).solution
+
+
+def pinv(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/inverse/pinv.py:31-96.  The CG rule is the hot-path one: CG on the normal equations A^H A (a
+    Product chain of the plan: transposed core, core), plus eps * I, applied to A^H b."""
+    if isinstance(A, Identity):
+        return A
+    if isinstance(A, ScalarMul):
+        return ScalarMul(1 / A.c, shape=A.shape, dtype=A.dtype, device=A.c.device)
+    if isinstance(A, Diagonal):
+        return Diagonal(1. / A.diag)
+    if isinstance(alg, Auto):          # pinv.py:50-62
+        alg = LSTSQ() if bool(np.prod(A.shape) <= 1e6) else CG(**alg.__dict__)
+    if isinstance(alg, CG):            # pinv.py:65-71
+        M = A.H @ A
+        cons = (1e-6 if A.dtype == torch.float32 else 1e-15) * max(A.shape)
+        Op = IterativeOperatorWInfo(M, alg)
+        return PSD(Op + cons * I_like(M)) @ A.H
+    if isinstance(alg, LSTSQ):
+        return LSTSQSolve(A)
+    raise NotImplementedError(f"pinv with {type(alg).__name__} is outside the Krylov hot path")
+
+
 # ---------------------------------------------------------------------------------------------------- eig
 def get_slice(num, which):
     """cola/linalg/decompositions/decompositions.py:214-224"""
@@ -209,6 +249,12 @@ def get_slice(num, which):
 def eigmax(A: LinearOperator, alg: Algorithm = Auto()):
     """cola/linalg/eig/eigs.py:44-57"""
     es, _ = eig(A, k=1, which="LM", alg=alg)
+    return es[0]
+
+
+def eigmin(A: LinearOperator, alg: Algorithm = Auto()):
+    """cola/linalg/eig/eigs.py:60-73"""
+    es, _ = eig(A, k=1, which="SM", alg=alg)
     return es[0]
 
 

@@ -959,6 +959,8 @@ def compile_plan(A):
                     scale = scale * float(M.c)
                 elif isinstance(M, Identity):
                     continue
+                elif isinstance(M, Transpose) and M.pushed() is not None:
+                    rest.append(M.pushed())                    # a transposed Dense / CSR leaf is a core like any other
                 else:
                     rest.append(M)
             if not rest:

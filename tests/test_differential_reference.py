@@ -329,3 +329,22 @@ def test_random_operator_trees(seed, emu):
         assert close(L.diag(A, 0, L.Exact()), de) and close(L.trace(A), tr), what
         compared += 1
     assert compared >= 30
+
+
+def test_pinv_and_eigmin(emu):
+    """pinv with CG runs on the normal equations A^H A as a two-core Product chain (pinv.py:65-71); small operators
+    under Auto take the dense least squares; eigmin is eig(k=1, 'SM') (eigs.py:60-73)."""
+    M = pb.randn_np((20, 8), f64, 90)
+    B = pb.randn_np((20, 3), f64, 91)
+    A, Ar = cb.ops.Dense(M), cola.ops.Dense(M)
+    P, Pr = L.pinv(A, L.CG(tol=1e-12, max_iters=100)), cola.linalg.pinv(Ar, RCG(tol=1e-12, max_iters=100))
+    assert tuple(P.shape) == tuple(Pr.shape) == (8, 20)
+    assert close(P @ B, Pr @ B, 1e-10) and close(P @ B, torch.linalg.lstsq(M, B).solution, 1e-9)
+    normal = P.Ms[0].Ms[0].A                                     # the operator handed to CG
+    assert normal.plan().describe() == "1*DenseCore@DenseCore"
+    assert type(L.pinv(A)).__name__ == type(cola.linalg.pinv(Ar)).__name__ == "LSTSQSolve"
+    assert close(L.pinv(A) @ B, cola.linalg.pinv(Ar) @ B)
+    d = pb.t(pb.rs(92).uniform(0.5, 1.5, size=8), f64)
+    assert close(L.pinv(cb.ops.Diagonal(d)).diag, cola.linalg.pinv(cola.ops.Diagonal(d)).diag)
+    S = pb.spd_dense(12, f64, 5)
+    assert close(L.eigmin(cb.PSD(cb.ops.Dense(S))), cola.linalg.eigmin(cola.PSD(cola.ops.Dense(S))))
