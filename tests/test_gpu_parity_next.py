@@ -253,3 +253,19 @@ def test_triangular_inverse(cb):
     S = M @ M.T
     Sinv = L.inv(T.T) @ Ti
     assert rel(S @ (Sinv @ X), X) < 1e-11
+
+
+def test_pinv_normal_equations(cb):
+    """pinv(A, CG) (pinv.py:65-71): CG on A^T A as a two-core Product chain of the plan (transposed Dense core, Dense
+    core), applied to A^T b; rectangular operator, checked against the dense least-squares solution."""
+    L, ops = cb.linalg, cb.ops
+    M = pb.randn_np((300, 40), torch.float64, 93).to(DEV)
+    B = pb.randn_np((300, 5), torch.float64, 94).to(DEV)
+    A = ops.Dense(M)
+    P = L.pinv(A, L.CG(tol=1e-12, max_iters=200))
+    assert tuple(P.shape) == (40, 300)
+    assert P.Ms[0].Ms[0].A.plan().describe() == "1*DenseCore@DenseCore"
+    x = P @ B
+    assert rel(x, torch.linalg.lstsq(M, B).solution) < 1e-8
+    assert rel(M.T @ (M @ x), M.T @ B) < 1e-9                    # normal equations
+    assert float(L.eigmin(cb.PSD(ops.Dense((M.T @ M).contiguous())), L.Lanczos(max_iters=40, tol=1e-12))) > 0

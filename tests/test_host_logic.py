@@ -169,6 +169,10 @@ def test_triangular_inverse(emu):
     gn.test_triangular_inverse(emu)
 
 
+def test_pinv_normal_equations(emu):
+    gn.test_pinv_normal_equations(emu)
+
+
 def test_plan_follows_in_place_parameter_updates(emu):
     """Plans hold derived copies (scaled diagonals, folded scalars, the CSR form of a Tridiagonal): an in-place write
     to a leaf (an optimizer step) or a replaced leaf must recompile, an untouched operator must not."""
