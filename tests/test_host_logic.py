@@ -204,3 +204,53 @@ def test_native_api_refuses_parameters_that_require_grad(emu):
         A @ X
     with torch.no_grad():
         assert torch.equal(A @ X, 2 * X)
+
+
+def test_bench_e2e_double_buffering_logic(emu, monkeypatch):
+    """bench.py's end-to-end loop overlaps the copies of adjacent steps with the solve on a second stream.  With the
+    CUDA stream / event objects replaced by recorders (no GPU here) the schedule itself is checked: no wait on an
+    event that was not recorded, an input buffer is only refilled after the solve that read it, every step's
+    solution reaches the host buffer, iterations are counted once per step."""
+    import contextlib
+
+    import bench
+    from tests import problems as pb
+    log = []
+
+    class Stream:
+        def wait_event(self, ev):
+            assert ev.recorded, "wait on an event that was never recorded"
+            log.append(("wait", ev.name))
+
+    class Event:
+        count = 0
+
+        def __init__(self, **kw):
+            self.recorded, self.name = False, Event.count
+            Event.count += 1
+
+        def record(self, stream=None):
+            self.recorded = True
+            log.append(("record", self.name))
+
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: Stream())
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: Stream())
+    monkeypatch.setattr(torch.cuda, "Event", Event)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+    P = pb.problem("lap24_f32")
+    A = pb.to_b200(P["spec"], "cpu", P["ann"])
+    alg = emu.linalg.CG(tol=1e-30, max_iters=10)
+    x_ref, _ = alg(A, P["B"])
+    for steps in (1, 2, 5):
+        x_host = torch.zeros_like(P["B"])
+        assert bench.e2e_double_buffered(alg, A, P["B"], x_host, "cpu", steps) == 10 * steps
+        assert torch.equal(x_host, x_ref)
+    # loaded[0], loaded[1], released[0], released[1] are events 0..3 of a call: buffer 1 is refilled for step 3 only
+    # after solve 1 released it (wait on released[1] precedes the second record of loaded[1])
+    Event.count = 0
+    log.clear()
+    bench.e2e_double_buffered(alg, A, P["B"], torch.zeros_like(P["B"]), "cpu", 4)
+    second_fill = [i for i, e in enumerate(log) if e == ("record", 1)][1]
+    assert ("wait", 3) in log[:second_fill]
