@@ -883,6 +883,8 @@ class Plan:
         if X.dtype != self.dtype or Y.dtype != self.dtype:
             raise TypeError(f"operand dtype {X.dtype}/{Y.dtype} does not match operator dtype {self.dtype}")
         assert X.shape[0] == self.shape[1] and Y.shape[0] == self.shape[0] and X.shape[1] == Y.shape[1]
+        if X.shape[1] == 0 or X.shape[0] == 0 or Y.shape[0] == 0:
+            return                                             # empty block: nothing to launch (the reference returns (n, 0))
         square = self.shape[0] == self.shape[1]
         n_terms = len(self.terms)
         if n_terms == 0:
