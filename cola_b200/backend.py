@@ -136,6 +136,30 @@ def off_ptr(t, elem_offset):
     return ctypes.c_void_p(t.data_ptr() + elem_offset * t.element_size())
 
 
+_PINNED = {}
+
+
+def read_small(t):
+    """Host copy of a small device tensor WITHOUT a DMA transfer (cola_publish_bytes): a one-block kernel writes the
+    bytes into mapped pinned host memory in stream order, the host waits on an event and reads its own memory.
+    `t.cpu()` would be a pageable cudaMemcpy, which queues behind whatever large transfer occupies the D2H copy engine
+    (the polls of a solve whose previous 1 GiB result is still being copied out waited ~20 ms each)."""
+    require_cuda(t, "a polled tensor")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    key = (t.device.index, torch.cuda.current_stream().cuda_stream)
+    slot = _PINNED.get(key)
+    if slot is None or slot[0].numel() < nbytes:
+        slot = (torch.empty(max(4096, nbytes), dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+        _PINNED[key] = slot
+    pin, ev = slot
+    lib().call("cola_publish_bytes", ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(pin.data_ptr()), nbytes, stream_ptr())
+    ev.record()
+    ev.synchronize()
+    return pin[:nbytes].clone().view(t.dtype).reshape(t.shape)
+
+
 def scalar(dtype, x):
     return ctypes.c_float(x) if dtype == torch.float32 else ctypes.c_double(x)
 

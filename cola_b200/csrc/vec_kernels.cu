@@ -367,6 +367,12 @@ __global__ void cg_advance_kernel(cola_cg_ctl_t* ctl, const double* gamma, const
   }
 }
 
+// ---- small device -> mapped-pinned-host publication (poll of the stopping rules without a DMA transfer) --------
+__global__ void publish_kernel(const uint32_t* __restrict__ src, volatile uint32_t* dst, int64_t n_words) {
+  for (int64_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+}
+
 // ---- Lanczos three-term step: W -= alpha Vi + beta_prev Vim1   (lanczos.py:245-248) ---------------
 template <typename T, int VEC>
 struct ThreeTermOp {
@@ -476,7 +482,15 @@ using namespace cola;
 
 extern "C" {
 
-int cola_version(void) { return 1; }
+int cola_version(void) { return 2; }
+int cola_publish_bytes(const void* src, void* host_mapped, int64_t nbytes, void* stream) {
+  if (!src || !host_mapped) return fail(COLA_E_BADARG, "publish: null pointer");
+  if (nbytes <= 0) return COLA_OK;
+  if (nbytes % 4 != 0) return fail(COLA_E_BADARG, "publish: nbytes must be a multiple of 4");
+  publish_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(src),
+                                                                          static_cast<volatile uint32_t*>(host_mapped), nbytes / 4);
+  return cuda_status("publish");
+}
 const char* cola_last_error(void) { return g_err; }
 int64_t cola_launch_count(void) { return g_launches.load(); }
 

@@ -33,7 +33,7 @@ def arnoldi_fact(A: LinearOperator, rhs, max_iters, tol, pbar=False):
     nrm_sq = torch.zeros((m + 1, b), dtype=torch.float64, device=dev)
     be.col_dots(rhs, rhs, nrm_sq[0])
     be.col_scale(rhs, Q[0], nrm_sq[0], take_sqrt=True, mode=2)         # init_arnoldi (arnoldi.py:327-335)
-    norm_host = np.sqrt(nrm_sq[0].cpu().numpy())
+    norm_host = np.sqrt(be.read_small(nrm_sq[0]).numpy())
     h10 = None
     samples, evals, idx = [], 0, 0
     t0 = time.time()
@@ -54,7 +54,7 @@ def arnoldi_fact(A: LinearOperator, rhs, max_iters, tol, pbar=False):
             be.mgs_link(w, Q[j - 1], h[j - 1], Q[j], h[j])
         be.mgs_link(w, Q[idx], h[idx], None, None, wnorm2=nrm_sq[idx + 1])
         be.col_scale(w, w, nrm_sq[idx + 1], take_sqrt=True, mode=3, a=tol / 2.)   # w /= clip(norm, tol/2)
-        norm_host = np.sqrt(nrm_sq[idx + 1].cpu().numpy())                         # poll for the stop rule
+        norm_host = np.sqrt(be.read_small(nrm_sq[idx + 1]).numpy())                         # poll for the stop rule
         if idx == 0:
             h10 = norm_host.copy()                                                # H[:, 1, 0]
         idx += 1

@@ -87,6 +87,33 @@ def _global_error_trace(group, col_norms):
     return packed[:-1] / packed[-1]
 
 
+def _empty_block_cg(b, max_iters):
+    """A rank whose column block is empty (fewer right-hand sides than ranks, sharding.solve_sharded): no kernel runs,
+    but the rank still takes part in the collectives of `_global_stop_rule` / `_global_error_trace` so that the
+    other ranks do not wait for it; its `info` is the global one.  It has no residual of its own, so in every
+    round of the agreement it simply stands at the largest iteration count any rank reports."""
+    t0 = time.time()
+    it = 0
+    group = STOP_RULE_GROUP if _world(STOP_RULE_GROUP) > 1 else None
+    col_norms = torch.zeros((1, 0), dtype=torch.float64, device=b.device)
+    if group is not None:
+        import torch.distributed as dist
+        while True:
+            ks = torch.tensor([it, -it], dtype=torch.int64, device=b.device)
+            dist.all_reduce(ks, op=dist.ReduceOp.MAX, group=group)
+            k_max, k_min = int(ks[0]), -int(ks[1])
+            if k_max == k_min:
+                break
+            it = k_max
+        col_norms = torch.zeros((it + 1, 0), dtype=torch.float64, device=b.device)
+        trace = _global_error_trace(group, col_norms).cpu().numpy()
+    else:
+        trace = np.full(1, np.nan)
+    samples = np.concatenate([trace, trace[-1:]])
+    info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": (time.time() - t0) / (it + 1)}
+    return torch.empty_like(b), torch.empty_like(b), it, info
+
+
 @dataclass
 class CG(Algorithm):
     """cola/linalg/inverse/cg.py:13-36"""
@@ -123,6 +150,8 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     dt = A.dtype
     b = b.to(dt).contiguous()
     n, k = b.shape
+    if k == 0:
+        return _empty_block_cg(b, int(max_iters))
     dev = b.device
     max_iters = int(max_iters)
     lib = be.lib()
@@ -200,7 +229,7 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     def drive(limit):
         """Enqueue gated batches until the device-side rule (or the iteration cap `limit`) stops the loop."""
         while True:
-            c = ctl.cpu()
+            c = be.read_small(ctl)
             it, done = int(c[0]), int(c[1])
             if done:
                 return it
@@ -269,6 +298,8 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
     dt = A.dtype
     b = b.to(dt).contiguous()
     n, k = b.shape
+    if k == 0:
+        return _empty_block_cg(b, int(max_iters))
     dev = b.device
     max_iters = int(max_iters)
     lib = be.lib()
@@ -316,7 +347,7 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
 
     def drive(limit):
         while True:
-            c = ctl.cpu()
+            c = be.read_small(ctl)
             it, done = int(c[0]), int(c[1])
             if done:
                 return it

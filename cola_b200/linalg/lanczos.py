@@ -83,7 +83,7 @@ def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
             be.reorth_update(V, 1, i + 1, w, C, sign=-1.0)
             be.reorth_dots(V, 1, i + 1, w, C2)
         be.reorth_update(V, 1, i + 1, w, C2, sign=-1.0, wnorm2=sub_sq[i])
-        sub_host[i] = np.sqrt(sub_sq[i].cpu().numpy())     # poll: the stop rule needs subdiag[i]
+        sub_host[i] = np.sqrt(be.read_small(sub_sq[i]).numpy())     # poll: the stop rule needs subdiag[i]
         if i == 1:
             pass
         i += 1

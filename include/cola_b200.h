@@ -180,6 +180,14 @@ int cola_cg_tol_f64(const double* gamma0, double tol, double* tol_eff, int64_t k
 int cola_cg_advance_f32(cola_cg_ctl_t* ctl, const double* gamma, const float* tol_eff, int increment, void* stream);
 int cola_cg_advance_f64(cola_cg_ctl_t* ctl, const double* gamma, const double* tol_eff, int increment, void* stream);
 
+/* Publish a few bytes of device state (the CG control block, a row of squared norms) to MAPPED PINNED HOST memory
+ * from a kernel, in stream order: `host_mapped` is a cudaHostAlloc'ed buffer (directly addressable from the device
+ * under unified addressing), nbytes a multiple of 4.  This is how the loops poll their stopping rules (the two
+ * device->host syncs per iteration of cola/utils/torch_tqdm.py:42,88): the host waits on an event and reads its own
+ * memory, so the poll never queues behind a large DMA transfer on the copy engines (a 16-byte cudaMemcpy does: it
+ * cost 16 % of the end-to-end solve when 1 GiB result copies were in flight). */
+int cola_publish_bytes(const void* src, void* host_mapped, int64_t nbytes, void* stream);
+
 /* ---- Full reorthogonalisation (Lanczos CGS2: lanczos.py:287-296; Arnoldi MGS: arnoldi.py:304-311) ------
  * Krylov basis layout (B200-native, differs from the reference's (b, n, m+2) with the Krylov index
  * fastest): V is (n_vec, n, b) contiguous, i.e. vector j is an (n, b) row-major block at V + j*vstride,

@@ -231,7 +231,8 @@ def reorth_update_dots(V, j0, j1, W, C1, C2, sign=-1.0, gate=None):
 _WRAPPERS = dict(col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm,
                  mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
-                 tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link)
+                 tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,
+                 read_small=lambda t: t.detach().clone())      # cola_publish_bytes: a host copy of a few device bytes
 
 
 @contextlib.contextmanager

@@ -134,6 +134,42 @@ def test_sharded_host_loops_match_unsharded():
     assert results[0][8]["it_local"] < results[1][8]["it_local"] == results[1][8]["it_ref"]
 
 
+def _worker_fewer_rhs_than_ranks(rank, world, port, results):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cola_b200 as cb
+    from tests import problems as pb
+    from tests.host_harness import emulated_kernels
+    Pd = pb.problem("dense96_f64")
+    with emulated_kernels():
+        Ad = pb.to_b200(Pd["spec"], "cpu", Pd["ann"])
+        B1 = Pd["B"][:, :1].contiguous()                        # ONE right-hand side, two ranks: rank 0's block is (n, 0)
+        alg = cb.linalg.CG(tol=1e-9, max_iters=500)
+        xs, info = cb.sharding.solve_sharded(Ad, B1, alg, group=dist.group.WORLD)
+        xref, info_ref = alg(Ad, B1)
+        lo, hi = cb.sharding.column_range(1, rank, world)
+    results[rank] = (hi - lo, info["iterations"], info_ref["iterations"],
+                     float((xs - xref).abs().max() / xref.abs().max()),
+                     float(abs(info["errors"] - info_ref["errors"]).max() / info_ref["errors"].max()))
+    dist.destroy_process_group()
+
+
+def test_fewer_rhs_than_ranks():
+    """a rank with an empty column block must neither raise nor leave the others waiting in the
+    stop-rule all-reduce; every rank returns the unsharded iteration count, trace and solution."""
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_worker_fewer_rhs_than_ranks, args=(world, port, results), nprocs=world, join=True)
+    assert sorted(results[r][0] for r in range(world)) == [0, 1]
+    for r in range(world):
+        _, it, it_ref, xerr, terr = results[r]
+        assert it == it_ref and xerr < 1e-10 and terr < 1e-10, results[r]
+
+
 def test_column_range_covers_everything():
     from cola_b200.sharding import column_range
     for total in (1, 7, 64, 100, 1024):
