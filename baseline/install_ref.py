@@ -50,18 +50,31 @@ def install(force=False, verbose=False):
             print(r.stdout)
         if r.returncode != 0:
             raise RuntimeError("pip install of the reference failed:\n" + r.stdout[-2000:])
+    # The reference's setup.py uses find_packages(), which skips its directories without an __init__.py
+    # (cola/linalg/tbd, svd, preconditioning, ... are implicit namespace packages in the source tree): complete the
+    # installed package with every source file pip left out, unmodified.
+    missing = []
+    for dirpath, dirnames, filenames in os.walk(os.path.join(REF_SRC, "cola")):
+        dirnames[:] = [d for d in dirnames if d != "__pycache__"]
+        rel = os.path.relpath(dirpath, REF_SRC)
+        for fn in filenames:
+            if fn.endswith(".py") and not os.path.exists(os.path.join(TARGET, rel, fn)):
+                os.makedirs(os.path.join(TARGET, rel), exist_ok=True)
+                shutil.copy2(os.path.join(dirpath, fn), os.path.join(TARGET, rel, fn))
+                missing.append(os.path.join(rel, fn))
     for shim in ("plum", "optree"):
         shutil.copytree(os.path.join(SHIMS, shim), os.path.join(TARGET, shim),
                         ignore=shutil.ignore_patterns("__pycache__"))
     with open(os.path.join(TARGET, "INSTALL.json"), "w") as f:
         json.dump({"source": REF_SRC, "how": "pip install --no-index --no-build-isolation --no-deps --target baseline/_ref",
-                   "shims": ["plum", "optree"], "note": "unmodified reference package + this repo's import shims"}, f)
+                   "shims": ["plum", "optree"], "completed_namespace_files": missing,
+                   "note": "unmodified reference package + this repo's import shims"}, f)
     return TARGET
 
 
 def reference_sys_path():
     """sys.path entries (in order) that make `import cola` resolve to the reference, or [] when it is unavailable."""
-    if os.path.isdir(os.path.join(REF_SRC, "cola")):
+    if os.path.isdir(os.path.join(REF_SRC, "cola")) and not os.environ.get("COLA_REF_FORCE_INSTALLED"):
         return [SHIMS, REF_SRC]
     if installed():
         return [TARGET]

@@ -106,7 +106,7 @@ def from_cola(A, cola):
         # preconditioners.py:128-130: U diag(s) U^T + I as a two-core chain plus the identity
         U = A.U.contiguous()
         M = bops.Sum(bops.Product(bops.Dense(U), bops.Dense((A.subspace_scaling * U.T).contiguous())),
-                     bops.Identity(tuple(A.shape), A.dtype))
+                     bops.Identity(tuple(A.shape), A.dtype).to(U.device))
     elif unary is not None and isinstance(A, unary.LanczosUnary):
         M = b_stoch.LanczosUnary(from_cola(A.A, cola), A.f, **{k: v for k, v in getattr(A, "kwargs", {}).items()
                                                                 if k in ("max_iters", "tol", "pbar")})

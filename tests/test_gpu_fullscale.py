@@ -8,9 +8,14 @@ identical seeded inputs at the sizes the bench reports, not toy sizes.
         log-determinant value of those probes;
   cfg5  graph Laplacian reduced to 2^20 nodes (avg degree 16), fp64, Lanczos m = 32: alpha / beta and the top Ritz values.
 
-Tolerances are the north-star bar (1e-5 fp32, 1e-10 fp64) over the window in which the ORACLE itself is stable at
-that tolerance (measured here by re-running it on a perturbed / higher-precision copy, as tests/problems.py does
-for the small cases).  The oracle needs ~1-2 minutes of host time for the whole file."""
+Tolerances are the north-star bar (1e-5 fp32, 1e-10 fp64).  At these sizes the fp32 ORACLE (= the reference's fp32
+arithmetic on the CPU) is itself 1e-4 away from exact arithmetic from the first iteration on: its column reductions
+over n = 2^18 .. 2^22 rows accumulate sequentially in fp32 (first B200 run of this file: cfg2 errors[0] 0.372484 in the
+fp32 oracle, 0.3725923 in its own fp64 run, 0.372592 on the GPU, whose reductions accumulate in fp64).  The fp32
+configs are therefore held (a) to the bar against the oracle run in fp64 on the same fp32 inputs, and (b) against the
+fp32 oracle to within that oracle's own measured distance from its fp64 run.  fp64 (cfg5) is held to 1e-10 over the
+window in which the oracle is stable under a 1e-15 perturbation.  The oracle needs ~2-3 minutes of host time for the
+whole file."""
 import numpy as np
 import pytest
 import torch
@@ -41,6 +46,17 @@ def window_of(a, b, rtol):
     m = min(len(a), len(b))
     bad = np.nonzero(np.abs(a[:m] - b[:m]) > 0.25 * rtol * np.abs(b[:m]))[0]
     return int(bad[0]) if len(bad) else m
+
+
+def assert_trace(got, o64, o32, rtol, what):
+    """got vs the fp64 oracle at rtol, and vs the fp32 oracle within that oracle's own distance from fp64."""
+    got, o64, o32 = (np.asarray(a, dtype=np.float64) for a in (got, o64, o32))
+    assert got.shape == o64.shape == o32.shape, (what, got.shape, o64.shape, o32.shape)
+    np.testing.assert_allclose(got, o64, rtol=rtol, err_msg=f"{what}: vs the fp64 oracle")
+    floor = np.abs(o32 - o64)
+    bad = np.abs(got - o32) > 2.0 * floor + rtol * np.abs(o64)
+    assert not bad.any(), (what, "vs the fp32 oracle beyond its own fp32 noise", got[bad], o32[bad], o64[bad])
+    return float((floor / np.abs(o64)).max())
 
 
 @pytest.fixture(scope="module")
@@ -97,11 +113,15 @@ def test_cfg2_full_scale_cg_trace(cb, ko):
     data, rows, cols, shape = laplacian_coo(2048, torch.float32, "cpu")
     B = rhs_block(shape[0], 64, seed=0)
     xo, _, its_o, info_o = ko.cg(ko.SparseOp(data, rows, cols, shape), B, tol=1e-30, max_iters=iters)
+    x64, _, _, info_64 = ko.cg(ko.SparseOp(data.double(), rows, cols, shape), B.double(), tol=1e-30, max_iters=iters)
     A = cb.PSD(cb.ops.Sparse(data.to(DEV), rows.to(DEV), cols.to(DEV), shape))
     x, info = cb.linalg.CG(tol=1e-30, max_iters=iters)(A, B.to(DEV))
-    assert info["iterations"] == info_o["iterations"] == iters + 1
-    np.testing.assert_allclose(info["errors"], info_o["errors"], rtol=F32_TOL)
-    assert rel(x, xo) < F32_TOL, rel(x, xo)
+    assert info["iterations"] == info_o["iterations"] == info_64["iterations"] == iters + 1
+    floor = assert_trace(info["errors"], info_64["errors"], info_o["errors"], F32_TOL, "cfg2 info['errors']")
+    assert rel(x, x64) < F32_TOL, rel(x, x64)
+    assert rel(x, xo) < F32_TOL + 2 * rel(xo, x64), (rel(x, xo), rel(xo, x64))
+    print(f"cfg2: trace rel vs fp64 oracle {rel(info['errors'], info_64['errors']):.2e}, x rel {rel(x, x64):.2e}; "
+          f"fp32 oracle's own distance from fp64: trace {floor:.2e}, x {rel(xo, x64):.2e}")
 
 
 # ------------------------------------------------------------------------------------------------ cfg3
@@ -114,18 +134,21 @@ def _cfg3(ko, dtype=torch.float32):
 
 def test_cfg3_full_scale_cg_trace(cb, ko):
     """BASELINE config 3 at full size (64^3, 128 RHS, fp32): 20 CG iterations, tensor-core (3xTF32) and exact SIMT
-    contraction paths, against the oracle; window = where the fp32 oracle agrees with its own fp64 run."""
+    contraction paths, against the oracle in fp64 (bar) and in fp32 (within its own noise)."""
     iters = 20
     Fs, n, Ao = _cfg3(ko)
     B = torch.randn(n, CFG3_K, generator=torch.Generator().manual_seed(0))
     xo, _, _, info_o = ko.cg(Ao, B, tol=1e-30, max_iters=iters)
-    # stability window from 16 of the columns in fp64 (the trace is a mean over columns: compare like with like)
-    x32, _, _, i32 = ko.cg(Ao, B[:, :16].contiguous(), tol=1e-30, max_iters=iters)
-    _, _, A64 = _cfg3(ko, torch.float64)
-    x64, _, _, i64 = ko.cg(A64, B[:, :16].double().contiguous(), tol=1e-30, max_iters=iters)
-    window = window_of(i32["errors"], i64["errors"], F32_TOL)
+    A64 = ko.SumOp(ko.KroneckerOp(*[ko.DenseOp(F.double()) for F in Fs]), ko.ScaledIdentityOp(0.1, n, torch.float64))
+    x64, _, _, info_64 = ko.cg(A64, B.double(), tol=1e-30, max_iters=iters)
+    # window: where the fp64 oracle is insensitive (at the bar) to an fp32-rounding-sized perturbation of the factors
+    noise = [1.0 + 6e-8 * torch.randn(F.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(9 + i))
+             for i, F in enumerate(Fs)]
+    Ap = ko.SumOp(ko.KroneckerOp(*[ko.DenseOp(F.double() * z) for F, z in zip(Fs, noise)]),
+                  ko.ScaledIdentityOp(0.1, n, torch.float64))
+    _, _, _, info_p = ko.cg(Ap, B.double(), tol=1e-30, max_iters=iters)
+    window = window_of(info_p["errors"], info_64["errors"], F32_TOL)
     assert window >= 8, window
-    floor = rel(x32, x64)                                       # the fp32 oracle's own distance from exact arithmetic
     K = cb.ops.Kronecker(*[cb.PSD(cb.ops.Dense(F.to(DEV))) for F in Fs])
     A = cb.PSD(K + 0.1 * cb.ops.I_like(K))
     core = A.plan().terms[0][1][0]
@@ -134,11 +157,12 @@ def test_cfg3_full_scale_cg_trace(cb, ko):
         if tc:
             assert core._tc_ok(B.to(DEV)) == (CFG3_D == 64)
         x, info = cb.linalg.CG(tol=1e-30, max_iters=iters)(A, B.to(DEV))
-        assert info["iterations"] == info_o["iterations"]
-        np.testing.assert_allclose(info["errors"][:window], info_o["errors"][:window], rtol=F32_TOL,
-                                   err_msg=f"tensor cores: {tc}")
-        assert rel(x, xo) < max(F32_TOL, 4 * floor), (tc, rel(x, xo), floor)
-        print(f"cfg3 tc={tc}: window {window}/{len(info_o['errors'])}, x rel {rel(x, xo):.2e} (oracle fp32 vs fp64 {floor:.2e})")
+        assert info["iterations"] == info_o["iterations"] == info_64["iterations"]
+        floor = assert_trace(info["errors"][:window], info_64["errors"][:window], info_o["errors"][:window], F32_TOL,
+                             f"cfg3 info['errors'], tensor cores: {tc}")
+        assert rel(x, x64) < max(F32_TOL, 4 * rel(xo, x64)), (tc, rel(x, x64), rel(xo, x64))
+        print(f"cfg3 tc={tc}: window {window}/{len(info_o['errors'])}, trace rel {rel(info['errors'][:window], info_64['errors'][:window]):.2e}, "
+              f"x rel {rel(x, x64):.2e} (fp32 oracle vs fp64: trace {floor:.2e}, x {rel(xo, x64):.2e})")
     core.use_tensor_cores = True
 
 
@@ -155,9 +179,13 @@ def test_cfg4_shape_lanczos_and_slq(cb, ko):
     _, ao, bo, info_o = ko.lanczos(Ao, Z, m, 1e-7)
     A64 = ko.SumOp(ko.KroneckerOp(*[ko.DenseOp(F.double()) for F in Fs]), ko.DiagonalOp(dg.double()))
     _, a64, b64, _ = ko.lanczos(A64, Z.double(), m, 1e-7)
-    # window: leading coefficients on which the fp32 oracle agrees with its fp64 run at the bar
-    wa = min(window_of(ao[p].numpy(), a64[p].numpy(), F32_TOL) for p in range(2))
-    wb = min(window_of(bo[p].numpy(), b64[p].numpy(), F32_TOL) for p in range(2))
+    # window: leading coefficients on which the fp64 oracle is insensitive (at the bar) to an fp32-rounding-sized
+    # perturbation of the diagonal
+    zn = 1.0 + 6e-8 * torch.randn(n, dtype=torch.float64, generator=torch.Generator().manual_seed(4))
+    Ap = ko.SumOp(ko.KroneckerOp(*[ko.DenseOp(F.double()) for F in Fs]), ko.DiagonalOp(dg.double() * zn))
+    _, ap, bp, _ = ko.lanczos(Ap, Z.double(), m, 1e-7)
+    wa = min(window_of(ap[p].numpy(), a64[p].numpy(), F32_TOL) for p in range(2))
+    wb = min(window_of(bp[p].numpy(), b64[p].numpy(), F32_TOL) for p in range(2))
     w = min(wa, wb)
     assert w >= 6, (wa, wb)
     K = cb.ops.Kronecker(*[cb.PSD(cb.ops.Dense(F.to(DEV))) for F in Fs])
@@ -166,17 +194,18 @@ def test_cfg4_shape_lanczos_and_slq(cb, ko):
     alpha, beta = T.alpha[..., 0].cpu(), T.beta[..., 0].cpu()
     assert info["iterations"] == info_o["iterations"]
     assert tuple(alpha.shape) == tuple(ao.shape) and tuple(beta.shape) == tuple(bo.shape)
-    np.testing.assert_allclose(alpha[:, :w].numpy(), ao[:, :w].numpy(), rtol=F32_TOL)
-    np.testing.assert_allclose(beta[:, :w].numpy(), bo[:, :w].numpy(), rtol=F32_TOL)
-    assert rel(alpha, ao) < 100 * F32_TOL and rel(beta, bo) < 100 * F32_TOL
+    assert_trace(alpha[:, :w].numpy(), a64[:, :w].numpy(), ao[:, :w].numpy(), F32_TOL, "cfg4 alpha")
+    assert_trace(beta[:, :w].numpy(), b64[:, :w].numpy(), bo[:, :w].numpy(), F32_TOL, "cfg4 beta")
+    assert rel(alpha, a64) < 100 * F32_TOL and rel(beta, b64) < 100 * F32_TOL
     # SLQ value of the same two probes (quadrature is a smooth function of T: tight even past the window)
     from cola_b200.linalg import stochastic
     est = stochastic.slq_per_probe(A, torch.log, Z.to(DEV), m, 1e-7)
     est_o = ko.slq_per_probe(Ao, torch.log, Z, m, 1e-7)
     est_64 = ko.slq_per_probe(A64, torch.log, Z.double(), m, 1e-7)
     floor = float((est_o.double() - est_64).abs().max() / est_64.abs().max())     # the oracle's own fp32 noise
-    assert rel(est, est_o) < max(F32_TOL, 4 * floor), (rel(est, est_o), floor)
-    print(f"cfg4: coefficient window {w}/{m}, slq rel {rel(est, est_o):.2e} (oracle fp32 vs fp64 {floor:.2e})")
+    assert rel(est, est_64) < F32_TOL, (rel(est, est_64), floor)
+    assert rel(est, est_o) < F32_TOL + 2 * floor, (rel(est, est_o), floor)
+    print(f"cfg4: coefficient window {w}/{m}, slq rel vs fp64 oracle {rel(est, est_64):.2e} (fp32 oracle vs fp64 {floor:.2e})")
 
 
 # ------------------------------------------------------------------------------------------------ cfg5
