@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcola_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "cola_b200.h")
 
 _CTYPES = {
-    "int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
+    "int": ctypes.c_int, "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float, "double": ctypes.c_double,
     "void": None,
 }
 
@@ -158,6 +158,16 @@ def read_small(t):
     ev.record()
     ev.synchronize()
     return pin[:nbytes].clone().view(t.dtype).reshape(t.shape)
+
+
+def small_ints(values, device):
+    """int32 device tensor of four values, written by a kernel from its arguments (cola_store_i32x4): no pageable
+    H2D memcpy, which would queue behind a large transfer on the copy engine (see read_small)."""
+    a, b, c, d = (int(v) for v in values)
+    t = torch.empty(4, dtype=torch.int32, device=device)
+    require_cuda(t, "a control block")
+    lib().call("cola_store_i32x4", ptr(t), a, b, c, d, stream_ptr())
+    return t
 
 
 def scalar(dtype, x):

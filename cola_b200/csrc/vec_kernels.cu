@@ -373,6 +373,11 @@ __global__ void publish_kernel(const uint32_t* __restrict__ src, volatile uint32
   __threadfence_system();
 }
 
+// ---- four 32-bit words from kernel arguments into device memory (control blocks built without a DMA transfer) ----
+__global__ void store_i32x4_kernel(int32_t* dst, int32_t a, int32_t b, int32_t c, int32_t d) {
+  dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+}
+
 // ---- Lanczos three-term step: W -= alpha Vi + beta_prev Vim1   (lanczos.py:245-248) ---------------
 template <typename T, int VEC>
 struct ThreeTermOp {
@@ -490,6 +495,11 @@ int cola_publish_bytes(const void* src, void* host_mapped, int64_t nbytes, void*
   publish_kernel<<<1, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(static_cast<const uint32_t*>(src),
                                                                           static_cast<volatile uint32_t*>(host_mapped), nbytes / 4);
   return cuda_status("publish");
+}
+int cola_store_i32x4(int32_t* dst, int32_t a, int32_t b, int32_t c, int32_t d, void* stream) {
+  if (!dst) return fail(COLA_E_BADARG, "store_i32x4: null pointer");
+  store_i32x4_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dst, a, b, c, d);
+  return cuda_status("store_i32x4");
 }
 const char* cola_last_error(void) { return g_err; }
 int64_t cola_launch_count(void) { return g_launches.load(); }

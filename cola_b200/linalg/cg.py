@@ -199,14 +199,14 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
         p.copy_(r)
         gamma.zero_()
         pap.zero_()
-        ctl.copy_(torch.tensor([0, 0, max_iters, k], dtype=torch.int32))
+        ctl.copy_(be.small_ints([0, 0, max_iters, k], dev))
     else:
         p = r.clone()
         ap = torch.empty_like(b)
         gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)
         pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
         tol_eff = torch.empty(k, dtype=dt, device=dev)
-        ctl = torch.tensor([0, 0, max_iters, k], dtype=torch.int32, device=dev)
+        ctl = be.small_ints([0, 0, max_iters, k], dev)
     be.col_dots(r, r, gamma[0])
     lib.call(f"cola_cg_tol_{sx}", be.ptr(gamma), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
     it_ptr, done_ptr = ctl[0:1], ctl[1:2]
@@ -270,7 +270,7 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     # ---- info dict exactly as while_loop_winfo builds it (torch_tqdm.py:35-62): the tracked error is sampled
     # before every cond evaluation (it+1 of them) and once more after the loop; the first two are dropped.
     col_norms = torch.sqrt(gamma[:it + 1])
-    trace = (col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).cpu().numpy()
+    trace = be.read_small(col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).numpy()
     samples = np.concatenate([trace, trace[-1:]])
     info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
     if ws:                                                       # hand back copies: the workspace is reused
@@ -328,7 +328,7 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
     be.col_dots(r, r, rnorm2[0])
     tol_eff = torch.empty(k, dtype=dt, device=dev)
     lib.call(f"cola_cg_tol_{sx}", be.ptr(rnorm2), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
-    ctl = torch.tensor([0, 0, max_iters, k], dtype=torch.int32, device=dev)
+    ctl = be.small_ints([0, 0, max_iters, k], dev)
     it_ptr, done_ptr = ctl[0:1], ctl[1:2]
     lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(rnorm2), be.ptr(tol_eff), 0, st())
     gamma_next = gamma[1:]                                       # row `it` of this view is gamma[it + 1]
@@ -360,7 +360,7 @@ def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):
                                                                     be.ptr(tol_eff), 0, st()), ctl, tol_eff, max_iters)
     elapsed = time.time() - t0
     col_norms = torch.sqrt(rnorm2[:it + 1])
-    trace = (col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).cpu().numpy()
+    trace = be.read_small(col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).numpy()
     samples = np.concatenate([trace, trace[-1:]])
     info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
     be.col_scale(x, x, mult_sq, take_sqrt=True, mode=0)          # x * ||b||  (cg.py:119)

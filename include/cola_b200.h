@@ -188,6 +188,11 @@ int cola_cg_advance_f64(cola_cg_ctl_t* ctl, const double* gamma, const double* t
  * cost 16 % of the end-to-end solve when 1 GiB result copies were in flight). */
 int cola_publish_bytes(const void* src, void* host_mapped, int64_t nbytes, void* stream);
 
+/* The opposite direction: four 32-bit words passed as kernel arguments are stored to dst[0..3] in stream order.  The
+ * loops build their control blocks (cola_cg_ctl_t: iteration, done flag, cap, columns) with it: a 16-byte pageable
+ * cudaMemcpy would queue on the H2D copy engine behind the next solve's 1 GiB right-hand-side block. */
+int cola_store_i32x4(int32_t* dst, int32_t a, int32_t b, int32_t c, int32_t d, void* stream);
+
 /* ---- Full reorthogonalisation (Lanczos CGS2: lanczos.py:287-296; Arnoldi MGS: arnoldi.py:304-311) ------
  * Krylov basis layout (B200-native, differs from the reference's (b, n, m+2) with the Krylov index
  * fastest): V is (n_vec, n, b) contiguous, i.e. vector j is an (n, b) row-major block at V + j*vstride,

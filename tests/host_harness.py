@@ -232,7 +232,8 @@ _WRAPPERS = dict(col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matma
                  mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
                  tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,
-                 read_small=lambda t: t.detach().clone())      # cola_publish_bytes: a host copy of a few device bytes
+                 read_small=lambda t: t.detach().clone(),
+                 small_ints=lambda values, device: torch.tensor([int(v) for v in values], dtype=torch.int32))      # cola_publish_bytes: a host copy of a few device bytes
 
 
 @contextlib.contextmanager
