@@ -166,6 +166,251 @@ __global__ void __launch_bounds__(kCsrThreads, 4) csr_spmm_kernel(CsrArgs<T> a) 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Software-pipelined variant for wide right-hand-side blocks (NZL = 1): the CSR staging and the L2 prefetch of the
+// gathered X rows run PF tiles AHEAD of the row loop, so the row loop's dependent loads are L2 hits instead of
+// DRAM round trips and no staging phase (rowptr -> colidx -> X, two exposed DRAM latencies plus two barriers per
+// tile in the kernel above) sits on the critical path:
+//     iteration i:  wait(cp.async) + one barrier | prefetch.L2 X rows of tile i+PF | cp.async colidx/vals of tile
+//                   i+PF+1 -> smem ring | cp.async rowptr slice of tile i+PF+2 | row loop of tile i
+// The ring holds PF+2 tiles of (colidx, vals) and PF+3 rowptr slices; cp.async (LDGSTS) lands in shared memory
+// without holding registers or stalling the issuing warp.  ncu of the non-pipelined kernel on cfg2: long_scoreboard
+// 9.6 of 16.5 warps/issue, DRAM 36 %, L2 25 % -- a latency-bound gather; this removes the DRAM part of that latency.
+// The row loop gathers up to BATCH non-zeros of a row in one predicated batch (one round trip for rows of <= BATCH
+// non-zeros instead of ceil(nnz/4) + remainder).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// CH: 16-byte column chunks per thread.  Thread l of a row group owns columns [(h*lanes + l)*VEC, +VEC) for h < CH, so
+// every load instruction of the group covers lanes*16 contiguous bytes.  CH = 2 halves the per-non-zero overhead
+// (shared-memory read of (col, val), address arithmetic, loop control) per FMA: the first kernel executed ~110 warp
+// instructions per row against ~13 of loads + FMAs + stores and ran at 54 % issue utilisation -- issue-bound as much as
+// latency-bound.
+// 16 bytes of X at base + col * pitch: one mad.wide.u32 (IMAD.WIDE.U32) for the address + one 128-bit read-only load
+template <typename T>
+__device__ __forceinline__ Vec<T, 16 / (int)sizeof(T)> gather16(uint64_t base, uint32_t col, uint32_t pitch) {
+  Vec<T, 16 / (int)sizeof(T)> r;
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("{ .reg .u64 a; mad.wide.u32 a, %4, %5, %6; ld.global.nc.v4.f32 {%0,%1,%2,%3}, [a]; }"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(col), "r"(pitch), "l"(base));
+  } else {
+    asm volatile("{ .reg .u64 a; mad.wide.u32 a, %2, %3, %4; ld.global.nc.v2.f64 {%0,%1}, [a]; }"
+                 : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(col), "r"(pitch), "l"(base));
+  }
+  return r;
+}
+
+template <typename T, int CH, bool EPI, bool DOTS, int PF, int BATCH, int MINB>
+__global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArgs<T> a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  constexpr int VEC = 16 / (int)sizeof(T);
+  constexpr int NZS = PF + 2, RPS = PF + 3;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: nz[NZS][cap] (col, val) | rp[RPS][rows_per_tile + 1] | red[256*VEC doubles]
+  Nz<T>* s_nz = reinterpret_cast<Nz<T>*>(smem_raw);
+  int32_t* s_rp = reinterpret_cast<int32_t*>(s_nz + (size_t)NZS * a.cap);
+  const int tid = threadIdx.x;
+  const int g = tid / a.lanes, l = tid - g * a.lanes;
+  const bool col_ok = g < a.groups;
+  const uint32_t ldxb = (uint32_t)(a.ldx * (int64_t)sizeof(T));      // row pitch of X in bytes (< 2^32, checked by the launcher)
+  const uint32_t chunk_b = (uint32_t)a.lanes * 16u;                   // byte distance between a thread's column chunks
+  // The thread's two column-chunk base addresses, made opaque to the compiler: otherwise it keeps "parameter + lane
+  // offset" symbolic and re-derives every gather address with LDC.64 + IMAD.WIDE + IADD3 + IADD3.X (+ shifts); as an
+  // opaque 64-bit register a gather address is ONE IMAD.WIDE.U32 (col * pitch + base).
+  uint64_t xb0 = reinterpret_cast<uint64_t>(a.X) + (uint64_t)l * 16, xb1 = xb0 + chunk_b;
+  asm volatile("" : "+l"(xb0), "+l"(xb1));
+  const char* __restrict__ Xb = reinterpret_cast<const char*>(a.X) + (size_t)l * 16;
+  char* __restrict__ Yb = reinterpret_cast<char*>(a.Y) + (size_t)l * 16;
+  const size_t ldyb = (size_t)a.ldy * sizeof(T);
+  const int rpt = a.rows_per_tile, rps = rpt + 1, cap = a.cap;
+  const int64_t n_tiles = (a.n_rows + rpt - 1) / rpt;
+
+  // fp64 column accumulators: thread-private slots in shared memory (slot q of thread t at [q*256 + t]: conflict-free),
+  // touched once per tile -- 16 registers less in the row loop
+  double* s_dacc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_rp + (size_t)RPS * rps + 1) + 7) & ~(uintptr_t)7);
+  if constexpr (DOTS) {
+#pragma unroll
+    for (int q = 0; q < CH * VEC; ++q) s_dacc[q * kCsrThreads + tid] = 0.0;
+  }
+
+  auto tile_of = [&](int i) -> int64_t { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
+  auto rows_of = [&](int64_t t) -> int { return (int)min((int64_t)rpt, a.n_rows - t * rpt); };
+  auto load_rp = [&](int i) {
+    const int64_t t = tile_of(i);
+    if (t >= n_tiles) return;
+    const int rows = rows_of(t);
+    int32_t* dst = s_rp + (i % RPS) * rps;
+    const int32_t* src = a.rowptr + t * rpt;
+    for (int j = tid; j <= rows; j += kCsrThreads) cp_async_small<4>(dst + j, src + j);
+  };
+  auto stage = [&](int i) {   // rowptr slice of tile i has landed and is visible
+    const int64_t t = tile_of(i);
+    if (t >= n_tiles) return;
+    const int32_t* rp = s_rp + (i % RPS) * rps;
+    const int32_t base = rp[0], nnz = rp[rows_of(t)] - base;
+    if (nnz > cap) return;    // heavy tile: its row loop reads the CSR arrays directly
+    Nz<T>* dn = s_nz + (size_t)(i % NZS) * cap;
+    for (int j = tid; j < nnz; j += kCsrThreads) {
+      cp_async_small<4>(&dn[j].off, a.colidx + base + j);
+      cp_async_small<(int)sizeof(T)>(&dn[j].val, a.vals + base + j);
+    }
+  };
+  auto prefetch = [&](int i) {   // staged colidx of tile i has landed and is visible
+    const int64_t t = tile_of(i);
+    if (t >= n_tiles) return;
+    const int32_t* rp = s_rp + (i % RPS) * rps;
+    const int32_t nnz = rp[rows_of(t)] - rp[0];
+    if (nnz > cap) return;
+    const Nz<T>* dn = s_nz + (size_t)(i % NZS) * cap;
+    for (int j = tid; j < nnz; j += kCsrThreads) {
+      const char* xr = reinterpret_cast<const char*>(a.X) + (uint64_t)dn[j].off * (uint64_t)ldxb;
+      for (int b = 0; b < a.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + b));
+    }
+  };
+
+  // prologue: rowptr slices of tiles 0..PF+1, then the CSR ranges of tiles 0..PF
+  for (int i = 0; i <= PF + 1; ++i) load_rp(i);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  for (int i = 0; i <= PF; ++i) stage(i);
+  cp_async_commit();
+
+  for (int i = 0; tile_of(i) < n_tiles; ++i) {
+    cp_async_wait_all();
+    __syncthreads();   // staged data of tiles <= i+PF and rowptr of tile i+PF+1 visible; tile i-1's row loop finished
+    if (a.l2_prefetch) {
+      if (i == 0)
+        for (int q = 0; q < PF; ++q) prefetch(q);
+      prefetch(i + PF);
+    }
+    stage(i + PF + 1);
+    load_rp(i + PF + 2);
+    cp_async_commit();
+    if (!col_ok) continue;
+
+    const int64_t tile = tile_of(i);
+    const int64_t row0 = tile * rpt;
+    const int rows = rows_of(tile);
+    const int32_t* rp = s_rp + (i % RPS) * rps;
+    const int32_t base = rp[0];
+    const bool staged = rp[rows] - base <= cap;
+    const Nz<T>* tn = s_nz + (size_t)(i % NZS) * cap;
+    // per-tile dot partials in T (fp32: a handful of rows per thread), folded into the fp64 accumulators once per
+    // tile: the two F2F.F64.F32 conversions per element of a per-element fp64 product cost 0.13 ms of the 0.78 ms kernel
+    T facc[CH][VEC];
+#pragma unroll
+    for (int h = 0; h < CH; ++h)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) facc[h][v] = (T)0;
+
+    for (int r = g; r < rows; r += a.groups) {
+      const int64_t row = row0 + r;
+      const int32_t s = rp[r] - base, e = rp[r + 1] - base;
+      T acc[CH][VEC];
+#pragma unroll
+      for (int h = 0; h < CH; ++h)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[h][v] = (T)0;
+      if (staged) {
+        for (int32_t j = s; j < e; j += BATCH) {
+          // one predicated batch: all loads of up to BATCH non-zeros in flight, then predicated FMAs (no zero fill)
+          Vec<T, VEC> x[BATCH][CH];
+          T w[BATCH];
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            if (j + u < e) {
+              const Nz<T> nz = tn[j + u];
+              w[u] = nz.val;
+              x[u][0] = gather16<T>(xb0, nz.off, ldxb);
+              if constexpr (CH > 1) x[u][1] = gather16<T>(xb1, nz.off, ldxb);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < BATCH; ++u) {
+            if (j + u < e) {
+#pragma unroll
+              for (int h = 0; h < CH; ++h)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) acc[h][v] += w[u] * x[u][h].v[v];
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int32_t j = s; j < e; ++j) {
+          const uint32_t c = (uint32_t)a.colidx[base + j];
+          const T w = a.vals[base + j];
+          const char* xp = Xb + (uint64_t)c * (uint64_t)ldxb;
+#pragma unroll
+          for (int h = 0; h < CH; ++h) {
+            const Vec<T, VEC> x = ldg<T, VEC>(reinterpret_cast<const T*>(xp + h * chunk_b));
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) acc[h][v] += w * x.v[v];
+          }
+        }
+      }
+      const char* xrow = Xb + (uint64_t)row * (uint64_t)ldxb;
+      char* yrow = Yb + (size_t)row * ldyb;
+      T sd = (T)0;
+      if constexpr (EPI) sd = a.shift + (a.diag ? a.diag[row] : (T)0);      // (shift + diag_i) x_i as one term
+#pragma unroll
+      for (int h = 0; h < CH; ++h) {
+        Vec<T, VEC> y;
+        if constexpr (EPI) {
+          const Vec<T, VEC> xo = ldg<T, VEC>(reinterpret_cast<const T*>(xrow + h * chunk_b));   // own row: an L1 hit
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) y.v[v] = a.alpha * acc[h][v] + sd * xo.v[v];
+          if (a.accumulate) {
+            const Vec<T, VEC> yo = ldg<T, VEC>(reinterpret_cast<const T*>(yrow + h * chunk_b));
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) y.v[v] += yo.v[v];
+          }
+          if constexpr (DOTS) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) facc[h][v] += xo.v[v] * y.v[v];
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) y.v[v] = a.alpha * acc[h][v];
+          if (a.accumulate) {
+            const Vec<T, VEC> yo = ldg<T, VEC>(reinterpret_cast<const T*>(yrow + h * chunk_b));
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) y.v[v] += yo.v[v];
+          }
+        }
+        stg_stream<T, VEC>(reinterpret_cast<T*>(yrow + h * chunk_b), y);
+      }
+    }
+    if constexpr (DOTS) {
+#pragma unroll
+      for (int h = 0; h < CH; ++h)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s_dacc[(h * VEC + v) * kCsrThreads + tid] += (double)facc[h][v];
+    }
+  }
+  cp_async_wait_all();
+
+  if constexpr (DOTS) {
+    double* red = s_dacc + (size_t)CH * VEC * kCsrThreads;
+    double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k_full : 0);
+#pragma unroll
+    for (int h = 0; h < CH; ++h) {
+      double dacc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) dacc[v] = s_dacc[(h * VEC + v) * kCsrThreads + tid];
+      block_col_reduce<VEC>(red, dacc, col_ok, tid, g, l, a.lanes, kCsrThreads / a.lanes,
+                            (int64_t)(h * a.lanes + l) * VEC, a.k, -1, out);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // SpMV-like shapes (k <= 4: single-RHS CG, Lanczos with one start vector, cfg5): no shared-memory staging, no
 // block barriers.  SUB threads share a row: each reads a strided subset of the row's (colidx, val) pairs straight
 // from global memory (consecutive lanes -> consecutive non-zeros: coalesced), gathers X, and the partial sums are
@@ -306,8 +551,48 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
       break;
     }
     const bool off32 = (double)n_cols * (double)ldx < 4294967296.0;
+    // wide blocks whose rows split into whole 16-byte chunks, two per thread: the software-pipelined kernel
+    static const int env_pipe = getenv("COLA_CSR_PIPE") ? atoi(getenv("COLA_CSR_PIPE")) : 1;      // 0: first kernel (A/B)
+    static const int env_rpg = getenv("COLA_CSR_RPG") ? atoi(getenv("COLA_CSR_RPG")) : 8;
+    constexpr int kFullVec = 16 / (int)sizeof(T);
+    const bool pipe = env_pipe && nzl == 1 && vec == kFullVec && a.k % (2 * kFullVec) == 0 &&
+                      (double)n_cols * (double)ldx * sizeof(T) < 4294967296.0 && a.k / (2 * kFullVec) <= kCsrThreads;
+    if (pipe) {
+      a.lanes = (int)(a.k / (2 * kFullVec));
+      a.groups = kCsrThreads / a.lanes;
+      a.rows_per_tile = a.groups * (env_rpg > 0 && env_rpg <= 16 ? env_rpg : 8);
+      constexpr int pf = 1;
+      // measured on cfg2 (B200): prefetch.global.L2 of the gathered rows one tile ahead changes nothing (0.607 vs
+      // 0.626 ms): the row loop's ~1 us average miss latency is queueing in the memory system, not a cold L2
+      a.l2_prefetch = getenv("COLA_CSR_PIPE_PREFETCH") ? 1 : 0;
+      int64_t want2 = (int64_t)(1.5 * avg * a.rows_per_tile) + 64;
+      const int cap_max2 = sizeof(T) == 4 ? 3072 : 2048;
+      a.cap = (int)(want2 < 256 ? 256 : (want2 > cap_max2 ? cap_max2 : want2));
+      n_tiles = (n_rows + a.rows_per_tile - 1) / a.rows_per_tile;
+      smem = (size_t)(pf + 2) * a.cap * sizeof(Nz<T>) + (size_t)(pf + 3) * (a.rows_per_tile + 1) * 4 + 16 +
+             (dots ? (size_t)kCsrThreads * (2 + 1) * kFullVec * sizeof(double) : 0);   // fp64 accumulator slots + reduction scratch
+    }
+#define COLA_CSR_PIPE_LAUNCH2(EPIV, DOTSV, PFV, BV, MB)                                                       \
+  do {                                                                                                        \
+    auto kern = csr_spmm_pipe_kernel<T, 2, EPIV, DOTSV, PFV, BV, MB>;                                         \
+    static int attr_smem = 0;                                                                                 \
+    if (smem > 48 * 1024 && (int)smem > attr_smem) {                                                          \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+      attr_smem = (int)smem;                                                                                  \
+    }                                                                                                         \
+    int per_sm = 0;                                                                                           \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCsrThreads, smem);                          \
+    if (per_sm < 1) per_sm = 1;                                                                               \
+    int64_t grid = (int64_t)sm_count() * per_sm;                                                              \
+    if (grid > n_tiles) grid = n_tiles;                                                                       \
+    kern<<<(unsigned)grid, kCsrThreads, smem, st>>>(a);                                                       \
+  } while (0)
+  /* measured on cfg2: batch 6 / 2 CTAs per SM 0.59 ms; batch 4: 0.68; batch 8 (spills): 0.72; 3 CTAs per SM at 80
+     registers (spills): 0.77-0.96; prefetch distance 2: 0.58 */
+#define COLA_CSR_PIPE_LAUNCH(EPIV, DOTSV) COLA_CSR_PIPE_LAUNCH2(EPIV, DOTSV, 1, 6, 2)
 #define COLA_CSR_LAUNCH(EPIV, DOTSV, OFFV)                                                                    \
   do {                                                                                                        \
+    if (pipe) { COLA_CSR_PIPE_LAUNCH(EPIV, DOTSV); break; }                                                   \
     auto kern = nzl == 8 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 8>                                      \
               : nzl == 4 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 4>                                      \
               : nzl == 2 ? csr_spmm_kernel<T, VEC, EPIV, DOTSV, OFFV, 2>                                      \

@@ -100,7 +100,9 @@ def test_cfg2_spmm_64rhs_vs_oracle(g, cb, ko):
     ref = Yo.double() + (0.25 + dg.double())[:, None] * X.double()
     assert rel(Y2, ref) < 1e-6
     assert rel(dots, (X.double() * ref).sum(0)) < 1e-6
-    assert rel(dots, (Xd.double() * Y2.double()).sum(0)) < 1e-12
+    # fp32 blocks: the products of a tile's rows (<= 8 per thread) are summed in fp32 and folded into the fp64
+    # accumulators once per tile (csr_spmm_pipe_kernel), so the fused dots agree with an all-fp64 sum to ~1e-7
+    assert rel(dots, (Xd.double() * Y2.double()).sum(0)) < 1e-6
     # ragged widths of the same operator: 48 (12 lanes), 16, 8 columns
     for k in (48, 16, 8):
         assert rel(S @ Xd[:, :k].contiguous(), Yo[:, :k]) < 1e-6, k
