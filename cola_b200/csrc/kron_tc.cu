@@ -661,6 +661,354 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
   }
 }
 
+// =======================================================================================================
+// Second-generation fused kernel (round 2).  Same formulation, tile shape, descriptors and phase walk as
+// kron_fused_tc_kernel; what changed is everything around the MMAs, driven by profiles/r1_kron_tc_summary.md
+// (per-tile critical path, 339 MB written for a 134 MB result, 85 us of the last phase spent in 64 scattered
+// loads + stores per epilogue thread):
+//   * the RAW tile is the hi operand.  kind::tf32 reads the upper 19 bits of an fp32 word, i.e. hi = trunc(x) for
+//     free; the split warps only compute lo = rna_tf32(x - trunc(x)) (exact difference, rounded once) into ONE lo
+//     buffer: half the split's shared-memory writes, 64 KB less shared memory, and a ring slot is simply held
+//     until the MMAs that read it retire.  x = hi + lo to 2^-22 |x|, the same bound as the rounded split.
+//   * epilogue through shared memory and TMA stores (UTMASTG): TMEM -> registers -> a 32 KB staging tile (one
+//     128-byte row per warp instruction: conflict-free) -> four cp.async.bulk.tensor stores issued by a dedicated
+//     warp.  In the last mode the operator's INPUT tile for the fused epilogue (alpha K x + (shift + diag) x,
+//     <x, y>) is TMA-loaded into the same staging tile ahead of time and y is written over it in place, so the
+//     epilogue threads issue no global memory instructions at all.
+//   * 8 epilogue warps (two per TMEM lane quadrant, 32 columns each), 4 split warps.
+//   * launched cooperatively (co-residency of the device-wide phase barrier is checked by the driver), and EVERY
+//     phase after the first starts with that barrier: with several column chunks the workspace a phase overwrites
+//     may still be read by a slower CTA's previous phase (write-after-read race for k > 128).
+// Shared memory: factor hi|lo 32 KB, lo tile 32 KB, raw ring 3 x 32 KB, staging 2 x 32 KB = 224 KB.
+// =======================================================================================================
+constexpr int kF2Threads = 512;       // warps: 0 TMA loads, 1 MMA, 2 TMEM alloc, 3 staging (TMA stores + x tiles), 4-7 split, 8-15 epilogue
+constexpr int kF2Ring = 3;
+constexpr int kF2SplitWarps = 4;
+constexpr int kF2EpiWarps = 8;
+constexpr int kF2OffFacHi = 0;
+constexpr int kF2OffFacLo = kFacBytes;
+constexpr int kF2OffLo = 2 * kFacBytes;
+constexpr int kF2OffRing = kF2OffLo + kTileBytes;
+constexpr int kF2OffStg = kF2OffRing + kF2Ring * kTileBytes;
+constexpr int kF2OffBars = kF2OffStg + 2 * kTileBytes;
+constexpr int kF2Smem = kF2OffBars + 256 + 1024;
+static_assert(kF2Smem <= 232448, "fused2: shared memory budget");
+
+struct Fused2Maps {
+  CUtensorMap in[kMaxFused];     // source of mode i (swizzled operand boxes)
+  CUtensorMap fac[kMaxFused];
+  CUtensorMap out[kMaxFused];    // destination of mode i (plain boxes): ws0 / ws1 / Y
+  CUtensorMap xin;               // X with the destination geometry of the last mode (plain boxes): epilogue operand
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// lo = rna_tf32(x - trunc_tf32(x)) for `bytes` of a raw tile (layout-agnostic, elementwise)
+__device__ __forceinline__ void split_lo(const unsigned char* raw, unsigned char* lo, int bytes, int tid, int nthreads) {
+  for (int o = tid * 16; o < bytes; o += nthreads * 16) {
+    const float4 v = *reinterpret_cast<const float4*>(raw + o);
+    float4 l;
+    l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+    l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+    l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+    l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+    *reinterpret_cast<float4*>(lo + o) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kF2Threads, 1)
+    kron_fused2_tc_kernel(const __grid_constant__ Fused2Maps maps, FusedArgs a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const int D = a.D;
+  const uint32_t bar_full0 = sbase + kF2OffBars;               // [ring] raw tile (or factor) landed
+  const uint32_t bar_slotfree0 = bar_full0 + 8 * kF2Ring;      // [ring] MMAs reading the slot retired / factor copied (count 1)
+  const uint32_t bar_loready = bar_slotfree0 + 8 * kF2Ring;    // lo tile written (count kF2SplitWarps)
+  const uint32_t bar_lofree = bar_loready + 8;                 // MMAs reading the lo tile retired
+  const uint32_t bar_tfull0 = bar_lofree + 8;                  // [2] accumulator complete
+  const uint32_t bar_tempty0 = bar_tfull0 + 16;                // [2] accumulator drained (count kF2EpiWarps)
+  const uint32_t bar_stgfull0 = bar_tempty0 + 16;              // [2] staging tile ready for its next epilogue (free, or x tile landed)
+  const uint32_t bar_outready0 = bar_stgfull0 + 16;            // [2] staging tile holds y (count kF2EpiWarps)
+  const uint32_t bar_phase = bar_outready0 + 16;               // all stores of a phase complete (count 1)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kF2OffBars + 200);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kF2Ring; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_slotfree0 + 8 * s, 1); }
+    mbar_init(bar_loready, kF2SplitWarps);
+    mbar_init(bar_lofree, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull0 + 8 * s, 1);
+      mbar_init(bar_tempty0 + 8 * s, kF2EpiWarps);
+      mbar_init(bar_stgfull0 + 8 * s, 1);
+      mbar_init(bar_outready0 + 8 * s, kF2EpiWarps);
+    }
+    mbar_init(bar_phase, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int64_t n = 1;
+  for (int i = 0; i < D; ++i) n *= kD;
+  const int64_t n_pos_tiles = n / kD / 4;
+  const int pos_sh = 6 * (D - 1) - 2;
+  const int64_t pos_mask = n_pos_tiles - 1;
+  const int64_t n_tiles = n_pos_tiles * a.cpc;
+  const int n_phases = (int)a.n_chunks * D;
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  const int T = (int)((n_tiles - first + step - 1) / step);    // tiles of this CTA per phase (>= 1: grid <= n_tiles)
+
+  if (warp == 0) {
+    // ===== TMA loads: per phase the factor (through a ring slot), then the raw tiles =====
+    if (lane == 0) {
+      int rit = 0;
+      unsigned int barriers_passed = 0;
+      for (int ph = 0; ph < n_phases; ++ph) {
+        const int chunk = ph / D, mode = ph - chunk * D;
+        const int lsh = 6 * (D - 1 - mode);
+        const int64_t lmask = ((int64_t)1 << lsh) - 1;
+        {
+          const int s = rit % kF2Ring;
+          mbar_wait(bar_slotfree0 + 8 * s, ((rit / kF2Ring) & 1) ^ 1);
+          mbar_expect_tx(bar_full0 + 8 * s, kFacBytes);
+          const uint32_t dst = sbase + kF2OffRing + s * kTileBytes;
+          tma_load_2d(dst, &maps.fac[mode], bar_full0 + 8 * s, 0, 0);
+          tma_load_2d(dst + kFacBytes / 2, &maps.fac[mode], bar_full0 + 8 * s, 32, 0);
+          ++rit;
+        }
+        if (ph > 0) {
+          // the previous phase's stores are complete (this CTA), then device-wide: this phase reads what the others
+          // wrote (mode > 0) or overwrites a workspace the others may still be reading (mode 0 of a later chunk)
+          mbar_wait(bar_phase, (ph - 1) & 1);
+          ++barriers_passed;
+          if (!(a.dbg & 8)) grid_arrive_and_wait(a.sync_counter, barriers_passed * gridDim.x);
+          asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        const int in_base = (mode == 0) ? chunk * 32 * a.cpc : 0;
+        for (int64_t t = first; t < n_tiles; t += step, ++rit) {
+          const int64_t cc = t >> pos_sh, tp = t & pos_mask;
+          const int in_r0 = in_base + (int)cc * 32;
+          const int s = rit % kF2Ring;
+          mbar_wait(bar_slotfree0 + 8 * s, ((rit / kF2Ring) & 1) ^ 1);
+          mbar_expect_tx(bar_full0 + 8 * s, kTileBytes);
+          const uint32_t dst = sbase + kF2OffRing + s * kTileBytes;
+#pragma unroll
+          for (int at = 0; at < 4; ++at) {
+            const int64_t flat = tp * 4 + at;
+            const int64_t p = flat >> lsh, l = flat & lmask;
+            tma_load_3d(dst + at * kAtomBytes, &maps.in[mode], bar_full0 + 8 * s, in_r0, (int)l, (int)(p * kD));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int it = 0, rit = 0;
+      const uint64_t ad_ring0 = make_desc(sbase + kF2OffRing, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t ad_lo = make_desc(sbase + kF2OffLo, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t bd_hi = make_desc(sbase + kF2OffFacHi, 16, 1024, kLayoutSw128);
+      const uint64_t bd_lo = make_desc(sbase + kF2OffFacLo, 16, 1024, kLayoutSw128);
+      for (int ph = 0; ph < n_phases; ++ph) {
+        ++rit;                                                  // the factor's ring item
+        for (int j = 0; j < T; ++j, ++it, ++rit) {
+          const int acc = it & 1;
+          const int s = rit % kF2Ring;
+          mbar_wait(bar_tempty0 + 8 * acc, ((it >> 1) & 1) ^ 1);
+          mbar_wait(bar_loready, it & 1);                       // lo tile of this tile written (=> raw tile landed, factor in place)
+          tc_fence_after();
+          const uint32_t d = tmem_base + acc * kD;
+          const uint64_t ad_hi = ad_ring0 + (uint64_t)((s * kTileBytes) >> 4);
+          uint32_t accum = 0;
+          if (!(a.dbg & 2))
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {               // small terms first: A_lo B_hi, A_hi B_lo, A_hi B_hi
+            const uint64_t ad0 = (term == 0) ? ad_lo : ad_hi;
+            const uint64_t bd0 = (term == 1) ? bd_lo : bd_hi;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t ad = ad0 + (uint64_t)((kk * 1024) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)(((kk / 4) * (kFacBytes / 2) + (kk % 4) * 32) >> 4);
+              umma_tf32(d, ad, bd, kIdesc, accum);
+              accum = 1;
+            }
+          }
+          umma_commit(bar_slotfree0 + 8 * s);
+          umma_commit(bar_lofree);
+          umma_commit(bar_tfull0 + 8 * acc);
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== staging manager: x tiles of the last mode in, y tiles out (TMA) =====
+    if (lane == 0) {
+      const int total = n_phases * T;
+      // staging tile b is prepared for the epilogue of global tile j: free (plain arrive) or, for a last-mode tile,
+      // filled with the operator's input at the destination coordinates
+      auto prepare = [&](int j) {
+        if (j >= total) return;
+        const int b = j & 1;
+        const int ph = j / T;
+        const int chunk = ph / D, mode = ph - chunk * D;
+        const bool need_x = (mode == D - 1) && (a.shift != 0.f || a.diag != nullptr || a.dots != nullptr);
+        if (!need_x) { mbar_arrive(bar_stgfull0 + 8 * b); return; }
+        const int64_t t = first + (int64_t)(j - ph * T) * step;
+        const int64_t cc = t >> pos_sh, tp = t & pos_mask;
+        const int r0 = chunk * 32 * a.cpc + (int)cc * 32;
+        mbar_expect_tx(bar_stgfull0 + 8 * b, kTileBytes);
+        const uint32_t dst = sbase + kF2OffStg + b * kTileBytes;
+#pragma unroll
+        for (int at = 0; at < 4; ++at)                         // last mode: L = 1, atom = one p
+          tma_load_3d(dst + at * kAtomBytes, &maps.xin, bar_stgfull0 + 8 * b, r0, 0, (int)((tp * 4 + at) * kD));
+      };
+      prepare(0);
+      prepare(1);
+      int it = 0;
+      for (int ph = 0; ph < n_phases; ++ph) {
+        const int chunk = ph / D, mode = ph - chunk * D;
+        const bool last = (mode == D - 1);
+        const int lsh = 6 * (D - 1 - mode);
+        const int64_t lmask = ((int64_t)1 << lsh) - 1;
+        const int out_base = last ? chunk * 32 * a.cpc : 0;
+        for (int64_t t = first; t < n_tiles; t += step, ++it) {
+          const int b = it & 1;
+          const int64_t cc = t >> pos_sh, tp = t & pos_mask;
+          mbar_wait(bar_outready0 + 8 * b, (it >> 1) & 1);
+          if (!(a.dbg & 4)) {
+            const uint32_t src = sbase + kF2OffStg + b * kTileBytes;
+#pragma unroll
+            for (int at = 0; at < 4; ++at) {
+              const int64_t flat = tp * 4 + at;
+              const int64_t p = flat >> lsh, l = flat & lmask;
+              tma_store_3d(&maps.out[mode], src + at * kAtomBytes, out_base + (int)cc * 32, (int)l, (int)(p * kD));
+            }
+            bulk_commit();
+            bulk_wait_read0();                                  // the stores have read the staging tile
+          }
+          prepare(it + 2);
+        }
+        bulk_wait_all0();                                       // this phase's results are in global memory
+        __threadfence();
+        mbar_arrive(bar_phase);
+      }
+    }
+  } else if (warp >= 4 && warp < 4 + kF2SplitWarps) {
+    // ===== lo operand: raw ring slot -> lo tile (or, at a phase start, the factor pair) =====
+    const int tid = threadIdx.x - 128;
+    constexpr int kSplitThreads = kF2SplitWarps * 32;
+    int it = 0, rit = 0;
+    for (int ph = 0; ph < n_phases; ++ph) {
+      {
+        const int s = rit % kF2Ring;
+        mbar_wait(bar_full0 + 8 * s, (rit / kF2Ring) & 1);
+        if (it >= 1) mbar_wait(bar_lofree, (it - 1) & 1);      // every MMA of the previous phase retired (in order)
+        const unsigned char* raw = smem + kF2OffRing + s * kTileBytes;
+        for (int o = tid * 16; o < kFacBytes; o += kSplitThreads * 16)
+          *reinterpret_cast<float4*>(smem + kF2OffFacHi + o) = *reinterpret_cast<const float4*>(raw + o);
+        split_lo(raw, smem + kF2OffFacLo, kFacBytes, tid, kSplitThreads);
+        fence_async_smem();
+        // all split warps are done with the slot before it is handed back
+        asm volatile("bar.sync 1, %0;" ::"n"(kF2SplitWarps * 32) : "memory");
+        if (tid == 0) mbar_arrive(bar_slotfree0 + 8 * s);
+        ++rit;
+      }
+      for (int j = 0; j < T; ++j, ++it, ++rit) {
+        const int s = rit % kF2Ring;
+        mbar_wait(bar_full0 + 8 * s, (rit / kF2Ring) & 1);
+        if (it >= 1) mbar_wait(bar_lofree, (it - 1) & 1);      // MMAs of the previous tile no longer read the lo tile
+        if (!(a.dbg & 1)) split_lo(smem + kF2OffRing + s * kTileBytes, smem + kF2OffLo, kTileBytes, tid, kSplitThreads);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_loready);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: two warps per TMEM lane quadrant (= atom of the tile), 32 columns each =====
+    const int q = warp & 3, h = (warp - 8) >> 2;
+    int it = 0;
+    for (int ph = 0; ph < n_phases; ++ph) {
+      const int chunk = ph / D, mode = ph - chunk * D;
+      const bool last = (mode == D - 1);
+      const bool fused = last && (a.shift != 0.f || a.diag != nullptr || a.dots != nullptr);
+      const float* __restrict__ dg = last ? a.diag : nullptr;
+      const float alpha = last ? a.alpha : 1.f;
+      const int lsh = 6 * (D - 1 - mode);
+      const int64_t lmask = ((int64_t)1 << lsh) - 1;
+      const int64_t out_base = last ? (int64_t)chunk * 32 * a.cpc : 0;
+      double dacc = 0.0;
+      int64_t dacc_r0 = -1;
+      double* const dp = (last && a.dots != nullptr) ? a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k : 0) : nullptr;
+      for (int64_t t = first; t < n_tiles; t += step, ++it) {
+        const int acc = it & 1, b = it & 1;
+        const uint32_t par = (it >> 1) & 1;
+        const int64_t cc = t >> pos_sh, tp = t & pos_mask;
+        const int64_t out_r0 = out_base + cc * 32;
+        if (dp != nullptr && out_r0 != dacc_r0) {
+          if (dacc_r0 >= 0) atomicAdd(dp + dacc_r0 + lane, dacc);
+          dacc = 0.0;
+          dacc_r0 = out_r0;
+        }
+        mbar_wait(bar_tfull0 + 8 * acc, par);
+        tc_fence_after();
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kD + h * 32;
+        tmem_ld16_at<0>(taddr, v);
+        tmem_ld16_at<1>(taddr, v);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);      // accumulator back to the MMA warp
+        mbar_wait(bar_stgfull0 + 8 * b, par);                   // staging tile free / x tile landed
+        // atom q of the staging tile: row a (= column of D') is 128 B: r = lane
+        float* stg = reinterpret_cast<float*>(smem + kF2OffStg + b * kTileBytes + q * kAtomBytes) + (h * 32) * 32 + lane;
+        if (!fused) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) stg[i * 32] = alpha * __uint_as_float(v[i]);
+        } else {
+          const int64_t flat = tp * 4 + q;
+          const int64_t p = flat >> lsh, l = flat & lmask;
+          float facc = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = stg[i * 32];
+            float sd = a.shift;
+            if (dg != nullptr) sd += dg[((p * kD + h * 32 + i) << lsh) + l];
+            const float y = alpha * __uint_as_float(v[i]) + sd * x;
+            facc += x * y;
+            stg[i * 32] = y;
+          }
+          dacc += (double)facc;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_outready0 + 8 * b);
+      }
+      if (dp != nullptr && dacc_r0 >= 0) atomicAdd(dp + dacc_r0 + lane, dacc);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -686,6 +1034,21 @@ static int make_map_in(CUtensorMap* m, const float* in, int64_t pre, int64_t L, 
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(COLA_E_BADARG, "kron_tc: cuTensorMapEncodeTiled(in) failed");
+  return COLA_OK;
+}
+
+// same geometry as make_map_in, unswizzled: staging tiles of the epilogue (TMA stores of y, TMA loads of the x operand)
+static int make_map_plain(CUtensorMap* m, const float* ptr, int64_t pre, int64_t L, int64_t k) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return fail(COLA_E_UNSUPPORTED, "kron_tc: cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)L, (cuuint64_t)(pre * kD)};
+  cuuint64_t strides[2] = {(cuuint64_t)(k * 4), (cuuint64_t)(L * k * 4)};
+  cuuint32_t box[3] = {32, 1, (cuuint32_t)kD};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(COLA_E_BADARG, "kron_tc: cuTensorMapEncodeTiled(plain) failed");
   return COLA_OK;
 }
 
@@ -747,8 +1110,71 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
   float* ws0 = workspace;
   float* ws1 = workspace + n * 32;
   static const bool no_fused = getenv("COLA_KRON_NO_FUSED") != nullptr;   // A/B knob
+  static const bool v1_only = getenv("COLA_KRON_V1") != nullptr;           // A/B knob: first-generation fused kernel
+  if (n_factors <= kMaxFused && !no_fused && !v1_only && !accumulate) {
+    // ---- second-generation fused kernel: one cooperative launch for the whole matmat
+    static const int cpc_env2 = getenv("COLA_KRON_CPC") ? atoi(getenv("COLA_KRON_CPC")) : 0;
+    int cpc = cpc_env2 > 0 ? cpc_env2 : 4;
+    while (cpc > 1 && (k / 32) % cpc != 0) cpc >>= 1;
+    ws1 = workspace + n * 32 * cpc;
+    struct MapKey2 { const void* x; const void* y; const void* ws; const void* f[kMaxFused]; int64_t ldf[kMaxFused]; int64_t k, nf; int cpc; };
+    static thread_local MapKey2 cached_key2 = {};
+    static thread_local Fused2Maps cached_maps2;
+    static thread_local bool cached_valid2 = false;
+    MapKey2 key = {};
+    key.x = X; key.y = Y; key.ws = workspace; key.k = k; key.nf = n_factors; key.cpc = cpc;
+    for (int64_t i = 0; i < n_factors; ++i) { key.f[i] = factors[i]; key.ldf[i] = ldf[i]; }
+    if (!(cached_valid2 && memcmp(&key, &cached_key2, sizeof(MapKey2)) == 0)) {
+      for (int64_t i = 0; i < n_factors; ++i) {
+        COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
+        int rc = make_map_fac(&cached_maps2.fac[i], factors[i], ldf[i]);
+        if (rc) return rc;
+        int64_t pre = 1, L = 1;
+        for (int64_t j = 0; j < i; ++j) pre *= kD;
+        for (int64_t j = i + 1; j < n_factors; ++j) L *= kD;
+        const float* src = (i == 0) ? X : (((i - 1) % 2 == 0) ? ws0 : ws1);
+        rc = make_map_in(&cached_maps2.in[i], src, pre, L, (i == 0) ? k : 32 * cpc);
+        if (rc) return rc;
+        const bool last = (i == n_factors - 1);
+        float* dst = last ? Y : ((i % 2 == 0) ? ws0 : ws1);
+        rc = make_map_plain(&cached_maps2.out[i], dst, pre, L, last ? k : 32 * cpc);
+        if (rc) return rc;
+      }
+      int rc = make_map_plain(&cached_maps2.xin, X, n / kD, 1, k);
+      if (rc) return rc;
+      cached_key2 = key;
+      cached_valid2 = true;
+    }
+    FusedArgs fa;
+    fa.D = (int)n_factors;
+    fa.cpc = cpc;
+    fa.k = k; fa.n_chunks = k / (32 * cpc); fa.ws0 = ws0; fa.ws1 = ws1; fa.Y = Y; fa.X = X; fa.diag = diag; fa.alpha = alpha;
+    fa.shift = shift; fa.accumulate = 0; fa.dots = dots; fa.dots_row = dots_row; fa.gate = gate;
+    fa.sync_counter = reinterpret_cast<unsigned int*>(workspace + 2 * n * 128);
+    static const int fdbg2 = getenv("COLA_KRON_DBG") ? atoi(getenv("COLA_KRON_DBG")) : 0;
+    fa.dbg = fdbg2;
+    static bool smem_set2 = false;
+    if (!smem_set2) {
+      cudaFuncSetAttribute(kron_fused2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF2Smem);
+      smem_set2 = true;
+    }
+    cudaMemsetAsync(fa.sync_counter, 0, sizeof(unsigned int), st);
+    const int64_t n_tiles = n / kD / 4 * cpc;
+    int64_t grid = sm_count();
+    if (grid > n_tiles) grid = n_tiles;
+    // cooperative launch: the device-wide phase barrier needs every CTA resident; the driver refuses the launch otherwise
+    static const bool no_coop = getenv("COLA_KRON_NO_COOP") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kF2Threads); cfg.dynamicSmemBytes = kF2Smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = no_coop ? 0 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kron_fused2_tc_kernel, cached_maps2, fa);
+    if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, cudaGetErrorString(le)); }
+    return cuda_status("kron_fused2_tc");
+  }
   if (n_factors <= kMaxFused && !no_fused) {
-    // ---- one persistent launch for the whole matmat
+    // ---- one persistent launch for the whole matmat (first generation: kept for accumulate = 1 and A/B runs)
     FusedMaps maps;
     FusedArgs fa;
     // chunk width: whole RHS block up to 128 columns (fewest device-wide phases); COLA_KRON_CPC overrides (1, 2, 4)
