@@ -13,11 +13,11 @@ the C ABI in include/cola_b200.h; there is no CPU or eager-torch fallback.
 float32/float64 operators (cola_b200/plugin.py), which makes it a drop-in inside an existing wilson-labs/cola
 program.
 """
-from . import backend, linalg, ops, plugin, rng, sharding
+from . import autograd, backend, linalg, ops, plugin, rng, sharding
 from .ops import (PSD, Hermitian, LinearOperator, SelfAdjoint, Stiefel, Unitary, block_diag, densify, kron, kronsum,
                   lazify)
 
 from .plugin import from_cola, install, uninstall
 
-__all__ = ["backend", "linalg", "ops", "plugin", "rng", "sharding", "install", "uninstall", "from_cola", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
+__all__ = ["autograd", "backend", "linalg", "ops", "plugin", "rng", "sharding", "install", "uninstall", "from_cola", "PSD", "SelfAdjoint", "Hermitian", "Stiefel", "Unitary",
            "LinearOperator", "lazify", "kron", "kronsum", "densify", "block_diag"]

@@ -278,3 +278,29 @@ def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
                ptr(hprev) if hprev is not None else None, ptr(Qcur) if Qcur is not None else None,
                ptr(hcur) if hcur is not None else None, ptr(wnorm2) if wnorm2 is not None else None, n, b, ptr(gate),
                stream_ptr())
+
+
+# ---- parameter gradients (csrc/param_grad.cu) ------------------------------------------------------------
+def sddmm_csr(rowptr, colidx, n_rows, G, V, alpha, out):
+    """out[e] = alpha * <G[row(e), :], V[colidx[e], :]> over the CSR pattern; G, V (n, k) contiguous."""
+    k = V.shape[1]
+    dt = V.dtype
+    lib().call(f"cola_sddmm_csr_{sfx(dt)}", ptr(rowptr, torch.int32), ptr(colidx, torch.int32), n_rows, ptr(G, dt), k,
+               ptr(V, dt), k, k, scalar(dt, alpha), ptr(out, dt), 0, stream_ptr())
+
+
+def row_dots(G, g_row0, V, v_row0, n, alpha, out):
+    """out[i] = alpha * <G[g_row0 + i, :], V[v_row0 + i, :]>, i < n; G, V (rows, k) contiguous."""
+    k = V.shape[1]
+    dt = V.dtype
+    if n > 0:
+        lib().call(f"cola_row_dots_{sfx(dt)}", off_ptr(G, g_row0 * k), k, off_ptr(V, v_row0 * k), k, n, k,
+                   scalar(dt, alpha), ptr(out, dt), 0, stream_ptr())
+
+
+def gram_nt(G, g_off, Z, z_off, d_g, d_z, pre, post, alpha, C):
+    """C[a, j] += alpha * sum_{p, t} G[g_off + (p*d_g + a)*post + t] * Z[z_off + (p*d_z + j)*post + t]; C (d_g, d_z)
+    float64, zeroed by the caller."""
+    dt = Z.dtype
+    lib().call(f"cola_gram_nt_{sfx(dt)}", off_ptr(G, g_off), off_ptr(Z, z_off), d_g, d_z, pre, post,
+               ctypes.c_double(alpha), ptr(C, torch.float64), d_z, stream_ptr())

@@ -487,7 +487,7 @@ using namespace cola;
 
 extern "C" {
 
-int cola_version(void) { return 2; }
+int cola_version(void) { return 3; }
 int cola_publish_bytes(const void* src, void* host_mapped, int64_t nbytes, void* stream) {
   if (!src || !host_mapped) return fail(COLA_E_BADARG, "publish: null pointer");
   if (nbytes <= 0) return COLA_OK;

@@ -137,7 +137,16 @@ def cg(A: LinearOperator, rhs, x0=None, P=None, tol=1e-6, max_iters=5000, pbar=F
         x0 = x0[..., None] if x0 is not None else None
     if P is None:
         P = I_like(A)
-    soln, *_, infodict = run_batched_cg(A, rhs, x0, max_iters, tol, P, pbar=pbar)
+    from .. import autograd as ag
+    if ag.needs_grad(A, rhs):
+        # run_cg carries a custom backward (cg.py:72-91): cg_bwd re-applies the forward call's settings to the
+        # output cotangent and takes the parameter vjp at the solution
+        def run(A_, b_):
+            return run_batched_cg(A_, b_, x0, max_iters, tol, P, pbar=pbar)
+        soln, rest = ag.cg_with_grad(A, rhs, run)
+        infodict = rest[-1]
+    else:
+        soln, *_, infodict = run_batched_cg(A, rhs, x0, max_iters, tol, P, pbar=pbar)
     soln = soln.reshape(-1) if is_vector else soln
     return soln, infodict
 

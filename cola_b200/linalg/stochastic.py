@@ -209,6 +209,17 @@ def slq_per_probe(A, fun, Z, max_iters, tol, pbar=False):
 
 
 def slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key, probe_chunk_size=None, group=None, probes=None):
+    """cola/linalg/tbd/slq.py:34-52: the estimate, with slq_bwd (slq.py:10-31) as its backward when a parameter of A
+    requires grad (cola_b200/autograd.py)."""
+    from .. import autograd as ag
+    kw = dict(probe_chunk_size=probe_chunk_size, group=group, probes=probes)
+    if ag.needs_grad(A):
+        return ag.slq_with_grad(A, lambda: _slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key, **kw),
+                                dict(num_samples=num_samples, key=key, probe_chunk_size=probe_chunk_size))
+    return _slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key, **kw)
+
+
+def _slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key, probe_chunk_size=None, group=None, probes=None):
     """cola/linalg/tbd/slq.py:37-52.  The full (n, num_samples) probe block is drawn exactly as the reference
     draws it (one randn call), then processed in column chunks; with `group`, rank r takes the contiguous
     column range [r*P/G, (r+1)*P/G) and a single all-reduce combines (sum, count)."""

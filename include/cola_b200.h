@@ -249,6 +249,36 @@ int cola_mgs_link_f32(float* W, const float* Qprev, const double* hprev, const f
 int cola_mgs_link_f64(double* W, const double* Qprev, const double* hprev, const double* Qcur, double* hcur,
                       double* wnorm2, int64_t n, int64_t b, const int32_t* gate, void* stream);
 
+/* ---- parameter gradients of the backward passes ---------------------------------------------
+ * cg_bwd (cola/linalg/inverse/cg.py:72-86) and slq_bwd (cola/linalg/tbd/slq.py:10-31) end in
+ * xnp.vjp_derivs(fun = theta -> A(theta) @ V, primals = theta, duals = G) (cola/backends/torch_fns.py:244-260), which
+ * the reference leaves to torch autograd over its eager matmat.  Per leaf of the hot-path operators that vjp is one of
+ * the three contractions below; G and V are (n, k) row-major blocks with leading dimensions ldg / ldv. */
+
+/* Sparse values (operators.py:48-81):  out_vals[e] (+)= alpha * sum_c G[row(e), c] * V[colidx[e], c]
+ * over the CSR pattern (rowptr, colidx) -- a sampled dense-dense product; out_vals is aligned with `vals`. */
+int cola_sddmm_csr_f32(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, const float* G, int64_t ldg,
+                       const float* V, int64_t ldv, int64_t k, float alpha, float* out_vals, int accumulate, void* stream);
+int cola_sddmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, int64_t n_rows, const double* G, int64_t ldg,
+                       const double* V, int64_t ldv, int64_t k, double alpha, double* out_vals, int accumulate,
+                       void* stream);
+
+/* Diagonal (operators.py:323-348) and the bands of a Tridiagonal (:351-372, with row-shifted G / V pointers):
+ *   out[i] (+)= alpha * sum_c G[i, c] * V[i, c],  i < n. */
+int cola_row_dots_f32(const float* G, int64_t ldg, const float* V, int64_t ldv, int64_t n, int64_t k, float alpha, float* out,
+                      int accumulate, void* stream);
+int cola_row_dots_f64(const double* G, int64_t ldg, const double* V, int64_t ldv, int64_t n, int64_t k, double alpha,
+                      double* out, int accumulate, void* stream);
+
+/* Dense (operators.py:12-38; pre = 1, post = k: C = G V^T) and one factor of a Kronecker / KronSum (:198-275; G and Z
+ * viewed as (pre, d, post) like cola_mode_contract's operands: the "mode Gram" C = sum_p G_p Z_p^T):
+ *   C[a, j] += alpha * sum_{p < pre} sum_{t < post} G[(p*d_g + a)*post + t] * Z[(p*d_z + j)*post + t]
+ * C is a (d_g, d_z) DOUBLE accumulator with leading dimension ldc that the caller zeroes (split-K, fp64 atomics). */
+int cola_gram_nt_f32(const float* G, const float* Z, int64_t d_g, int64_t d_z, int64_t pre, int64_t post, double alpha,
+                     double* C, int64_t ldc, void* stream);
+int cola_gram_nt_f64(const double* G, const double* Z, int64_t d_g, int64_t d_z, int64_t pre, int64_t post, double alpha,
+                     double* C, int64_t ldc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

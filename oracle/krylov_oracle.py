@@ -669,3 +669,56 @@ def slq_per_probe(A, f, Z, max_iters=100, tol=1e-5):
     cut = 10 * eps * torch.max(lam, dim=1, keepdim=True)[0]
     flam = torch.where(torch.abs(lam) > cut, f(lam), torch.zeros_like(lam))
     return A.shape[-2] * torch.sum(tau**2 * flam, dim=-1)
+
+
+# ----------------------------------------------------------------------------------
+# backward passes  (cola/linalg/inverse/cg.py:72-86, cola/linalg/tbd/slq.py:10-31)
+# ----------------------------------------------------------------------------------
+def _param_vjp(make_op, params, V, G):
+    """xnp.vjp_derivs(fun = theta -> A(theta) @ V, primals = theta, duals = G) (cola/backends/torch_fns.py:244-260, real
+    dtypes: the conjugations are no-ops): torch autograd through the operator's eager matmat.  `make_op(params)` builds
+    the operator from the parameter tensors.  A SparseOp is rebuilt from its dense equivalent here: torch's CSR SpMM has
+    no autograd (the reference's own backward raises on Sparse for that reason, tests/golden/make_golden_bwd.py), the
+    gradient of the dense equivalent restricted to the pattern is what the rule means."""
+    ps = [p.detach().clone().requires_grad_(True) for p in params]
+    out = _differentiable(make_op(ps)).matmat(V)
+    return torch.autograd.grad(out, ps, grad_outputs=G, allow_unused=True)
+
+
+def _differentiable(A):
+    """The same operator with every SparseOp applied through index_add on its COO triplets (differentiable in the
+    values), recursively through the composite operators."""
+    if isinstance(A, SparseOp):
+        rows = torch.repeat_interleave(torch.arange(A.shape[0]), (A.indptr[1:] - A.indptr[:-1]).to(torch.int64))
+        cols = A.indices.to(torch.int64)
+        data = A.data
+
+        class _Coo(Op):
+            def matmat(self, X):
+                return torch.zeros((A.shape[0], X.shape[1]), dtype=X.dtype).index_add(0, rows, data[:, None] * X[cols])
+
+        return _Coo(A.shape, A.dtype)
+    for attr in ("terms", "factors", "blocks", "Ms"):
+        if hasattr(A, attr):
+            setattr(A, attr, [_differentiable(t) for t in getattr(A, attr)])
+    if isinstance(A, ScaledOp):
+        A.A = _differentiable(A.A)
+    return A
+
+
+def cg_bwd(make_op, params, soln, dy, x0=None, tol=1e-6, max_iters=1000, P=None):
+    """cg.py:72-86: db = run_batched_cg(A, dy, x0, max_iters, tol, P); dA = vjp(theta -> A(theta) @ soln, -db).
+    Returns (d_params, db)."""
+    A = make_op([p.detach() for p in params])
+    db, *_ = cg(A, dy, x0=x0, tol=tol, max_iters=max_iters, P=P)
+    return _param_vjp(make_op, params, soln, -db), db
+
+
+def slq_bwd(make_op, params, g, num_samples, key=None):
+    """slq.py:10-31: probes re-drawn from the key, solves = cg(A, probes, tol=1e-6, max_iters=100), dA = vjp(theta ->
+    A(theta) @ probes, g / num_samples * solves).  (As the reference notes, this assumes f = log.)"""
+    A = make_op([p.detach() for p in params])
+    key = sha_key(0) if key is None else key
+    probes = keyed_randn(A.shape[1], num_samples, dtype=A.dtype, key=key)
+    solves, *_ = cg(A, probes, tol=1e-6, max_iters=100)
+    return _param_vjp(make_op, params, probes, (1.0 / num_samples) * g * solves)

@@ -157,6 +157,22 @@ def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
         wnorm2.reshape(-1)[:b] += (W.double() ** 2).sum(0)
 
 
+def sddmm_csr(rowptr, colidx, n_rows, G, V, alpha, out):
+    counts = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
+    rows = torch.repeat_interleave(torch.arange(n_rows), counts)
+    out.copy_((alpha * (G.double()[rows] * V.double()[colidx.to(torch.int64)]).sum(1)).to(out.dtype))
+
+
+def row_dots(G, g_row0, V, v_row0, n, alpha, out):
+    out.copy_((alpha * (G.double()[g_row0:g_row0 + n] * V.double()[v_row0:v_row0 + n]).sum(1)).to(out.dtype))
+
+
+def gram_nt(G, g_off, Z, z_off, d_g, d_z, pre, post, alpha, C):
+    g = G.reshape(-1)[g_off:g_off + pre * d_g * post].reshape(pre, d_g, post).double()
+    z = Z.reshape(-1)[z_off:z_off + pre * d_z * post].reshape(pre, d_z, post).double()
+    C += alpha * torch.einsum("pat,pjt->aj", g, z)
+
+
 class _Fused:
     enabled = False
 
@@ -232,6 +248,7 @@ _WRAPPERS = dict(col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matma
                  mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
                  tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,
+                 sddmm_csr=sddmm_csr, row_dots=row_dots, gram_nt=gram_nt,
                  read_small=lambda t: t.detach().clone(),
                  small_ints=lambda values, device: torch.tensor([int(v) for v in values], dtype=torch.int32))      # cola_publish_bytes: a host copy of a few device bytes
 
