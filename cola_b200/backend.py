@@ -111,8 +111,8 @@ def require_cuda(t, what="operand"):
                            "run the call under torch.cuda.device(...) (cola_b200 launches on the current device)")
     # the kernels do not record autograd: returning a result without grad_fn would silently cut a training graph
     if getattr(t, "requires_grad", False) and torch.is_grad_enabled():
-        raise RuntimeError(f"{what} requires grad, but cola_b200's native API is not differentiable: detach it / use "
-                           "torch.no_grad(), or keep the reference's operators and call cola_b200.install(), under which "
+        raise RuntimeError(f"{what} requires grad, but a plain matmat of cola_b200's native API is not differentiable (solves through CG "
+                           "and the SLQ estimate are: cola_b200/autograd.py): detach it / use torch.no_grad(), or keep the reference's operators and call cola_b200.install(), under which "
                            "the reference's custom backward rules run with the solves on the kernels")
 
 

@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
   for (int c = 0; c < KMAX; ++c) dacc[c] = 0.0;
   for (int64_t row = grp; row < a.n_rows; row += n_grp) {
     const int32_t s = a.rowptr[row], e = a.rowptr[row + 1];
+    if (!EPI && a.accumulate && s == e) continue;   // a vertical strip without entries in this row: Y stays as it is
     T acc[KMAX];
 #pragma unroll
     for (int c = 0; c < KMAX; ++c) acc[c] = (T)0;

@@ -11,6 +11,7 @@ and executes it as one fused kernel per core operator K_t (shift / Diagonal / pA
 CUDA float32/float64 only; CPU tensors raise (there is no fallback path).
 """
 import copy
+import os
 import ctypes
 from functools import reduce
 from numbers import Number
@@ -684,13 +685,60 @@ class _DenseCore:
 
 
 class _CsrCore:
+    """CSR SpMM.  SpMV-shaped applications (k <= 4) of a matrix whose column indices have no locality (a random graph,
+    BASELINE config 5: every non-zero pulls a 32-byte DRAM sector for 8 useful bytes once the vector outgrows L2) run
+    COLUMN-BLOCKED: the pattern is cut once into vertical strips whose slice of X (SPMV_BLOCK_BYTES) stays resident in
+    L2, and the strips are applied one after the other, each accumulating into Y; the CSR arrays still stream through
+    once in total, Y is re-read per strip.  Row sums are then taken strip by strip (fp rounding order only)."""
+    SPMV_BLOCK_BYTES = int(os.environ.get("COLA_SPMV_BLOCK_MB", "32")) << 20
+
     def __init__(self, S):
         self.S = S
         self.shape = tuple(S.shape)
+        self._strips = {}
+
+    def _column_strips(self, k, itemsize):
+        """None (plain kernel), or [(indptr, indices, data, nnz)] per vertical strip, built on first use."""
+        key = (k, itemsize)
+        if key in self._strips:
+            return self._strips[key]
+        S = self.S
+        strips = None
+        x_bytes = S.shape[1] * k * itemsize
+        if self.SPMV_BLOCK_BYTES > 0 and x_bytes > 1.5 * self.SPMV_BLOCK_BYTES and S.nnz > 0:
+            rows = S.row_indices.to(torch.int64)
+            span = float((S.indices.to(torch.int64) - rows).abs().double().mean()) * k * itemsize
+            if span > self.SPMV_BLOCK_BYTES / 4:                # the gather window of a row does not fit L2 anyway
+                n_strips = -(-x_bytes // self.SPMV_BLOCK_BYTES)
+                width = -(-S.shape[1] // n_strips)
+                strip_of = torch.div(S.indices, width, rounding_mode="floor")
+                strips = []
+                for b in range(n_strips):
+                    idx = (strip_of == b).nonzero().reshape(-1)   # ascending: row-major order is kept
+                    counts = torch.bincount(rows[idx], minlength=S.shape[0])
+                    indptr = torch.zeros(S.shape[0] + 1, dtype=torch.int64, device=idx.device)
+                    indptr[1:] = torch.cumsum(counts, 0)
+                    strips.append((indptr.to(torch.int32).contiguous(), S.indices[idx].contiguous(), S.data[idx].contiguous(),
+                                   int(idx.numel())))
+                del strip_of
+            del rows
+        self._strips[key] = strips
+        return strips
 
     def apply(self, X, Y, epi):
         S = self.S
-        be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, S.max_row_nnz, X, Y, **epi.kw())
+        strips = self._column_strips(X.shape[1], X.element_size()) if X.shape[1] <= 4 else None
+        if strips is None:
+            return be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, S.max_row_nnz, X, Y, **epi.kw())
+        last = len(strips) - 1
+        for b, (indptr, indices, data, nnz) in enumerate(strips):
+            if b < last:       # partial row sums: Y = alpha * A_b X (+ Y)
+                be.csr_spmm(indptr, indices, data, S.shape, nnz, S.max_row_nnz, X, Y, alpha=epi.alpha,
+                            accumulate=epi.accumulate or b > 0, gate=epi.gate)
+            else:              # the last strip carries the epilogue: shift / diag / dots act on the complete row sum
+                kw = epi.kw()
+                kw["accumulate"] = epi.accumulate or b > 0
+                be.csr_spmm(indptr, indices, data, S.shape, nnz, S.max_row_nnz, X, Y, **kw)
 
 
 class _KronCore:

@@ -84,11 +84,11 @@ class SparseOp(Op):
         super().__init__(shape, data.dtype)
         order = torch.argsort(rows, stable=True)
         self.data, rows, cols = data[order], rows[order], cols[order]
-        csr = coo_array((self.data.numpy(), (rows.numpy(), cols.numpy())), shape=shape).tocsr()
+        csr = coo_array((self.data.detach().numpy(), (rows.numpy(), cols.numpy())), shape=shape).tocsr()
         self.indptr = torch.tensor(csr.indptr, dtype=torch.int32)
         self.indices = torch.tensor(csr.indices, dtype=torch.int32)
         self.csr = torch.sparse_csr_tensor(crow_indices=self.indptr, col_indices=self.indices,
-                                           values=self.data, size=shape)
+                                           values=self.data.detach(), size=shape)
 
     def matmat(self, X):
         return self.csr @ X

@@ -269,3 +269,52 @@ def test_pinv_normal_equations(cb):
     assert rel(x, torch.linalg.lstsq(M, B).solution) < 1e-8
     assert rel(M.T @ (M @ x), M.T @ B) < 1e-9                    # normal equations
     assert float(L.eigmin(cb.PSD(ops.Dense((M.T @ M).contiguous())), L.Lanczos(max_iters=40, tol=1e-12))) > 0
+
+
+def test_spmv_column_strips(cb, monkeypatch):
+    """SpMV-shaped applications of a pattern without locality run column-blocked (ops._CsrCore: vertical strips whose
+    slice of X stays in L2, BASELINE config 5).  Forced here by a small strip size: same result as the plain kernel
+    and as a dense fp64 product, with the fused epilogue (shift, Diagonal, <x, y> dots), inside a Sum (accumulate)
+    and through a Lanczos run."""
+    ops = cb.ops
+    g = torch.Generator().manual_seed(5)
+    n = 3000
+    for dt, tol in [(torch.float64, 1e-13), (torch.float32, 2e-6)]:
+        rows = torch.randint(0, n, (12 * n, ), generator=g)
+        cols = torch.randint(0, n, (12 * n, ), generator=g)
+        key = torch.unique(torch.cat([rows * n + cols, cols * n + rows, torch.arange(n) * (n + 1)]))
+        rows, cols = key // n, key % n
+        vals = torch.randn(rows.numel(), dtype=dt, generator=g)
+        vals = torch.where(rows == cols, torch.full_like(vals, 30.0), 0.5 * (vals + torch.zeros_like(vals)))
+        Ad = torch.zeros(n, n, dtype=torch.float64)
+        Ad[rows, cols] = vals.double()
+        Ad = 0.5 * (Ad + Ad.T)
+        vals = Ad[rows, cols].to(dt)
+        dg = torch.rand(n, dtype=dt, generator=g)
+        D2 = torch.randn(n, n, dtype=dt, generator=g) / n
+        for k in (1, 2, 4):
+            X = torch.randn(n, k, dtype=dt, generator=g).to(DEV)
+            outs = []
+            for strip_bytes in (1 << 40, 4096):
+                monkeypatch.setattr(ops._CsrCore, "SPMV_BLOCK_BYTES", strip_bytes)
+                S = ops.Sparse(vals.to(DEV), rows.to(DEV), cols.to(DEV), (n, n))
+                A = ops.Dense(D2.to(DEV)) + S + 0.25 * ops.I_like(S) + ops.Diagonal(dg.to(DEV))
+                core = A.plan().terms[-1][1][0]
+                Y = torch.empty_like(X)
+                dots = torch.zeros(k, dtype=torch.float64, device=DEV)
+                A.matmat_into(X, Y, dots=dots)
+                assert (core._column_strips(k, X.element_size()) is not None) == (strip_bytes == 4096)
+                ref = (D2.double() + Ad + torch.diag(0.25 + dg.double())) @ X.double().cpu()
+                assert rel(Y, ref) < tol, (dt, k, strip_bytes, rel(Y, ref))
+                assert rel(dots, (X.double().cpu() * ref).sum(0)) < tol
+                outs.append(Y)
+            assert rel(outs[0], outs[1]) < tol
+    # a Lanczos run on the strips: same Ritz values as on the plain kernel
+    evs = []
+    for strip_bytes in (1 << 40, 4096):
+        monkeypatch.setattr(ops._CsrCore, "SPMV_BLOCK_BYTES", strip_bytes)
+        S = cb.SelfAdjoint(ops.Sparse(vals.double().to(DEV), rows.to(DEV), cols.to(DEV), (n, n)))
+        ev, _ = cb.linalg.eig(S, 4, "LM", cb.linalg.Lanczos(max_iters=40, tol=1e-12, key=3))
+        evs.append(ev)
+    assert rel(evs[0], evs[1]) < 1e-10
+

@@ -194,6 +194,10 @@ def test_plan_follows_in_place_parameter_updates(emu):
     assert torch.allclose(T.beta[0, 0], ((X[:, 0] + d) @ (A.to_dense() @ (X[:, 0] + d))) / ((X[:, 0] + d) @ (X[:, 0] + d)))
 
 
+def test_spmv_column_strips(emu, monkeypatch):
+    gn.test_spmv_column_strips(emu, monkeypatch)
+
+
 def test_native_api_refuses_parameters_that_require_grad(emu):
     """The kernels do not record autograd: a leaf that requires grad raises while recording is on (instead of handing
     back a result without grad_fn), and is accepted under torch.no_grad()."""
