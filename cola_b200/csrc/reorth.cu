@@ -25,6 +25,7 @@ struct RoArgs {
   const T* V; int64_t vstride, j0, j1; const T* Wc; T* W; int64_t n, b;
   double* C; const double* Cc; T sign; double* wnorm2; const int32_t* gate;
   int lanes_per_row, rows_per_chunk, vec_path;
+  int fold;   // reorth_dots on a single column viewed as (n / fold, fold): the fold partial columns add into C[j]
 };
 
 // accumulate type: fp32 partials over one chunk (<= rows_per_chunk terms per lane) are promoted to fp64
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kDotsThreads) reorth_dots_kernel(RoArgs<T> a) 
   __syncthreads();
   for (int64_t i = tid; i < nj * b; i += kDotsThreads) {
     double s = csm[i];
-    if (s != 0.0) atomicAdd(a.C + a.j0 * b + i, s);
+    if (s != 0.0) atomicAdd(a.fold ? (a.C + a.j0 + i / b) : (a.C + a.j0 * b + i), s);
   }
 }
 
@@ -446,6 +447,15 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
   COLA_REQUIRE(j1 >= j0 && j0 >= 0, "reorth_dots: bad vector range");
   if (j1 == j0 || n <= 0 || b <= 0) return COLA_OK;
   const int maxv = 16 / (int)sizeof(T);
+  // A single column (one Lanczos start vector, BASELINE config 5) is contiguous: it is swept as an (n / maxv, maxv)
+  // block with 16-byte loads, the maxv partial columns folding into the one coefficient (4.3 -> see DESIGN.md TB/s).
+  int fold = 0;
+  if (b == 1 && n % maxv == 0 && vstride % maxv == 0 && ((uintptr_t)V % 16 == 0) && ((uintptr_t)W % 16 == 0) &&
+      getenv("COLA_REORTH_NO_FOLD") == nullptr) {
+    fold = maxv;
+    n /= maxv;
+    b = maxv;
+  }
   // vector path: b*sizeof(T) a multiple of 16 B and rows 16 B aligned
   int vec = 1;
   {
@@ -476,7 +486,7 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
     int64_t jb = ja + max_nj < j1 ? ja + max_nj : j1;
     RoArgs<T> a{};
     a.V = V; a.vstride = vstride; a.j0 = ja; a.j1 = jb; a.Wc = W; a.n = n; a.b = b; a.C = C; a.gate = gate;
-    a.lanes_per_row = Lr; a.rows_per_chunk = (int)w_rows;
+    a.lanes_per_row = Lr; a.rows_per_chunk = (int)w_rows; a.fold = fold;
     size_t smem = (size_t)((jb - ja) * b * 8 + w_bytes);
     int64_t n_chunks = (n + w_rows - 1) / w_rows;
     int per_sm = (int)(budget / (int64_t)smem);

@@ -1,6 +1,6 @@
 from .algorithm_base import Algorithm, Auto, IterativeOperatorWInfo
 from .arnoldi import arnoldi, arnoldi_eigs, arnoldi_fact
-from .cg import CG, cg, run_batched_cg
+from .cg import CG, cg, release_cg_workspace, run_batched_cg
 from .dispatch import (LSTSQ, LU, Arnoldi, Cholesky, Eigh, Exact, Lanczos, TriangularInv, apply_unary, diag, eig, eigmax,
                        eigmin, pinv, exact_diag, exp, get_slice,
                        inv, isqrt, log, logdet, pow, slogdet, solve, sqrt, trace)

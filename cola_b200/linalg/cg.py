@@ -178,7 +178,9 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
     if graph_ok:
         key = (n, k, dt, max_iters, str(dev))
         cached = A.__dict__.get("_cg_workspace")
-        if cached is not None and cached["key"] == key:
+        if cached is not None and cached.get("busy"):
+            graph_ok = False                                     # in use by a concurrent solve: fresh state, eager loop
+        elif cached is not None and cached["key"] == key:
             ws = cached
         else:
             ws = {"key": key, "graph": None,
@@ -189,106 +191,123 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
                   "ctl": torch.empty(4, dtype=torch.int32, device=dev)}
             A.__dict__["_cg_workspace"] = ws
 
-    # ---- setup: normalise RHS, residual, gamma0, tolerances (cg.py:96-101, 122-130)
-    mult_sq = torch.zeros(k, dtype=torch.float64, device=dev)
-    be.col_dots(b, b, mult_sq)
-    r = ws["r"] if ws else torch.empty_like(b)
-    be.col_scale(b, r, mult_sq, take_sqrt=True, mode=1)          # b / ||b|| (safe)
-    x = ws["x"] if ws else torch.empty_like(b)
-    if x0 is None:
-        x.zero_()
-    else:
-        x.copy_(x0.to(dt))
-        ax = torch.empty_like(b)
-        A.matmat_into(x, ax)
-        be.axpby(ax, r, -1.0, 1.0)                               # r0 = b - A x0
-        del ax
-    if ws:
-        p, ap, gamma, pap, tol_eff, ctl = ws["p"], ws["ap"], ws["gamma"], ws["pap"], ws["tol_eff"], ws["ctl"]
-        p.copy_(r)
-        gamma.zero_()
-        pap.zero_()
-        ctl.copy_(be.small_ints([0, 0, max_iters, k], dev))
-    else:
-        p = r.clone()
-        ap = torch.empty_like(b)
-        gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)
-        pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
-        tol_eff = torch.empty(k, dtype=dt, device=dev)
-        ctl = be.small_ints([0, 0, max_iters, k], dev)
-    be.col_dots(r, r, gamma[0])
-    lib.call(f"cola_cg_tol_{sx}", be.ptr(gamma), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
-    it_ptr, done_ptr = ctl[0:1], ctl[1:2]
-    lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 0, st())   # initial cond_fun
+    def _solve():
+        # ---- setup: normalise RHS, residual, gamma0, tolerances (cg.py:96-101, 122-130)
+        mult_sq = torch.zeros(k, dtype=torch.float64, device=dev)
+        be.col_dots(b, b, mult_sq)
+        r = ws["r"] if ws else torch.empty_like(b)
+        be.col_scale(b, r, mult_sq, take_sqrt=True, mode=1)          # b / ||b|| (safe)
+        x = ws["x"] if ws else torch.empty_like(b)
+        if x0 is None:
+            x.zero_()
+        else:
+            x.copy_(x0.to(dt))
+            ax = torch.empty_like(b)
+            A.matmat_into(x, ax)
+            be.axpby(ax, r, -1.0, 1.0)                               # r0 = b - A x0
+            del ax
+        if ws:
+            p, ap, gamma, pap, tol_eff, ctl = ws["p"], ws["ap"], ws["gamma"], ws["pap"], ws["tol_eff"], ws["ctl"]
+            p.copy_(r)
+            gamma.zero_()
+            pap.zero_()
+            ctl.copy_(be.small_ints([0, 0, max_iters, k], dev))
+        else:
+            p = r.clone()
+            ap = torch.empty_like(b)
+            gamma = torch.zeros((max_iters + 2, k), dtype=torch.float64, device=dev)
+            pap = torch.zeros((max_iters + 1, k), dtype=torch.float64, device=dev)
+            tol_eff = torch.empty(k, dtype=dt, device=dev)
+            ctl = be.small_ints([0, 0, max_iters, k], dev)
+        be.col_dots(r, r, gamma[0])
+        lib.call(f"cola_cg_tol_{sx}", be.ptr(gamma), be.scalar(dt, tol), be.ptr(tol_eff), k, st())
+        it_ptr, done_ptr = ctl[0:1], ctl[1:2]
+        lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 0, st())   # initial cond_fun
 
-    def enqueue(n_iters):
-        for _ in range(n_iters):
-            A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)
-            lib.call(f"cola_cg_update_r_{sx}", be.ptr(r), be.ptr(ap), n, k, k, be.ptr(ctl), be.ptr(gamma),
-                     be.ptr(pap), be.ptr(gamma), st())
-            lib.call(f"cola_cg_update_xp_{sx}", be.ptr(x), be.ptr(r), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma),
-                     be.ptr(pap), st())
-            lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
+        def enqueue(n_iters):
+            for _ in range(n_iters):
+                A.matmat_into(p, ap, dots=pap, dots_row=it_ptr, gate=done_ptr)
+                lib.call(f"cola_cg_update_r_{sx}", be.ptr(r), be.ptr(ap), n, k, k, be.ptr(ctl), be.ptr(gamma),
+                         be.ptr(pap), be.ptr(gamma), st())
+                lib.call(f"cola_cg_update_xp_{sx}", be.ptr(x), be.ptr(r), be.ptr(p), n, k, k, be.ptr(ctl), be.ptr(gamma),
+                         be.ptr(pap), st())
+                lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma), be.ptr(tol_eff), 1, st())
 
-    t0 = time.time()
-    if ws and ws["graph"] is not None and ws.get("token") != A.plan().graph_token():
-        ws["graph"] = None                                       # the operator's scratch buffers moved: recapture
-    loop = {"graph": ws["graph"] if ws else None, "batches": 0}
+        t0 = time.time()
+        if ws and ws["graph"] is not None and ws.get("token") != A.plan().graph_token():
+            ws["graph"] = None                                       # the operator's scratch buffers moved: recapture
+        loop = {"graph": ws["graph"] if ws else None, "batches": 0}
 
-    def drive(limit):
-        """Enqueue gated batches until the device-side rule (or the iteration cap `limit`) stops the loop."""
-        while True:
-            c = be.read_small(ctl)
-            it, done = int(c[0]), int(c[1])
-            if done:
-                return it
-            remaining = limit - it
-            if graph_ok and loop["graph"] is None and loop["batches"] >= 1 and remaining >= 2 * CHECK_EVERY:
-                # Every kernel reads the iteration index and the stop flag from the device control block, so a batch
-                # of iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
-                # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
-                graph = torch.cuda.CUDAGraph()
-                # No garbage collection while the stream is capturing: a cyclic collection can finalise another
-                # operator's cached CUDAGraph (cudaGraphExecDestroy / cudaFree), which invalidates the capture in
-                # progress (seen as cudaErrorStreamCaptureInvalidated, depending on test order).  torch.cuda.graph()
-                # itself runs gc.collect() just before capture begins.
-                gc_on = gc.isenabled()
-                gc.disable()
-                try:
-                    with torch.cuda.graph(graph):
-                        enqueue(CHECK_EVERY)
-                finally:
-                    if gc_on:
-                        gc.enable()
-                loop["graph"] = graph
-                ws["graph"], ws["token"] = graph, A.plan().graph_token()
-                # capture does not execute: fall through to the replay below
-            if loop["graph"] is not None:
-                loop["graph"].replay()
-            else:
-                enqueue(min(CHECK_EVERY, remaining))
-            loop["batches"] += 1
+        def drive(limit):
+            """Enqueue gated batches until the device-side rule (or the iteration cap `limit`) stops the loop."""
+            while True:
+                c = be.read_small(ctl)
+                it, done = int(c[0]), int(c[1])
+                if done:
+                    return it
+                remaining = limit - it
+                if graph_ok and loop["graph"] is None and loop["batches"] >= 1 and remaining >= 2 * CHECK_EVERY:
+                    # Every kernel reads the iteration index and the stop flag from the device control block, so a batch
+                    # of iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
+                    # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
+                    graph = torch.cuda.CUDAGraph()
+                    # No garbage collection while the stream is capturing: a cyclic collection can finalise another
+                    # operator's cached CUDAGraph (cudaGraphExecDestroy / cudaFree), which invalidates the capture in
+                    # progress (seen as cudaErrorStreamCaptureInvalidated, depending on test order).  torch.cuda.graph()
+                    # itself runs gc.collect() just before capture begins.
+                    gc_on = gc.isenabled()
+                    gc.disable()
+                    try:
+                        with torch.cuda.graph(graph):
+                            enqueue(CHECK_EVERY)
+                    finally:
+                        if gc_on:
+                            gc.enable()
+                    loop["graph"] = graph
+                    ws["graph"], ws["token"] = graph, A.plan().graph_token()
+                    # capture does not execute: fall through to the replay below
+                if loop["graph"] is not None:
+                    loop["graph"].replay()
+                else:
+                    enqueue(min(CHECK_EVERY, remaining))
+                loop["batches"] += 1
 
-    it = drive(max_iters)
-    group = STOP_RULE_GROUP if _world(STOP_RULE_GROUP) > 1 else None
-    if group is not None:
-        it = _global_stop_rule(group, it, drive, lambda: lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma),
-                                                                    be.ptr(tol_eff), 0, st()), ctl, tol_eff, max_iters)
-    elapsed = time.time() - t0
+        it = drive(max_iters)
+        group = STOP_RULE_GROUP if _world(STOP_RULE_GROUP) > 1 else None
+        if group is not None:
+            it = _global_stop_rule(group, it, drive, lambda: lib.call(f"cola_cg_advance_{sx}", be.ptr(ctl), be.ptr(gamma),
+                                                                        be.ptr(tol_eff), 0, st()), ctl, tol_eff, max_iters)
+        elapsed = time.time() - t0
 
-    # ---- info dict exactly as while_loop_winfo builds it (torch_tqdm.py:35-62): the tracked error is sampled
-    # before every cond evaluation (it+1 of them) and once more after the loop; the first two are dropped.
-    col_norms = torch.sqrt(gamma[:it + 1])
-    trace = be.read_small(col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).numpy()
-    samples = np.concatenate([trace, trace[-1:]])
-    info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
-    if ws:                                                       # hand back copies: the workspace is reused
-        x_out, r_out = torch.empty_like(x), torch.empty_like(r)
-    else:
-        x_out, r_out = x, r
-    be.col_scale(x, x_out, mult_sq, take_sqrt=True, mode=0)      # x * ||b||  (cg.py:119)
-    be.col_scale(r, r_out, mult_sq, take_sqrt=True, mode=0)
-    return x_out, r_out, it, info
+        # ---- info dict exactly as while_loop_winfo builds it (torch_tqdm.py:35-62): the tracked error is sampled
+        # before every cond evaluation (it+1 of them) and once more after the loop; the first two are dropped.
+        col_norms = torch.sqrt(gamma[:it + 1])
+        trace = be.read_small(col_norms.mean(dim=1) if group is None else _global_error_trace(group, col_norms)).numpy()
+        samples = np.concatenate([trace, trace[-1:]])
+        info = {"iterations": it + 1, "errors": samples[2:].astype(np.float64), "iteration_time": elapsed / (it + 1)}
+        if ws:                                                       # hand back copies: the workspace is reused
+            x_out, r_out = torch.empty_like(x), torch.empty_like(r)
+        else:
+            x_out, r_out = x, r
+        be.col_scale(x, x_out, mult_sq, take_sqrt=True, mode=0)      # x * ||b||  (cg.py:119)
+        be.col_scale(r, r_out, mult_sq, take_sqrt=True, mode=0)
+        return x_out, r_out, it, info
+
+    # A workspace in use (a second solve on the same operator from another thread / stream) is never shared: that solve
+    # takes fresh buffers and the eager loop (ADVICE r1).  `release_cg_workspace(A)` frees the cached one.
+    if ws is not None:
+        ws["busy"] = True
+    try:
+        return _solve()
+    finally:
+        if ws is not None:
+            ws["busy"] = False
+
+
+def release_cg_workspace(A):
+    """Drops the solve state and the captured CUDA graph a graph-eligible solve leaves on the operator (four (n, k)
+    blocks, two fp64 traces, the graph): call it when no further solve of that shape is coming."""
+    A.__dict__.pop("_cg_workspace", None)
 
 
 def _run_batched_pcg(A, b, x0, max_iters, tol, P, pbar=False):

@@ -62,6 +62,34 @@ def probe_chunk(n, m, dtype, device, requested=None):
     return b
 
 
+def lanczos_chunks_lockstep(A, blocks, max_iters, tol, pbar, process, group=None):
+    """lanczos_fact over column chunks with the iteration count of the reference's ONE batched factorisation.
+    Its stop rule is an any() over all columns (lanczos.py:256-268), so the batch runs as long as its slowest
+    column needs; a chunk on its own may stop earlier and would hand back a smaller T.  First pass: every chunk with
+    the rule on.  Chunks that stopped before the longest one are redone with the rule off (tol = -1) and exactly
+    that many steps.  `blocks` are callables returning an (n, b) block, `process(i, state)` the per-chunk result.
+    With max_iters binding (the usual SLQ / f(A)v setting) there is no second pass.  With `group` (probe columns
+    sharded over ranks) the longest count is agreed on with one MAX all-reduce."""
+    results, iters = [], []
+    for i, get in enumerate(blocks):
+        st = lanczos_fact(A, get(), max_iters=max_iters, tol=tol, pbar=pbar)
+        iters.append(st.iters)
+        results.append(process(i, st))
+        del st
+    longest = max(iters) if iters else 0
+    if group is not None:
+        import torch.distributed as dist
+        agreed = torch.tensor([longest], dtype=torch.int64, device=A.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MAX, group=group)
+        longest = int(agreed[0])
+    for i, get in enumerate(blocks):
+        if iters[i] < longest:
+            st = lanczos_fact(A, get(), max_iters=longest, tol=-1.0, pbar=pbar)
+            results[i] = process(i, st)
+            del st
+    return results
+
+
 class LanczosUnary(LinearOperator):
     """cola/linalg/unary/unary.py:37-60"""
     def __init__(self, A: LinearOperator, f: Callable, **kwargs):
@@ -80,9 +108,13 @@ class LanczosUnary(LinearOperator):
         n, k = V.shape
         out = torch.empty_like(V)
         cb = probe_chunk(n, max_iters, self.dtype, V.device, kw.pop("probe_chunk", None))
-        for c0, c1 in friendly_chunks(k, cb, self.dtype):
+        chunks = friendly_chunks(k, cb, self.dtype)
+        tol, pbar = kw.pop("tol", 1e-7), kw.pop("pbar", False)
+        assert not kw, f"unexpected Lanczos arguments {sorted(kw)}"
+
+        def process(i, st):
+            c0, c1 = chunks[i]
             blk = V[:, c0:c1].contiguous()
-            st = lanczos_fact(self.A, blk, max_iters=max_iters, **kw)
             self.info.update(st.info)
             T = _tridiag_dense(st)
             eigvals, P = torch.linalg.eigh(T)                  # (b, iters, iters): tiny, library call
@@ -99,7 +131,9 @@ class LanczosUnary(LinearOperator):
             w = torch.zeros_like(blk)
             be.reorth_update(st.V, 1, st.iters + 1, w, C, sign=1.0)
             out[:, c0:c1] = w
-            del st
+
+        lanczos_chunks_lockstep(self.A, [lambda c=c: V[:, c[0]:c[1]].contiguous() for c in chunks], max_iters, tol, pbar,
+                                process)
         return out
 
 
@@ -196,7 +230,10 @@ def _tridiag_eig_first_row(st):
 
 def slq_per_probe(A, fun, Z, max_iters, tol, pbar=False):
     """n * sum_j tau_j^2 f(lambda_j) for every probe column of Z (n, b)  (slq.py:42-51)."""
-    st = lanczos_fact(A, Z, max_iters, tol, pbar)
+    return _quadrature(A, fun, lanczos_fact(A, Z, max_iters, tol, pbar))
+
+
+def _quadrature(A, fun, st):
     eps = torch.finfo(A.dtype).eps
     if USE_TRIDIAG_QL:
         eigvals, tau = _tridiag_eig_first_row(st)
@@ -234,9 +271,10 @@ def _slq_fwd(A, fun, num_samples, max_iters, tol, pbar, key, probe_chunk_size=No
         probes = DeferredProbes(n, num_samples, A.dtype, A.device, key)
     cb = probe_chunk(n, max_iters, A.dtype, A.device, probe_chunk_size)
     total = torch.zeros(2, dtype=torch.float64, device=A.device)
-    for c0, c1 in friendly_chunks(hi - lo, cb, A.dtype, start=lo):
-        Z = probes.columns(c0, c1)
-        est = slq_per_probe(A, fun, Z, max_iters, tol, pbar)
+    chunks = friendly_chunks(hi - lo, cb, A.dtype, start=lo)
+    ests = lanczos_chunks_lockstep(A, [lambda c=c: probes.columns(c[0], c[1]) for c in chunks], max_iters, tol, pbar,
+                                   lambda i, st: _quadrature(A, fun, st), group=group)
+    for est in ests:
         total[0] += est.to(torch.float64).sum()
         total[1] += est.numel()
     if group is not None:

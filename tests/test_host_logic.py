@@ -194,6 +194,24 @@ def test_plan_follows_in_place_parameter_updates(emu):
     assert torch.allclose(T.beta[0, 0], ((X[:, 0] + d) @ (A.to_dense() @ (X[:, 0] + d))) / ((X[:, 0] + d) @ (X[:, 0] + d)))
 
 
+def test_lanczos_chunks_run_in_lockstep(emu):
+    """LanczosUnary / SLQ split wide probe blocks into chunks (HBM budget).  The reference's single batched Lanczos
+    stops when ALL columns satisfy the rule (lanczos.py:256-268), so every chunk must take the longest chunk's
+    iteration count: here the last chunk's columns live in a 2-dimensional invariant subspace and would stop
+    after 3 steps on their own."""
+    ops = emu.ops
+    d = torch.tensor([1.0, 2.0] * 3 + [3.0, 4.0, 5.0, 6.0, 7.0, 8.0], dtype=torch.float64)
+    A = emu.SelfAdjoint(ops.Diagonal(d))
+    g = torch.Generator().manual_seed(0)
+    V = torch.randn(12, 8, dtype=torch.float64, generator=g)
+    V[6:, 4:] = 0.0                                            # columns 4-7: only the eigenvalues 1 and 2
+    one = emu.linalg.LanczosUnary(A, torch.exp, max_iters=10, tol=1e-7, probe_chunk=8)
+    two = emu.linalg.LanczosUnary(A, torch.exp, max_iters=10, tol=1e-7, probe_chunk=4)
+    Y1, Y2 = one @ V, two @ V
+    assert one.info["iterations"] == two.info["iterations"] > 4
+    assert gp.rel(Y1, Y2) < 1e-12 and gp.rel(Y1, torch.exp(d)[:, None] * V) < 1e-6
+
+
 def test_spmv_column_strips(emu, monkeypatch):
     gn.test_spmv_column_strips(emu, monkeypatch)
 

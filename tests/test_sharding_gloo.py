@@ -30,7 +30,9 @@ def _worker(rank, world, port, results):
         def __matmul__(self, Z):
             return ko.lanczos_unary_matmat(Ao, torch.log, Z, 20, 1e-12)[0]
 
-    stochastic.slq_per_probe = lambda A, f, Z, m, tol, pbar=False: ko.slq_per_probe(Ao, f, Z, m, tol)
+    # the per-chunk factorisation + quadrature (lanczos_fact on the kernels) stated with the oracle
+    stochastic.lanczos_chunks_lockstep = (lambda A, blocks, m, tol, pbar, process, group=None:
+                                          [ko.slq_per_probe(Ao, torch.log, get(), m, tol) for get in blocks])
     key = cb.rng.PRNGKey(42)
     num = max(int(1 / 0.2**2), 1)   # 24: same rounding as stochastic_lanczos_quad (slq.py:74)
     val = stochastic.slq_fwd(Stub(), torch.log, num_samples=num, max_iters=20, tol=1e-12, pbar=False, key=key,
