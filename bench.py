@@ -418,6 +418,9 @@ def _timed(fn):
     return e0.elapsed_time(e1) * 1e-3, out
 
 
+TF32_PEAK_TFLOPS = 1166.0   # 128*256*8 MAC / 130.8 cycles * 2 * 148 SMs * 1.965 GHz (profiles/r2_umma_rate.log)
+
+
 def secondary_cfg3(ctx, cb, iters=100, reps=10):
     """BASELINE config 3 (every rank its own 128-RHS block; rank 0 reports its own rate x world = weak scaling)."""
     dev = ctx.dev
@@ -454,7 +457,10 @@ def secondary_cfg3(ctx, cb, iters=100, reps=10):
                          "unit": "GB/s", "frac": by * iters * reps / s * 1e-9 / peak,
                          "matmat": {"ms": mm_ms, "algorithmic_bytes": mm_by, "GBps": mm_by / mm_ms * 1e-6,
                                     "frac_hbm": mm_by / mm_ms * 1e-6 / peak, "fp32_equiv_TFLOPs": mm_flop / mm_ms * 1e-9,
-                                    "tf32_mma_TFLOPs_issued": 3 * mm_flop / mm_ms * 1e-9}},
+                                    "tf32_mma_TFLOPs_issued": 3 * mm_flop / mm_ms * 1e-9,
+                                    "tf32_peak_TFLOPs": TF32_PEAK_TFLOPS, "frac_tensor": 3 * mm_flop / mm_ms * 1e-9 / TF32_PEAK_TFLOPS,
+                                    "tf32_peak_source": "measured on this pool: scripts/umma_rate.cu, tcgen05.mma kind::tf32 "
+                                                        "128x256x8 at 130.8 cycles per SM (profiles/r2_umma_rate.log)"}},
             "final_mean_rel_residual": r_true, "recurrence_residual": float(info["errors"][-1]),
             "clocks": clocks.summary(), "gpu_launches": int(launches)}
 

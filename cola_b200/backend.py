@@ -203,11 +203,11 @@ def diag_matmat(X, Y, shift, diag, accumulate, dots=None, dots_row=None, gate=No
 
 
 def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False, dots=None,
-             dots_row=None, gate=None):
+             dots_row=None, gate=None, far_diagonal=0):
     k = X.shape[1]
     dt = vals.dtype
     lib().call(f"cola_csr_spmm_{sfx(dt)}", ptr(rowptr, torch.int32), ptr(colidx, torch.int32), ptr(vals), shape[0],
-               shape[1], nnz, max_row_nnz, ptr(X, dt), k, k, ptr(Y, dt), k, scalar(dt, alpha), scalar(dt, shift),
+               shape[1], nnz, max_row_nnz, int(far_diagonal), ptr(X, dt), k, k, ptr(Y, dt), k, scalar(dt, alpha), scalar(dt, shift),
                ptr(diag, dt) if diag is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
                stream_ptr())
 
@@ -289,13 +289,15 @@ def sddmm_csr(rowptr, colidx, n_rows, G, V, alpha, out):
                ptr(V, dt), k, k, scalar(dt, alpha), ptr(out, dt), 0, stream_ptr())
 
 
-def row_dots(G, g_row0, V, v_row0, n, alpha, out):
-    """out[i] = alpha * <G[g_row0 + i, :], V[v_row0 + i, :]>, i < n; G, V (rows, k) contiguous."""
+def row_dots(G, g_row0, V, v_row0, n, alpha, out, out_sq=None, accumulate=False):
+    """out[i] (+)= alpha * <G[g_row0 + i, :], V[v_row0 + i, :]>, i < n; G, V (rows, k) contiguous.  With out_sq also
+    out_sq[i] (+)= sum_c (G[.., c] V[.., c])^2."""
     k = V.shape[1]
     dt = V.dtype
     if n > 0:
         lib().call(f"cola_row_dots_{sfx(dt)}", off_ptr(G, g_row0 * k), k, off_ptr(V, v_row0 * k), k, n, k,
-                   scalar(dt, alpha), ptr(out, dt), 0, stream_ptr())
+                   scalar(dt, alpha), ptr(out, dt), ptr(out_sq, dt) if out_sq is not None else None, int(accumulate),
+                   stream_ptr())
 
 
 def gram_nt(G, g_off, Z, z_off, d_g, d_z, pre, post, alpha, C):

@@ -40,20 +40,31 @@ __global__ void __launch_bounds__(256)
 template <typename T, int LPR>
 __global__ void __launch_bounds__(256)
     row_dots_kernel(const T* __restrict__ G, int64_t ldg_, const T* __restrict__ V, int64_t ldv, int64_t n, int64_t k,
-                    T alpha, T* __restrict__ out, int accumulate) {
+                    T alpha, T* __restrict__ out, T* __restrict__ out_sq, int accumulate) {
   const int sub = threadIdx.x % LPR;
   const int64_t r0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPR;
   const int64_t stride = ((int64_t)gridDim.x * blockDim.x) / LPR;
   for (int64_t row = r0; row < n; row += stride) {
     const T* __restrict__ g = G + row * ldg_;
     const T* __restrict__ v = V + row * ldv;
-    double acc = 0.0;
-    for (int64_t c = sub; c < k; c += LPR) acc += (double)g[c] * (double)v[c];
+    double acc = 0.0, acc2 = 0.0;
+    for (int64_t c = sub; c < k; c += LPR) {
+      const double pr = (double)g[c] * (double)v[c];
+      acc += pr;
+      acc2 += pr * pr;
+    }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+    }
     if (sub == 0) {
       const T r = alpha * (T)acc;
       out[row] = accumulate ? out[row] + r : r;
+      if (out_sq != nullptr) {
+        const T r2 = (T)acc2;
+        out_sq[row] = accumulate ? out_sq[row] + r2 : r2;
+      }
     }
   }
 }
@@ -128,7 +139,7 @@ static int sddmm_launch(const int32_t* rowptr, const int32_t* colidx, int64_t n_
 
 template <typename T>
 static int row_dots_launch(const T* G, int64_t ldg_, const T* V, int64_t ldv, int64_t n, int64_t k, T alpha, T* out,
-                           int accumulate, void* stream) {
+                           T* out_sq, int accumulate, void* stream) {
   COLA_REQUIRE(G && V && out, "row_dots: null pointer");
   COLA_REQUIRE(n >= 0 && k >= 1 && ldg_ >= k && ldv >= k, "row_dots: bad shape");
   if (n == 0) return COLA_OK;
@@ -139,12 +150,12 @@ static int row_dots_launch(const T* G, int64_t ldg_, const T* V, int64_t ldv, in
   const int64_t cap = (int64_t)sm_count() * 16;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   switch (lpr) {
-    case 1: row_dots_kernel<T, 1><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, accumulate); break;
-    case 2: row_dots_kernel<T, 2><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, accumulate); break;
-    case 4: row_dots_kernel<T, 4><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, accumulate); break;
-    case 8: row_dots_kernel<T, 8><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, accumulate); break;
-    case 16: row_dots_kernel<T, 16><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, accumulate); break;
-    default: row_dots_kernel<T, 32><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, accumulate); break;
+    case 1: row_dots_kernel<T, 1><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, out_sq, accumulate); break;
+    case 2: row_dots_kernel<T, 2><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, out_sq, accumulate); break;
+    case 4: row_dots_kernel<T, 4><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, out_sq, accumulate); break;
+    case 8: row_dots_kernel<T, 8><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, out_sq, accumulate); break;
+    case 16: row_dots_kernel<T, 16><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, out_sq, accumulate); break;
+    default: row_dots_kernel<T, 32><<<grid, 256, 0, st>>>(G, ldg_, V, ldv, n, k, alpha, out, out_sq, accumulate); break;
   }
   return cuda_status("row_dots");
 }
@@ -187,12 +198,12 @@ int cola_sddmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, int64_t n_r
   return sddmm_launch<double>(rowptr, colidx, n_rows, G, ldg, V, ldv, k, alpha, out_vals, accumulate, stream);
 }
 int cola_row_dots_f32(const float* G, int64_t ldg, const float* V, int64_t ldv, int64_t n, int64_t k, float alpha, float* out,
-                      int accumulate, void* stream) {
-  return row_dots_launch<float>(G, ldg, V, ldv, n, k, alpha, out, accumulate, stream);
+                      float* out_sq, int accumulate, void* stream) {
+  return row_dots_launch<float>(G, ldg, V, ldv, n, k, alpha, out, out_sq, accumulate, stream);
 }
 int cola_row_dots_f64(const double* G, int64_t ldg, const double* V, int64_t ldv, int64_t n, int64_t k, double alpha,
-                      double* out, int accumulate, void* stream) {
-  return row_dots_launch<double>(G, ldg, V, ldv, n, k, alpha, out, accumulate, stream);
+                      double* out, double* out_sq, int accumulate, void* stream) {
+  return row_dots_launch<double>(G, ldg, V, ldv, n, k, alpha, out, out_sq, accumulate, stream);
 }
 int cola_gram_nt_f32(const float* G, const float* Z, int64_t d_g, int64_t d_z, int64_t pre, int64_t post, double alpha,
                      double* C, int64_t ldc, void* stream) {

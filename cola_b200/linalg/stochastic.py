@@ -191,16 +191,15 @@ def hutchinson_diag_estimate(A: LinearOperator, k=0, bs=100, tol=3e-2, max_iters
             z = torch.sign(z)
         lo, hi = (rank * bs) // world, ((rank + 1) * bs) // world
         zl = z[:, lo:hi].contiguous()
-        if k == 0:
-            est = (A @ zl) * zl
-        elif k > 0:                                    # (A z)[r] * z[r + k]   (roll by -k, :190-194)
-            est = (A @ zl)[:n - k] * zl[k:]
-        else:                                          # (A z)[j + |k|] * z[j]
-            est = (A @ zl)[-k:] * zl[:n + k]
-        part = torch.stack([est.sum(-1), (est**2).sum(-1)])
+        Az = A @ zl
+        # sum_probes est and est^2 with est = (A z)[r] * z[r + k] (roll by -k, :190-194; k < 0: (A z)[j + |k|] * z[j]): one
+        # pass of the row-dots kernel over the two blocks, no (n, bs) temporaries
+        part = sums if group is None else torch.zeros_like(sums)
+        if hi > lo:
+            be.row_dots(Az, max(-k, 0), zl, max(k, 0), n - abs(k), 1.0, part[0], out_sq=part[1], accumulate=group is None)
         if group is not None:
             dist.all_reduce(part, group=group)
-        sums += part
+            sums += part
         i += 1
     samples.append(samples[-1])
     info = {"iterations": evals, "errors": np.array(samples[2:]), "iteration_time": (time.time() - t0) / evals}

@@ -66,13 +66,15 @@ int64_t cola_launch_count(void);
 
 /* Sparse CSR  Y = A X.   Replaces Sparse._matmat -> torch.sparse_csr @ dense
  * (cola/ops/operators.py:77-78, indices int32 per :73-74).  nnz = rowptr[n_rows]; max_row_nnz = longest row
- * (0 if unknown): both only steer tiling / prefetch depth, never results. */
+ * (0 if unknown); far_diagonal = distance |col - row| of the pattern's dominant far diagonal (the grid width of a
+ * stencil matrix; 0 if none / unknown): a CTA then takes strips of rows that distance apart, so the rows gathered across
+ * it are re-used from L1.  All three only steer tiling, never results. */
 int cola_csr_spmm_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const float* X, int64_t ldx, int64_t k, float* Y, int64_t ldy, float alpha,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const float* X, int64_t ldx, int64_t k, float* Y, int64_t ldy, float alpha,
                       float shift, const float* diag, int accumulate, double* dots, const int32_t* dots_row,
                       const int32_t* gate, void* stream);
 int cola_csr_spmm_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const double* X, int64_t ldx, int64_t k, double* Y, int64_t ldy, double alpha,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const double* X, int64_t ldx, int64_t k, double* Y, int64_t ldy, double alpha,
                       double shift, const double* diag, int accumulate, double* dots, const int32_t* dots_row,
                       const int32_t* gate, void* stream);
 
@@ -264,11 +266,13 @@ int cola_sddmm_csr_f64(const int32_t* rowptr, const int32_t* colidx, int64_t n_r
                        void* stream);
 
 /* Diagonal (operators.py:323-348) and the bands of a Tridiagonal (:351-372, with row-shifted G / V pointers):
- *   out[i] (+)= alpha * sum_c G[i, c] * V[i, c],  i < n. */
+ *   out[i] (+)= alpha * sum_c G[i, c] * V[i, c],  i < n.
+ * With out_sq != NULL also  out_sq[i] (+)= sum_c (G[i, c] * V[i, c])^2 : the two running sums of the Hutchinson diagonal
+ * estimator, sum_probes z*(Az) and its square (cola/linalg/trace/diagonal_estimation.py:190-199), in one pass. */
 int cola_row_dots_f32(const float* G, int64_t ldg, const float* V, int64_t ldv, int64_t n, int64_t k, float alpha, float* out,
-                      int accumulate, void* stream);
+                      float* out_sq, int accumulate, void* stream);
 int cola_row_dots_f64(const double* G, int64_t ldg, const double* V, int64_t ldv, int64_t n, int64_t k, double alpha,
-                      double* out, int accumulate, void* stream);
+                      double* out, double* out_sq, int accumulate, void* stream);
 
 /* Dense (operators.py:12-38; pre = 1, post = k: C = G V^T) and one factor of a Kronecker / KronSum (:198-275; G and Z
  * viewed as (pre, d, post) like cola_mode_contract's operands: the "mode Gram" C = sum_p G_p Z_p^T):

@@ -80,7 +80,7 @@ def diag_matmat(X, Y, shift, diag, accumulate, dots=None, dots_row=None, gate=No
 
 
 def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False,
-             dots=None, dots_row=None, gate=None):
+             dots=None, dots_row=None, gate=None, far_diagonal=0):
     if not _open(gate):
         return
     # like the kernels, products are accumulated in double and rounded once to the path dtype
@@ -163,8 +163,13 @@ def sddmm_csr(rowptr, colidx, n_rows, G, V, alpha, out):
     out.copy_((alpha * (G.double()[rows] * V.double()[colidx.to(torch.int64)]).sum(1)).to(out.dtype))
 
 
-def row_dots(G, g_row0, V, v_row0, n, alpha, out):
-    out.copy_((alpha * (G.double()[g_row0:g_row0 + n] * V.double()[v_row0:v_row0 + n]).sum(1)).to(out.dtype))
+def row_dots(G, g_row0, V, v_row0, n, alpha, out, out_sq=None, accumulate=False):
+    pr = G.double()[g_row0:g_row0 + n] * V.double()[v_row0:v_row0 + n]
+    res = (alpha * pr.sum(1)).to(out.dtype)
+    out.copy_(out + res if accumulate else res)
+    if out_sq is not None:
+        res2 = (pr * pr).sum(1).to(out.dtype)
+        out_sq.copy_(out_sq + res2 if accumulate else res2)
 
 
 def gram_nt(G, g_off, Z, z_off, d_g, d_z, pre, post, alpha, C):

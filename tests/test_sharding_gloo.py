@@ -33,6 +33,8 @@ def _worker(rank, world, port, results):
     # the per-chunk factorisation + quadrature (lanczos_fact on the kernels) stated with the oracle
     stochastic.lanczos_chunks_lockstep = (lambda A, blocks, m, tol, pbar, process, group=None:
                                           [ko.slq_per_probe(Ao, torch.log, get(), m, tol) for get in blocks])
+    from tests import host_harness
+    cb.backend.row_dots = host_harness.row_dots      # the estimator's two running sums (cola_row_dots_*), stated on CPU
     key = cb.rng.PRNGKey(42)
     num = max(int(1 / 0.2**2), 1)   # 24: same rounding as stochastic_lanczos_quad (slq.py:74)
     val = stochastic.slq_fwd(Stub(), torch.log, num_samples=num, max_iters=20, tol=1e-12, pbar=False, key=key,
