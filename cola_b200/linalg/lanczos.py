@@ -43,8 +43,8 @@ def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
     V[0].zero_()
     alpha_acc = torch.zeros((m, b), dtype=torch.float64, device=dev)      # diag   (<w, v_i>)
     sub_sq = torch.zeros((m + 1, b), dtype=torch.float64, device=dev)     # subdiag^2 (||w||^2)
-    C = torch.zeros((m + 2, b), dtype=torch.float64, device=dev)
-    C2 = torch.zeros((m + 2, b), dtype=torch.float64, device=dev)
+    CC = torch.zeros((2, m + 2, b), dtype=torch.float64, device=dev)    # coefficients of the two Gram-Schmidt passes
+    C, C2 = CC[0], CC[1]
     nrm = torch.zeros(b, dtype=torch.float64, device=dev)
     # init_lanczos: V[1] = rhs / ||rhs||   (lanczos.py:281-283)
     be.col_dots(rhs, rhs, nrm)
@@ -76,8 +76,7 @@ def lanczos_fact(A: LinearOperator, rhs, max_iters=100, tol=1e-7, pbar=False):
         A.matmat_into(vi, w, dots=alpha_acc[i - 1])        # w = A v_i ; diag[i-1] = <w, v_i>
         be.lanczos_three_term(w, vi, V[i - 1] if i > 1 else None, alpha_acc[i - 1], sub_sq[i - 1] if i > 1 else None)
         # do_double_gram (lanczos.py:287-296): dots, update, dots, update -- the middle two share one sweep
-        C[1:i + 1].zero_()
-        C2[1:i + 1].zero_()
+        CC.zero_()                                         # one fill for both passes' accumulators
         be.reorth_dots(V, 1, i + 1, w, C)
         if not be.reorth_update_dots(V, 1, i + 1, w, C, C2, sign=-1.0):
             be.reorth_update(V, 1, i + 1, w, C, sign=-1.0)
