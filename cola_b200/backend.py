@@ -203,11 +203,11 @@ def diag_matmat(X, Y, shift, diag, accumulate, dots=None, dots_row=None, gate=No
 
 
 def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False, dots=None,
-             dots_row=None, gate=None, far_diagonal=0):
+             dots_row=None, gate=None):
     k = X.shape[1]
     dt = vals.dtype
     lib().call(f"cola_csr_spmm_{sfx(dt)}", ptr(rowptr, torch.int32), ptr(colidx, torch.int32), ptr(vals), shape[0],
-               shape[1], nnz, max_row_nnz, int(far_diagonal), ptr(X, dt), k, k, ptr(Y, dt), k, scalar(dt, alpha), scalar(dt, shift),
+               shape[1], nnz, max_row_nnz, ptr(X, dt), k, k, ptr(Y, dt), k, scalar(dt, alpha), scalar(dt, shift),
                ptr(diag, dt) if diag is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
                stream_ptr())
 

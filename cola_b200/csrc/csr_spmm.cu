@@ -30,10 +30,6 @@ struct CsrArgs {
   int lanes, groups, rows_per_tile, cap;
   int need_x;
   int l2_prefetch, row_bytes;
-  // strip tiles of the pipelined kernel (see csr_spmm_pipe_kernel): a tile is `strips` strips of `strip_rows` consecutive
-  // rows, `strip_stride` rows apart for the first n_tiles2d tiles (they cover rows [0, rows2d)), consecutive afterwards
-  int strips, strip_rows;
-  int64_t strip_stride, n_tiles2d, rows2d, tiles_per_blk;
 };
 
 // One staged non-zero: element offset of its X row (col * ldx, computed ONCE per non-zero while staging
@@ -209,20 +205,13 @@ __device__ __forceinline__ Vec<T, 16 / (int)sizeof(T)> gather16(uint64_t base, u
   return r;
 }
 
-// STRIP TILES.  A CTA tile is S strips of R consecutive rows; R = the rows one pass of the block covers, so pass s of
-// the row loop is strip s.  For a pattern with a dominant far diagonal at distance D (a stencil on a D-wide grid:
-// BASELINE config 2, D = 2048) the host sets the strip stride to D: the rows a strip gathers across the far diagonals
-// are the neighbouring strips of the SAME tile, i.e. L1 hits one or two passes later, instead of L2 round trips to rows
-// another SM fetched (ncu on cfg2 with 256 consecutive rows per tile: L1 hit rate 37 %, 3.2 GB = 3 gathered rows per
-// output row from L2; with 8 x 32 strip tiles 1.3).  Without a hint the strips are consecutive (stride = R): the
-// plain 1-D tile.  Rows not covered by whole 2-D blocks (S * D rows each) are taken by 1-D tiles.
 template <typename T, int CH, bool EPI, bool DOTS, int PF, int BATCH, int MINB>
 __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArgs<T> a) {
   if (a.gate != nullptr && *a.gate != 0) return;
   constexpr int VEC = 16 / (int)sizeof(T);
   constexpr int NZS = PF + 2, RPS = PF + 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // layout: nz[NZS][cap] (col, val) | rp[RPS][S][R + 1] | red[256*VEC doubles]
+  // layout: nz[NZS][cap] (col, val) | rp[RPS][rows_per_tile + 1] | red[256*VEC doubles]
   Nz<T>* s_nz = reinterpret_cast<Nz<T>*>(smem_raw);
   int32_t* s_rp = reinterpret_cast<int32_t*>(s_nz + (size_t)NZS * a.cap);
   const int tid = threadIdx.x;
@@ -238,74 +227,49 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
   const char* __restrict__ Xb = reinterpret_cast<const char*>(a.X) + (size_t)l * 16;
   char* __restrict__ Yb = reinterpret_cast<char*>(a.Y) + (size_t)l * 16;
   const size_t ldyb = (size_t)a.ldy * sizeof(T);
-  const int S = a.strips, R = a.strip_rows, rps = R + 1, cap = a.cap;
-  const int tile_rp = S * rps;                                        // rowptr entries of one tile
-  const int64_t n_tiles = a.n_tiles2d + (a.n_rows - a.rows2d + (int64_t)S * R - 1) / ((int64_t)S * R);
+  const int rpt = a.rows_per_tile, rps = rpt + 1, cap = a.cap;
+  const int64_t n_tiles = (a.n_rows + rpt - 1) / rpt;
 
   // fp64 column accumulators: thread-private slots in shared memory (slot q of thread t at [q*256 + t]: conflict-free),
   // touched once per tile -- 16 registers less in the row loop
-  double* s_dacc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_rp + (size_t)RPS * tile_rp + 1) + 7) & ~(uintptr_t)7);
+  double* s_dacc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_rp + (size_t)RPS * rps + 1) + 7) & ~(uintptr_t)7);
   if constexpr (DOTS) {
 #pragma unroll
     for (int q = 0; q < CH * VEC; ++q) s_dacc[q * kCsrThreads + tid] = 0.0;
   }
 
   auto tile_of = [&](int i) -> int64_t { return (int64_t)blockIdx.x + (int64_t)i * gridDim.x; };
-  // first row of strip 0 and the strip stride of tile t
-  auto tile_geom = [&](int64_t t, int64_t& row0, int64_t& stride) {
-    if (t < a.n_tiles2d) {
-      const int64_t blk = t / a.tiles_per_blk, c = t - blk * a.tiles_per_blk;
-      row0 = blk * S * a.strip_stride + c * R;
-      stride = a.strip_stride;
-    } else {
-      row0 = a.rows2d + (t - a.n_tiles2d) * S * R;
-      stride = R;
-    }
-  };
-  auto strip_rows_of = [&](int64_t strip_row0) -> int {
-    const int64_t left = a.n_rows - strip_row0;
-    return left <= 0 ? 0 : (left < R ? (int)left : R);
-  };
+  auto rows_of = [&](int64_t t) -> int { return (int)min((int64_t)rpt, a.n_rows - t * rpt); };
   auto load_rp = [&](int i) {
     const int64_t t = tile_of(i);
     if (t >= n_tiles) return;
-    int64_t row0, stride;
-    tile_geom(t, row0, stride);
-    int32_t* dst = s_rp + (i % RPS) * tile_rp;
-    for (int j = tid; j < tile_rp; j += kCsrThreads) {
-      const int sidx = j / rps, q = j - sidx * rps;
-      const int64_t sr0 = row0 + sidx * stride;
-      const int rows = strip_rows_of(sr0);
-      if (rows > 0 && q <= rows) cp_async_small<4>(dst + j, a.rowptr + sr0 + q);   // strips past the last row: nothing
-    }
+    const int rows = rows_of(t);
+    int32_t* dst = s_rp + (i % RPS) * rps;
+    const int32_t* src = a.rowptr + t * rpt;
+    for (int j = tid; j <= rows; j += kCsrThreads) cp_async_small<4>(dst + j, src + j);
   };
-  // non-zeros of strip sidx of a tile whose rowptr slices are visible at rp
-  auto strip_nnz = [&](const int32_t* rp, int64_t row0, int64_t stride, int sidx) -> int32_t {
-    const int rows = strip_rows_of(row0 + sidx * stride);
-    return rows > 0 ? rp[sidx * rps + rows] - rp[sidx * rps] : 0;
-  };
-  auto tile_nnz = [&](const int32_t* rp, int64_t row0, int64_t stride) -> int32_t {
-    int32_t tot = 0;
-    for (int sidx = 0; sidx < S; ++sidx) tot += strip_nnz(rp, row0, stride, sidx);
-    return tot;
-  };
-  auto stage = [&](int i) {   // rowptr slices of tile i have landed and are visible
+  auto stage = [&](int i) {   // rowptr slice of tile i has landed and is visible
     const int64_t t = tile_of(i);
     if (t >= n_tiles) return;
-    int64_t row0, stride;
-    tile_geom(t, row0, stride);
-    const int32_t* rp = s_rp + (i % RPS) * tile_rp;
-    const int32_t nnz = tile_nnz(rp, row0, stride);
+    const int32_t* rp = s_rp + (i % RPS) * rps;
+    const int32_t base = rp[0], nnz = rp[rows_of(t)] - base;
     if (nnz > cap) return;    // heavy tile: its row loop reads the CSR arrays directly
     Nz<T>* dn = s_nz + (size_t)(i % NZS) * cap;
-    // the strips' ranges are staged back to back; a thread's slots j ascend, so its strip cursor only moves forward
-    int sidx = 0;
-    int32_t lo = 0, cnt = strip_nnz(rp, row0, stride, 0);
     for (int j = tid; j < nnz; j += kCsrThreads) {
-      while (j >= lo + cnt) { lo += cnt; ++sidx; cnt = strip_nnz(rp, row0, stride, sidx); }
-      const int32_t src = rp[sidx * rps] + (j - lo);
-      cp_async_small<4>(&dn[j].off, a.colidx + src);
-      cp_async_small<(int)sizeof(T)>(&dn[j].val, a.vals + src);
+      cp_async_small<4>(&dn[j].off, a.colidx + base + j);
+      cp_async_small<(int)sizeof(T)>(&dn[j].val, a.vals + base + j);
+    }
+  };
+  auto prefetch = [&](int i) {   // staged colidx of tile i has landed and is visible
+    const int64_t t = tile_of(i);
+    if (t >= n_tiles) return;
+    const int32_t* rp = s_rp + (i % RPS) * rps;
+    const int32_t nnz = rp[rows_of(t)] - rp[0];
+    if (nnz > cap) return;
+    const Nz<T>* dn = s_nz + (size_t)(i % NZS) * cap;
+    for (int j = tid; j < nnz; j += kCsrThreads) {
+      const char* xr = reinterpret_cast<const char*>(a.X) + (uint64_t)dn[j].off * (uint64_t)ldxb;
+      for (int b = 0; b < a.row_bytes; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(xr + b));
     }
   };
 
@@ -320,15 +284,22 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
   for (int i = 0; tile_of(i) < n_tiles; ++i) {
     cp_async_wait_all();
     __syncthreads();   // staged data of tiles <= i+PF and rowptr of tile i+PF+1 visible; tile i-1's row loop finished
+    if (a.l2_prefetch) {
+      if (i == 0)
+        for (int q = 0; q < PF; ++q) prefetch(q);
+      prefetch(i + PF);
+    }
     stage(i + PF + 1);
     load_rp(i + PF + 2);
     cp_async_commit();
     if (!col_ok) continue;
 
-    int64_t row0, stride;
-    tile_geom(tile_of(i), row0, stride);
-    const int32_t* rp = s_rp + (i % RPS) * tile_rp;
-    const bool staged = tile_nnz(rp, row0, stride) <= cap;
+    const int64_t tile = tile_of(i);
+    const int64_t row0 = tile * rpt;
+    const int rows = rows_of(tile);
+    const int32_t* rp = s_rp + (i % RPS) * rps;
+    const int32_t base = rp[0];
+    const bool staged = rp[rows] - base <= cap;
     const Nz<T>* tn = s_nz + (size_t)(i % NZS) * cap;
     // per-tile dot partials in T (fp32: a handful of rows per thread), folded into the fp64 accumulators once per
     // tile: the two F2F.F64.F32 conversions per element of a per-element fp64 product cost 0.13 ms of the 0.78 ms kernel
@@ -338,31 +309,22 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
 #pragma unroll
       for (int v = 0; v < VEC; ++v) facc[h][v] = (T)0;
 
-    int sidx = 0, ri = g;                                   // this group's next row: row ri of strip sidx
-    int32_t soff = 0;                                       // staged slot of strip sidx's first non-zero
-    while (ri >= R && sidx < S) { ri -= R; soff += strip_nnz(rp, row0, stride, sidx); ++sidx; }
-    for (; sidx < S; ) {
-      const int64_t sr0 = row0 + sidx * stride;
-      const int srows = strip_rows_of(sr0);
-      if (ri < srows) {
-      const int64_t row = sr0 + ri;
-      const int32_t* rps_ = rp + sidx * rps;
-      const int32_t gbase = rps_[0];                        // global index of the strip's first non-zero
-      const int32_t sbase = soff - gbase;                   // staged slot = global index + sbase
-      const int32_t s = rps_[ri], e = rps_[ri + 1];
+    for (int r = g; r < rows; r += a.groups) {
+      const int64_t row = row0 + r;
+      const int32_t s = rp[r] - base, e = rp[r + 1] - base;
       T acc[CH][VEC];
 #pragma unroll
       for (int h = 0; h < CH; ++h)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[h][v] = (T)0;
       if (staged) {
-        for (int32_t j = s + sbase; j < e + sbase; j += BATCH) {
+        for (int32_t j = s; j < e; j += BATCH) {
           // one predicated batch: all loads of up to BATCH non-zeros in flight, then predicated FMAs (no zero fill)
           Vec<T, VEC> x[BATCH][CH];
           T w[BATCH];
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
-            if (j + u < e + sbase) {
+            if (j + u < e) {
               const Nz<T> nz = tn[j + u];
               w[u] = nz.val;
               x[u][0] = gather16<T>(xb0, nz.off, ldxb);
@@ -371,7 +333,7 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
           }
 #pragma unroll
           for (int u = 0; u < BATCH; ++u) {
-            if (j + u < e + sbase) {
+            if (j + u < e) {
 #pragma unroll
               for (int h = 0; h < CH; ++h)
 #pragma unroll
@@ -382,8 +344,8 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
       } else {
 #pragma unroll 1
         for (int32_t j = s; j < e; ++j) {
-          const uint32_t c = (uint32_t)a.colidx[j];
-          const T w = a.vals[j];
+          const uint32_t c = (uint32_t)a.colidx[base + j];
+          const T w = a.vals[base + j];
           const char* xp = Xb + (uint64_t)c * (uint64_t)ldxb;
 #pragma unroll
           for (int h = 0; h < CH; ++h) {
@@ -424,9 +386,6 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
         }
         stg_stream<T, VEC>(reinterpret_cast<T*>(yrow + h * chunk_b), y);
       }
-      }
-      ri += a.groups;
-      while (ri >= R && sidx < S) { ri -= R; soff += strip_nnz(rp, row0, stride, sidx); ++sidx; }
     }
     if constexpr (DOTS) {
 #pragma unroll
@@ -530,7 +489,7 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
 
 template <typename T>
 int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_t n_rows, int64_t n_cols,
-             int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const T* X, int64_t ldx, int64_t k, T* Y, int64_t ldy, T alpha, T shift, const T* diag,
+             int64_t nnz, int64_t max_row_nnz, const T* X, int64_t ldx, int64_t k, T* Y, int64_t ldy, T alpha, T shift, const T* diag,
              int accumulate, double* dots, const int32_t* dots_row, const int32_t* gate, cudaStream_t st) {
   COLA_REQUIRE(rowptr && colidx && vals && X && Y, "csr_spmm: null pointer");
   COLA_REQUIRE(ldx >= k && ldy >= k, "csr_spmm: leading dimension < k");
@@ -602,26 +561,16 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     if (pipe) {
       a.lanes = (int)(a.k / (2 * kFullVec));
       a.groups = kCsrThreads / a.lanes;
-      // strip tiles: a strip = the rows of one block pass, S strips per tile (measured on cfg2 (B200), 1-D tiles:
-      // prefetch.global.L2 of the gathered rows one tile ahead changed nothing, 0.607 vs 0.626 ms)
-      a.strip_rows = a.groups;
-      a.strips = (env_rpg > 0 && env_rpg <= 16 ? env_rpg : 8);
-      a.rows_per_tile = a.strips * a.strip_rows;
-      static const bool no_2d = getenv("COLA_CSR_NO_STRIPS") != nullptr;   // A/B knob: consecutive strips only
-      const int64_t D = (far_diagonal > 0 && !no_2d) ? far_diagonal : 0;
-      const bool two_d = D >= 2 * a.strip_rows && D % a.strip_rows == 0 && n_rows >= (int64_t)a.strips * D;
-      a.strip_stride = two_d ? D : a.strip_rows;
-      a.tiles_per_blk = two_d ? D / a.strip_rows : 1;
-      const int64_t n_blk = two_d ? n_rows / ((int64_t)a.strips * D) : 0;
-      a.n_tiles2d = n_blk * a.tiles_per_blk;
-      a.rows2d = n_blk * a.strips * D;
+      a.rows_per_tile = a.groups * (env_rpg > 0 && env_rpg <= 16 ? env_rpg : 8);
       constexpr int pf = 1;
-      a.l2_prefetch = 0;
+      // measured on cfg2 (B200): prefetch.global.L2 of the gathered rows one tile ahead changes nothing (0.607 vs
+      // 0.626 ms): the row loop's ~1 us average miss latency is queueing in the memory system, not a cold L2
+      a.l2_prefetch = getenv("COLA_CSR_PIPE_PREFETCH") ? 1 : 0;
       int64_t want2 = (int64_t)(1.5 * avg * a.rows_per_tile) + 64;
       const int cap_max2 = sizeof(T) == 4 ? 3072 : 2048;
       a.cap = (int)(want2 < 256 ? 256 : (want2 > cap_max2 ? cap_max2 : want2));
-      n_tiles = a.n_tiles2d + (n_rows - a.rows2d + a.rows_per_tile - 1) / a.rows_per_tile;
-      smem = (size_t)(pf + 2) * a.cap * sizeof(Nz<T>) + (size_t)(pf + 3) * a.strips * (a.strip_rows + 1) * 4 + 16 +
+      n_tiles = (n_rows + a.rows_per_tile - 1) / a.rows_per_tile;
+      smem = (size_t)(pf + 2) * a.cap * sizeof(Nz<T>) + (size_t)(pf + 3) * (a.rows_per_tile + 1) * 4 + 16 +
              (dots ? (size_t)kCsrThreads * (2 + 1) * kFullVec * sizeof(double) : 0);   // fp64 accumulator slots + reduction scratch
     }
 #define COLA_CSR_PIPE_LAUNCH2(EPIV, DOTSV, PFV, BV, MB)                                                       \
@@ -685,19 +634,19 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
 using namespace cola;
 extern "C" {
 int cola_csr_spmm_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const float* X, int64_t ldx, int64_t k, float* Y,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const float* X, int64_t ldx, int64_t k, float* Y,
                       int64_t ldy,
                       float alpha, float shift, const float* diag, int accumulate, double* dots,
                       const int32_t* dots_row, const int32_t* gate, void* stream) {
-  return csr_spmm<float>(rowptr, colidx, vals, n_rows, n_cols, nnz, max_row_nnz, far_diagonal, X, ldx, k, Y, ldy, alpha, shift, diag, accumulate,
+  return csr_spmm<float>(rowptr, colidx, vals, n_rows, n_cols, nnz, max_row_nnz, X, ldx, k, Y, ldy, alpha, shift, diag, accumulate,
                          dots, dots_row, gate, reinterpret_cast<cudaStream_t>(stream));
 }
 int cola_csr_spmm_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const double* X, int64_t ldx, int64_t k, double* Y,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const double* X, int64_t ldx, int64_t k, double* Y,
                       int64_t ldy,
                       double alpha, double shift, const double* diag, int accumulate, double* dots,
                       const int32_t* dots_row, const int32_t* gate, void* stream) {
-  return csr_spmm<double>(rowptr, colidx, vals, n_rows, n_cols, nnz, max_row_nnz, far_diagonal, X, ldx, k, Y, ldy, alpha, shift, diag,
+  return csr_spmm<double>(rowptr, colidx, vals, n_rows, n_cols, nnz, max_row_nnz, X, ldx, k, Y, ldy, alpha, shift, diag,
                           accumulate, dots, dots_row, gate, reinterpret_cast<cudaStream_t>(stream));
 }
 }

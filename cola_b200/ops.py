@@ -315,26 +315,6 @@ class Sparse(LinearOperator):
     def _transpose(self):
         return Sparse(self.data, self.col_indices, self.row_indices, (self.shape[1], self.shape[0]))
 
-    @property
-    def far_diagonal(self):
-        """Distance |col - row| of the pattern's dominant far diagonal, or 0: the tiling hint of cola_csr_spmm_* (a stencil
-        matrix on a D-wide grid has a fifth or more of its entries at distance D).  Read off a sample of the entries once
-        per pattern; it steers tiling only."""
-        hint = self.__dict__.get("_far_diagonal")
-        if hint is None:
-            hint = 0
-            if self.nnz > 0 and self.shape[0] == self.shape[1]:
-                step = max(1, self.nnz // (1 << 20))
-                off = (self.indices[::step].to(torch.int64) - self.row_indices[::step].to(torch.int64)).abs()
-                off = off[off >= 64]
-                if off.numel() > 0:
-                    vals, counts = torch.unique(off, return_counts=True)
-                    top = int(torch.argmax(counts))
-                    if int(counts[top]) * 8 >= (self.nnz + step - 1) // step:      # at least an eighth of all entries
-                        hint = int(vals[top])
-            self.__dict__["_far_diagonal"] = hint
-        return hint
-
 
 class ScalarMul(LinearOperator):
     """operators.py:84-101"""
@@ -749,8 +729,7 @@ class _CsrCore:
         S = self.S
         strips = self._column_strips(X.shape[1], X.element_size()) if X.shape[1] <= 4 else None
         if strips is None:
-            return be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, S.max_row_nnz, X, Y, far_diagonal=S.far_diagonal,
-                               **epi.kw())
+            return be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, S.max_row_nnz, X, Y, **epi.kw())
         last = len(strips) - 1
         for b, (indptr, indices, data, nnz) in enumerate(strips):
             if b < last:       # partial row sums: Y = alpha * A_b X (+ Y)

@@ -66,15 +66,13 @@ int64_t cola_launch_count(void);
 
 /* Sparse CSR  Y = A X.   Replaces Sparse._matmat -> torch.sparse_csr @ dense
  * (cola/ops/operators.py:77-78, indices int32 per :73-74).  nnz = rowptr[n_rows]; max_row_nnz = longest row
- * (0 if unknown); far_diagonal = distance |col - row| of the pattern's dominant far diagonal (the grid width of a
- * stencil matrix; 0 if none / unknown): a CTA then takes strips of rows that distance apart, so the rows gathered across
- * it are re-used from L1.  All three only steer tiling, never results. */
+ * (0 if unknown): both only steer tiling / prefetch depth, never results. */
 int cola_csr_spmm_f32(const int32_t* rowptr, const int32_t* colidx, const float* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const float* X, int64_t ldx, int64_t k, float* Y, int64_t ldy, float alpha,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const float* X, int64_t ldx, int64_t k, float* Y, int64_t ldy, float alpha,
                       float shift, const float* diag, int accumulate, double* dots, const int32_t* dots_row,
                       const int32_t* gate, void* stream);
 int cola_csr_spmm_f64(const int32_t* rowptr, const int32_t* colidx, const double* vals, int64_t n_rows,
-                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, int64_t far_diagonal, const double* X, int64_t ldx, int64_t k, double* Y, int64_t ldy, double alpha,
+                      int64_t n_cols, int64_t nnz, int64_t max_row_nnz, const double* X, int64_t ldx, int64_t k, double* Y, int64_t ldy, double alpha,
                       double shift, const double* diag, int accumulate, double* dots, const int32_t* dots_row,
                       const int32_t* gate, void* stream);
 

@@ -80,7 +80,7 @@ def diag_matmat(X, Y, shift, diag, accumulate, dots=None, dots_row=None, gate=No
 
 
 def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False,
-             dots=None, dots_row=None, gate=None, far_diagonal=0):
+             dots=None, dots_row=None, gate=None):
     if not _open(gate):
         return
     # like the kernels, products are accumulated in double and rounded once to the path dtype

@@ -320,15 +320,13 @@ def test_spmv_column_strips(cb, monkeypatch):
 
 
 @pytest.mark.parametrize("g", [96, 100, 160, 201])
-def test_spmm_strip_tiles(g, cb):
-    """The pipelined SpMM takes strips of rows a far diagonal apart when the pattern has one (Sparse.far_diagonal: the
-    grid width of a stencil matrix): whole 2-D blocks, the 1-D tail tiles after them, grid widths that are / are not a
-    multiple of the strip height, fp32 and fp64, with the fused epilogue -- against a dense-equivalent fp64 product."""
+def test_spmm_pipelined_kernel_ragged_grids(g, cb):
+    """The software-pipelined SpMM (wide right-hand-side blocks) on grids whose row count is not a multiple of the tile,
+    fp32 and fp64, with the fused epilogue -- against a dense-equivalent fp64 product."""
     for dt, k, tol in [(torch.float32, 64, 2e-6), (torch.float64, 8, 1e-13), (torch.float32, 32, 2e-6)]:
         data, rows, cols, shape = pb.laplacian_2d_coo(g, dt)
         n = shape[0]
         S = cb.ops.Sparse(data.to(DEV), rows.to(DEV), cols.to(DEV), shape)
-        assert S.far_diagonal == g                      # 2 of 5 entries per row sit at distance g
         dg = torch.rand(n, dtype=dt, generator=torch.Generator().manual_seed(g))
         A = S + 0.5 * cb.ops.I_like(S) + cb.ops.Diagonal(dg.to(DEV))
         X = pb.randn_np((n, k), dt, 7).to(DEV)

@@ -212,19 +212,6 @@ def test_lanczos_chunks_run_in_lockstep(emu):
     assert gp.rel(Y1, Y2) < 1e-12 and gp.rel(Y1, torch.exp(d)[:, None] * V) < 1e-6
 
 
-def test_far_diagonal_hint(emu):
-    """The tiling hint of cola_csr_spmm_*: the grid width for a stencil pattern, 0 for a pattern without a far diagonal."""
-    from tests import problems as pb
-    data, rows, cols, shape = pb.laplacian_2d_coo(96, torch.float32)
-    assert emu.ops.Sparse(data, rows, cols, shape).far_diagonal == 96
-    data, rows, cols, shape = pb.laplacian_2d_coo(24, torch.float32)      # too narrow to matter
-    assert emu.ops.Sparse(data, rows, cols, shape).far_diagonal == 0
-    n = 5000
-    g = torch.Generator().manual_seed(1)
-    r, c = torch.randint(0, n, (40000, ), generator=g), torch.randint(0, n, (40000, ), generator=g)
-    assert emu.ops.Sparse(torch.ones(40000), r, c, (n, n)).far_diagonal == 0
-
-
 def test_spmv_column_strips(emu, monkeypatch):
     gn.test_spmv_column_strips(emu, monkeypatch)
 
