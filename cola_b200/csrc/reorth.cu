@@ -26,6 +26,7 @@ struct RoArgs {
   double* C; const double* Cc; T sign; double* wnorm2; const int32_t* gate;
   int lanes_per_row, rows_per_chunk, vec_path;
   int fold;   // reorth_dots on a single column viewed as (n / fold, fold): the fold partial columns add into C[j]
+  int qsplit; // reorth_dots: row parts per (vector, chunk) work item (see the kernel)
 };
 
 // accumulate type: fp32 partials over one chunk (<= rows_per_chunk terms per lane) are promoted to fp64
@@ -60,15 +61,23 @@ __global__ void __launch_bounds__(kDotsThreads) reorth_dots_kernel(RoArgs<T> a) 
       }
     }
     __syncthreads();
-    for (int64_t j = a.j0 + warp; j < a.j1; j += kDotsWarps) {
+    // Work items = (vector j, row part q of the chunk), dealt round-robin to the 16 warps.  With one part per vector a
+    // basis of 65 vectors costs 5 rounds for 4.06 rounds of work and a basis of 4 keeps 12 warps idle; Q parts per vector
+    // even that out (the parts of a vector then meet in shared memory with an atomic add).
+    const int Q = a.qsplit;
+    const int part_rows = ((rows + Q - 1) / Q + rows_per_step - 1) / rows_per_step * rows_per_step;
+    for (int64_t item = warp; item < nj * Q; item += kDotsWarps) {
+      const int64_t j = a.j0 + item / Q;
+      const int r_begin = (int)(item % Q) * part_rows;
+      const int r_end = min(rows, r_begin + part_rows);
       const T* vj = a.V + j * a.vstride + row0 * b;
       T acc[NC][VEC];
 #pragma unroll
       for (int c = 0; c < NC; ++c)
 #pragma unroll
         for (int v = 0; v < VEC; ++v) acc[c][v] = (T)0;
-#pragma unroll 4
-      for (int r = rsub; r < rows; r += rows_per_step) {
+#pragma unroll 8
+      for (int r = r_begin + rsub; r < r_end; r += rows_per_step) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
           const int64_t col = ((int64_t)c * Lr + cl) * VEC;
@@ -87,7 +96,10 @@ __global__ void __launch_bounds__(kDotsThreads) reorth_dots_kernel(RoArgs<T> a) 
           double s = (double)acc[c][v];
           for (int o = Lr; o < 32; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
           const int64_t col = ((int64_t)c * Lr + cl) * VEC + v;
-          if (rsub == 0 && col < b) csm[(j - a.j0) * b + col] += s;  // this warp is the only writer of row j
+          if (rsub == 0 && col < b) {
+            if (Q == 1) csm[(j - a.j0) * b + col] += s;            // this warp is the only writer of row j
+            else atomicAdd(csm + (j - a.j0) * b + col, s);
+          }
         }
       }
     }
@@ -487,11 +499,20 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
     RoArgs<T> a{};
     a.V = V; a.vstride = vstride; a.j0 = ja; a.j1 = jb; a.Wc = W; a.n = n; a.b = b; a.C = C; a.gate = gate;
     a.lanes_per_row = Lr; a.rows_per_chunk = (int)w_rows; a.fold = fold;
+    {
+      const int64_t njb = jb - ja;
+      const int steps = (int)(w_rows / (32 / Lr));              // row steps of a full chunk per warp
+      int q = (njb % kDotsWarps == 0) ? 1 : 4;                  // whole rounds already: keep the exclusive accumulation
+      while (q > 1 && steps / q < 8) q >>= 1;                   // a part is at least one unrolled burst of 8 steps
+      if (getenv("COLA_REORTH_QSPLIT")) q = atoi(getenv("COLA_REORTH_QSPLIT"));
+      a.qsplit = q < 1 ? 1 : q;
+    }
     size_t smem = (size_t)((jb - ja) * b * 8 + w_bytes);
     int64_t n_chunks = (n + w_rows - 1) / w_rows;
     int per_sm = (int)(budget / (int64_t)smem);
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
+    if (const char* e = getenv("COLA_REORTH_DOTS_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // A/B knob
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (grid > n_chunks) grid = n_chunks;
 #define COLA_LAUNCH_DOTS(VECV, NCV)                                                                              \
