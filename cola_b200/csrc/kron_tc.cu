@@ -888,7 +888,8 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
       cfg.dynamicSmemBytes = kF4Smem;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeCooperative; attr[0].val.cooperative = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
+      static const bool no_coop = getenv("COLA_KRON_NO_COOP") != nullptr;   // A/B knob (launch overhead measurement only)
+      cfg.attrs = attr; cfg.numAttrs = no_coop ? 0 : 1;
       cudaError_t le = cudaLaunchKernelEx(&cfg, kron_fused4_tc_kernel, cached_maps, fa);
       if (le != cudaSuccess) { cudaGetLastError(); return fail((int)le, cudaGetErrorString(le)); }
       if (want_prof) {   // bring-up only: synchronous dump of the per-role wait breakdown (mean over CTAs)

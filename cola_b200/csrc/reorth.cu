@@ -511,7 +511,10 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
     int64_t n_chunks = (n + w_rows - 1) / w_rows;
     int per_sm = (int)(budget / (int64_t)smem);
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
+    // measured (B200, profiles/r2_reorth_dots_ctas.log): more resident CTAs is not better -- 51 vectors x 64 fp32 columns run
+    // at 6.2 TB/s with 2 CTAs per SM, 5.0 with 3, 4.8 with 4; the folded single fp64 column at 4.1 / 5.5 / 4.0 TB/s
+    const int per_sm_cap = fold ? 3 : 2;
+    if (per_sm > per_sm_cap) per_sm = per_sm_cap;
     if (const char* e = getenv("COLA_REORTH_DOTS_CTAS")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // A/B knob
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (grid > n_chunks) grid = n_chunks;

@@ -146,6 +146,29 @@ def test_cg_edge_cases(cb):
     assert float(x[:, 1].abs().sum()) == 0.0
 
 
+def test_cg_workspace_is_not_shared_while_in_use(cb):
+    """A graph-eligible solve keeps its state and captured batch on the operator.  A solve that finds that workspace in
+    use (another thread / stream) takes fresh buffers instead of writing into it, and
+    release_cg_workspace() drops it."""
+    P = pb.problem("dense96_f64")
+    A = pb.to_b200(P["spec"], DEV, P["ann"])
+    B = P["B"].to(DEV)
+    alg = cb.linalg.CG(tol=1e-10, max_iters=200)
+    x1, info1 = alg(A, B)
+    ws = A.__dict__["_cg_workspace"]
+    assert ws["graph"] is not None and not ws["busy"]
+    ws["busy"] = True                                    # as if a concurrent solve held it
+    marker = ws["x"].clone()
+    x2, info2 = alg(A, B)
+    assert torch.equal(ws["x"], marker)                  # untouched
+    assert info2["iterations"] == info1["iterations"] and rel(x2, x1) < 1e-12
+    ws["busy"] = False
+    x3, _ = alg(A, B)                                    # replays the cached batch again
+    assert rel(x3, x1) < 1e-12
+    cb.linalg.release_cg_workspace(A)
+    assert "_cg_workspace" not in A.__dict__
+
+
 @pytest.mark.parametrize("case", sorted(PCG_CASES))
 def test_pcg_nystrom_vs_oracle_and_golden(case, golden, cb):
     """Preconditioned CG: NystromPrecond built on the device (library QR/Cholesky/SVD of the
