@@ -225,6 +225,23 @@ def mode_contract(M, d_out, d_in, pre, post, inp, out, alpha=1.0, shift=0.0, dia
                ptr(gate), stream_ptr())
 
 
+def mode_contract_tc_ok(M, pre, L, k, X):
+    """True when cola_mode_contract_tc_f32 takes this mode: fp32, a square 64- or 128-wide factor, k % 32 == 0."""
+    d = M.shape[0]
+    return (M.dtype == torch.float32 and X.dtype == torch.float32 and M.shape[0] == M.shape[1] and
+            bool(lib().cdll.cola_mode_contract_tc_supported(d, pre, L, k)))
+
+
+def mode_contract_tc(M, pre, L, k, inp, out, alpha=1.0, shift=0.0, diag=None, epi_x=None, accumulate=False, dots=None,
+                     dots_row=None, gate=None):
+    """out[p, a, l, r] = alpha * sum_j M[a, j] inp[p, j, l, r] on the tensor cores (3xTF32); epilogue as mode_contract."""
+    dt = torch.float32
+    lib().call("cola_mode_contract_tc_f32", ptr(M, dt), M.stride(0), M.shape[0], pre, L, k, ptr(inp, dt), ptr(out, dt),
+               ctypes.c_float(alpha), ctypes.c_float(shift), ptr(diag, dt) if diag is not None else None,
+               ptr(epi_x, dt) if epi_x is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
+               stream_ptr())
+
+
 def reorth_dots(V, j0, j1, W, C, gate=None):
     """V (n_vec, n, b) contiguous, W (n, b), C (n_vec, b) float64."""
     n, b = W.shape

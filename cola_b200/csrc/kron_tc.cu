@@ -693,6 +693,9 @@ __global__ void __launch_bounds__(kF4Threads, 1)
         } else {
           const float* pd = (dg != nullptr) ? dg + (((p * kD + h * 32) << lsh) + l) : nullptr;
           const int64_t dstride = (int64_t)1 << lsh;
+          // <x, y> of the 32 stored values in fp32, folded into the fp64 accumulator once per tile: a per-element fp64
+          // product costs two F2F conversions each (measured on the SpMM epilogue: 17 % of that kernel)
+          float facc = 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i, po += row_stride) {
             float yy = y[i];
@@ -702,9 +705,10 @@ __global__ void __launch_bounds__(kF4Threads, 1)
               yy += sd * xv[i];
             }
             if (accumulate) yy += *po;
-            if (fused) dacc += (double)xv[i] * (double)yy;      // of the stored value: earlier terms of a Sum included
+            if (fused) facc += xv[i] * yy;                      // of the stored value: earlier terms of a Sum included
             *po = yy;
           }
+          dacc += (double)facc;
         }
       }
       if (dp != nullptr && dacc_r0 >= 0) atomicAdd(dp + dacc_r0 + lane, dacc);
@@ -727,15 +731,306 @@ __global__ void __launch_bounds__(kF4Threads, 1)
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
   }
-  if ((a.dbg & 64) && threadIdx.x == 0) {
-    // measurement knob (COLA_KRON_DBG=64): the last CTA to leave zeroes the phase counters, the host skips its memset
-    __threadfence();
-    const unsigned int prev = atomicAdd(a.counters + kFusedMaxPhases, 1u);
-    if (prev == gridDim.x - 1) {
-      for (int i = 0; i < n_phases; ++i) a.counters[i] = 0u;
-      a.counters[kFusedMaxPhases] = 0u;
-      __threadfence();
+}
+
+// =======================================================================================================
+// One mode contraction per launch on the tensor cores, factor size KD = 64 or 128 (round 2):
+//     out[p, a, l, r] = sum_j F[a, j] in[p, j, l, r],   F (KD x KD),  in (pre, KD, L, k) with k % 32 == 0
+// Same tile formulation and 3xTF32 scheme as the fused kernel (positions = 4 atoms x 32 right-hand sides, raw TMA tile =
+// hi operand, lo tile from the split warps, epilogue straight from registers), without phases: the tiles of one mode are
+// independent, so a persistent grid walks them with no device-wide synchronisation.  It serves the modes the fused kernel
+// does not take: 128-wide factors (BASELINE config 4: Kronecker(128, 128, 64)) and 64-wide modes next to them.
+//   KD = 64 : factor pair stacked along N (8 + 8 MMAs per tile), ring of 4 raw tiles, 2 lo tiles.
+//   KD = 128: the contraction index is taken in two halves of 64 (two raw half-tiles per output tile accumulate into one
+//             128-column accumulator); per half  A_lo F_hi  first (the lo tile is then free for the next split while the
+//             16 MMAs on the raw tile run), then  A_hi F_hi, A_hi F_lo  (N = 128 each: 24 MMAs of 79 cycles per half).
+//             F_hi | F_lo resident (128 KB) + ring of 2 raw half-tiles + 1 lo tile = 224 KB.
+// The epilogue of the operator (alpha, shift, diag, accumulate, <x, y> dots) applies when L == 1 (the last factor of a
+// Kronecker chain), like cola_mode_contract_*'s.
+// =======================================================================================================
+constexpr int kMtThreads = 512;       // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 split, 8-15 epilogue
+struct ModeTcArgs {
+  float* out; const float* epi_x; const float* diag;
+  int64_t L, pre, k;                  // in viewed as (pre, KD, L, k); out (pre, KD, L, k)
+  int64_t n_pos_tiles;                // pre * L / 4
+  float alpha, shift; int accumulate; int fused;
+  double* dots; const int32_t* dots_row; const int32_t* gate;
+};
+
+template <int KD>
+struct ModeTcCfg {
+  static constexpr int kHalves = KD / 64;
+  static constexpr int kFacBytes1 = KD * KD * 4;                  // one of hi / lo
+  static constexpr int kRing = KD == 64 ? 4 : 2;
+  static constexpr int kLoBufs = KD == 64 ? 2 : 1;
+  static constexpr int kOffFac = 0;
+  static constexpr int kOffLo = 2 * kFacBytes1;
+  static constexpr int kOffRing = kOffLo + kLoBufs * kTileBytes;
+  static constexpr int kOffBars = kOffRing + kRing * kTileBytes;
+  static constexpr int kSmem = kOffBars + 256 + 1024;
+  static_assert(kSmem <= 232448, "mode_tc: shared memory budget");
+};
+
+template <int KD>
+__global__ void __launch_bounds__(kMtThreads, 1)
+    mode_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_fac, ModeTcArgs a) {
+  using C = ModeTcCfg<KD>;
+  if (a.gate != nullptr && *a.gate != 0) return;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar_full0 = sbase + C::kOffBars;                 // [ring] raw half-tile landed
+  const uint32_t bar_slotfree0 = bar_full0 + 8 * C::kRing;        // [ring] MMAs reading the slot retired
+  const uint32_t bar_loready0 = bar_slotfree0 + 8 * C::kRing;     // [lo bufs] lo tile written (count 4)
+  const uint32_t bar_lofree0 = bar_loready0 + 16;                 // [lo bufs] MMAs reading the lo tile retired
+  const uint32_t bar_tfull0 = bar_lofree0 + 16;                   // [2] accumulator complete
+  const uint32_t bar_tempty0 = bar_tfull0 + 16;                   // [2] accumulator drained (count 8)
+  const uint32_t bar_fac = bar_tempty0 + 16;                      // factor landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::kOffBars + 200);
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kRing; ++s) { mbar_init(bar_full0 + 8 * s, 1); mbar_init(bar_slotfree0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_loready0 + 8 * s, 4);
+      mbar_init(bar_lofree0 + 8 * s, 1);
+      mbar_init(bar_tfull0 + 8 * s, 1);
+      mbar_init(bar_tempty0 + 8 * s, 8);
     }
+    mbar_init(bar_fac, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // ---- factor: TMA boxes of 32 k-columns x KD rows, then hi = rna(F) in place and lo beside it -------------------
+  // KD = 64 : k-chunk c at c * 16 KB as [hi rows | lo rows] (the stacked N = 128 operand);  KD = 128: hi chunks c * 16 KB,
+  // lo chunks 64 KB further.
+  constexpr int kChunkBytes = KD * 128;                           // one k-chunk of one of hi / lo
+  constexpr int kChunkStride = KD == 64 ? 2 * kChunkBytes : kChunkBytes;
+  constexpr int kLoOffset = KD == 64 ? kChunkBytes : C::kFacBytes1;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar_fac, C::kFacBytes1);
+    for (int c = 0; c < KD / 32; ++c) tma_load_2d(sbase + C::kOffFac + c * kChunkStride, &map_fac, bar_fac, c * 32, 0);
+  }
+  mbar_wait(bar_fac, 0);
+  for (int o = threadIdx.x * 16; o < C::kFacBytes1; o += kMtThreads * 16) {
+    const int c = o / kChunkBytes, w = o - c * kChunkBytes;
+    unsigned char* hp = smem + C::kOffFac + c * kChunkStride + w;
+    const float4 v = *reinterpret_cast<const float4*>(hp);
+    float4 hh, l;
+    hh.x = tf32_rna(v.x); hh.y = tf32_rna(v.y); hh.z = tf32_rna(v.z); hh.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - hh.x); l.y = tf32_rna(v.y - hh.y); l.z = tf32_rna(v.z - hh.z); l.w = tf32_rna(v.w - hh.w);
+    *reinterpret_cast<float4*>(hp) = hh;
+    *reinterpret_cast<float4*>(hp + kLoOffset) = l;
+  }
+  fence_async_smem();
+  __syncthreads();
+
+  const int64_t ncb = a.k / 32;                                   // 32-column blocks
+  const int64_t n_tiles = a.n_pos_tiles * ncb;                    // position tile major, column block minor
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0) {
+    // ===== TMA loads: kHalves raw half-tiles per output tile =====
+    if (lane == 0) {
+      int rit = 0;
+      for (int64_t t = first; t < n_tiles; t += step) {
+        const int64_t tp = t / ncb, cc = t - tp * ncb;
+        for (int h = 0; h < C::kHalves; ++h, ++rit) {
+          const int s = rit % C::kRing;
+          mbar_wait(bar_slotfree0 + 8 * s, ((rit / C::kRing) & 1) ^ 1);
+          mbar_expect_tx(bar_full0 + 8 * s, kTileBytes);
+          const uint32_t dst = sbase + C::kOffRing + s * kTileBytes;
+#pragma unroll
+          for (int at = 0; at < 4; ++at) {
+            const int64_t flat = tp * 4 + at;
+            const int64_t p = flat / a.L, l = flat - p * a.L;
+            tma_load_3d(dst + at * kAtomBytes, &map_in, bar_full0 + 8 * s, (int)(cc * 32), (int)l, (int)(p * KD + h * 64));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int it = 0, rit = 0;
+      const uint64_t ad_ring0 = make_desc(sbase + C::kOffRing, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t ad_lo0 = make_desc(sbase + C::kOffLo, kAtomBytes, 512, kLayoutSw128Base32);
+      const uint64_t bd0 = make_desc(sbase + C::kOffFac, 16, 1024, kLayoutSw128);
+      for (int64_t t = first; t < n_tiles; t += step, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_tempty0 + 8 * acc, (((it >> 1) & 1) ^ 1));
+        const uint32_t d = tmem_base + acc * 128;
+        for (int h = 0; h < C::kHalves; ++h, ++rit) {
+          const int s = rit % C::kRing;
+          const int lb = rit % C::kLoBufs;
+          mbar_wait(bar_loready0 + 8 * lb, (rit / C::kLoBufs) & 1);      // lo tile written (=> raw half-tile landed)
+          tc_fence_after();
+          const uint64_t ad_hi = ad_ring0 + (uint64_t)((s * kTileBytes) >> 4);
+          const uint64_t ad_lo = ad_lo0 + (uint64_t)((lb * kTileBytes) >> 4);
+          if constexpr (KD == 64) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {                              // A_hi x [F_hi ; F_lo]
+              const uint64_t bd = bd0 + (uint64_t)(((kk / 4) * kChunkStride + (kk % 4) * 32) >> 4);
+              umma_tf32(d, ad_hi + (uint64_t)((kk * 1024) >> 4), bd, kIdescN128, kk ? 1u : 0u);
+            }
+            umma_commit(bar_slotfree0 + 8 * s);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {                              // A_lo x F_hi
+              const uint64_t bd = bd0 + (uint64_t)(((kk / 4) * kChunkStride + (kk % 4) * 32) >> 4);
+              umma_tf32(d, ad_lo + (uint64_t)((kk * 1024) >> 4), bd, kIdesc, 1u);
+            }
+            umma_commit(bar_lofree0 + 8 * lb);
+          } else {
+            // k-steps of this half: global k index 8 * h + kk
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {                              // A_lo x F_hi first: frees the single lo tile early
+              const int kg = h * 8 + kk;
+              const uint64_t bd = bd0 + (uint64_t)(((kg / 4) * kChunkStride + (kg % 4) * 32) >> 4);
+              umma_tf32(d, ad_lo + (uint64_t)((kk * 1024) >> 4), bd, kIdescN128, (h | kk) ? 1u : 0u);
+            }
+            umma_commit(bar_lofree0 + 8 * lb);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {                              // A_hi x F_hi
+              const int kg = h * 8 + kk;
+              const uint64_t bd = bd0 + (uint64_t)(((kg / 4) * kChunkStride + (kg % 4) * 32) >> 4);
+              umma_tf32(d, ad_hi + (uint64_t)((kk * 1024) >> 4), bd, kIdescN128, 1u);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {                              // A_hi x F_lo
+              const int kg = h * 8 + kk;
+              const uint64_t bd = bd0 + (uint64_t)((kLoOffset + (kg / 4) * kChunkStride + (kg % 4) * 32) >> 4);
+              umma_tf32(d, ad_hi + (uint64_t)((kk * 1024) >> 4), bd, kIdescN128, 1u);
+            }
+            umma_commit(bar_slotfree0 + 8 * s);
+          }
+        }
+        umma_commit(bar_tfull0 + 8 * acc);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===== split warps: lo tile of every raw half-tile =====
+    const int tid = threadIdx.x - 128;
+    int rit = 0;
+    for (int64_t t = first; t < n_tiles; t += step) {
+      for (int h = 0; h < C::kHalves; ++h, ++rit) {
+        const int s = rit % C::kRing;
+        const int lb = rit % C::kLoBufs;
+        mbar_wait(bar_full0 + 8 * s, (rit / C::kRing) & 1);
+        mbar_wait(bar_lofree0 + 8 * lb, ((rit / C::kLoBufs) & 1) ^ 1);
+        const unsigned char* raw = smem + C::kOffRing + s * kTileBytes;
+        unsigned char* lo = smem + C::kOffLo + lb * kTileBytes;
+#pragma unroll 4
+        for (int o = tid * 16; o < kTileBytes; o += 128 * 16) {
+          const float4 v = *reinterpret_cast<const float4*>(raw + o);
+          uint4 l;
+          l.x = tf32_lo_bits(v.x); l.y = tf32_lo_bits(v.y); l.z = tf32_lo_bits(v.z); l.w = tf32_lo_bits(v.w);
+          *reinterpret_cast<uint4*>(lo + o) = l;
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_loready0 + 8 * lb);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===== epilogue: two warps per TMEM lane quadrant (= atom), KD / 2 output columns each, in groups of 32 =====
+    const int q = warp & 3, hw = (warp - 8) >> 2;
+    const bool fused = a.fused != 0;
+    const float* __restrict__ xin = a.epi_x;
+    const float* __restrict__ dg = a.diag;
+    float* __restrict__ outp = a.out;
+    const int64_t row_stride = a.L * a.k;
+    double dacc = 0.0;
+    int64_t dacc_c = -1;
+    double* const dp = (fused && a.dots != nullptr) ? a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k : 0) : nullptr;
+    int it = 0;
+    for (int64_t t = first; t < n_tiles; t += step, ++it) {
+      const int acc = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      const int64_t tp = t / ncb, cc = t - tp * ncb;
+      const int64_t flat = tp * 4 + q;
+      const int64_t p = flat / a.L, l = flat - p * a.L;
+      if (dp != nullptr && cc != dacc_c) {
+        if (dacc_c >= 0) atomicAdd(dp + dacc_c * 32 + lane, dacc);
+        dacc = 0.0;
+        dacc_c = cc;
+      }
+      constexpr int kGroups = KD / 64;                           // groups of 32 output columns per warp
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int a0 = hw * (KD / 2) + g * 32;                   // first output index of the group
+        const int64_t base = ((p * KD + a0) * a.L + l) * a.k + cc * 32 + lane;
+        float xv[32];
+        if (fused) {                                             // requested before the accumulator wait
+          const float* px = xin + base;
+#pragma unroll
+          for (int i = 0; i < 32; ++i, px += row_stride) xv[i] = *px;
+        }
+        if (g == 0) {
+          mbar_wait(bar_tfull0 + 8 * acc, par);
+          tc_fence_after();
+        }
+        float y[32];
+        {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + (KD == 64 ? hw * 32 : a0);
+          tmem_ld16_at<0>(taddr, v);
+          tmem_ld16_at<1>(taddr, v);
+          if constexpr (KD == 64) {
+            uint32_t w[32];
+            tmem_ld16_at<0>(taddr + 64, w);
+            tmem_ld16_at<1>(taddr + 64, w);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = a.alpha * (__uint_as_float(v[i]) + __uint_as_float(w[i]));
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = a.alpha * __uint_as_float(v[i]);
+          }
+        }
+        if (g == kGroups - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);     // accumulator back to the MMA warp
+        }
+        float* po = outp + base;
+        if (!fused && !a.accumulate) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i, po += row_stride) *po = y[i];
+        } else {
+          const float* pd = (fused && dg != nullptr) ? dg + (p * KD + a0) : nullptr;     // L == 1 when fused
+          float facc = 0.f;                                      // fp32 over the 32 values, fp64 across (see the fused kernel)
+#pragma unroll
+          for (int i = 0; i < 32; ++i, po += row_stride) {
+            float yy = y[i];
+            if (fused) {
+              float sd = a.shift;
+              if (pd != nullptr) sd += pd[i];
+              yy += sd * xv[i];
+            }
+            if (a.accumulate) yy += *po;
+            if (fused) facc += xv[i] * yy;
+            *po = yy;
+          }
+          dacc += (double)facc;
+        }
+      }
+    }
+    if (dp != nullptr && dacc_c >= 0) atomicAdd(dp + dacc_c * 32 + lane, dacc);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
   }
 }
 
@@ -753,10 +1048,10 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-static int make_map_in(CUtensorMap* m, const float* in, int64_t pre, int64_t L, int64_t k) {
+static int make_map_in(CUtensorMap* m, const float* in, int64_t pre, int64_t L, int64_t k, int64_t d = kD) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(COLA_E_UNSUPPORTED, "kron_tc: cuTensorMapEncodeTiled unavailable");
-  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)L, (cuuint64_t)(pre * kD)};
+  cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)L, (cuuint64_t)(pre * d)};
   cuuint64_t strides[2] = {(cuuint64_t)(k * 4), (cuuint64_t)(L * k * 4)};
   cuuint32_t box[3] = {32, 1, (cuuint32_t)kD};
   cuuint32_t es[3] = {1, 1, 1};
@@ -767,12 +1062,12 @@ static int make_map_in(CUtensorMap* m, const float* in, int64_t pre, int64_t L, 
   return COLA_OK;
 }
 
-static int make_map_fac(CUtensorMap* m, const float* F, int64_t ldf) {
+static int make_map_fac(CUtensorMap* m, const float* F, int64_t ldf, int64_t d = kD) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return fail(COLA_E_UNSUPPORTED, "kron_tc: cuTensorMapEncodeTiled unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)kD, (cuuint64_t)kD};
+  cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)d};
   cuuint64_t strides[1] = {(cuuint64_t)(ldf * 4)};
-  cuuint32_t box[2] = {32, (cuuint32_t)kD};
+  cuuint32_t box[2] = {32, (cuuint32_t)d};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)F, dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -887,11 +1182,9 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
         cudaFuncSetAttribute(kron_fused4_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kF4Smem);
         smem_set = true;
       }
-      static bool self_reset_primed = false;
-      if (!(fdbg & 64) || !self_reset_primed) {
-        cudaMemsetAsync(fa.counters, 0, sizeof(unsigned int) * (kFusedMaxPhases + 1), st);
-        self_reset_primed = true;
-      }
+      // (measured: letting the kernel's last CTA reset the counters instead of this memset changes nothing, 0.403 vs
+      // 0.407 ms per cfg3 CG iteration, and would rely on the workspace's contents surviving between calls)
+      cudaMemsetAsync(fa.counters, 0, sizeof(unsigned int) * n_phases, st);
       const int64_t n_tiles = n / kD / 4 * cpc;
       int64_t grid = sm_count();
       if (grid > n_tiles) grid = n_tiles;
@@ -1017,6 +1310,58 @@ int cola_kronsum_matmat_tc_f32(int64_t n_factors, const float* const* factors, c
     }
   }
   return COLA_OK;
+}
+
+int cola_mode_contract_tc_supported(int64_t d, int64_t pre, int64_t L, int64_t k) {
+  return ((d == 64 || d == 128) && pre >= 1 && L >= 1 && (pre * L) % 4 == 0 && k >= 32 && k % 32 == 0 &&
+          pre * d < (int64_t)1 << 31 && L < (int64_t)1 << 31) ? 1 : 0;
+}
+
+int cola_mode_contract_tc_f32(const float* M, int64_t ldm, int64_t d, int64_t pre, int64_t L, int64_t k, const float* in,
+                              float* out, float alpha, float shift, const float* diag, const float* epi_x, int accumulate,
+                              double* dots, const int32_t* dots_row, const int32_t* gate, void* stream) {
+  COLA_REQUIRE(M && in && out, "mode_contract_tc: null pointer");
+  COLA_REQUIRE(in != out, "mode_contract_tc: in and out must not alias");
+  COLA_REQUIRE(cola_mode_contract_tc_supported(d, pre, L, k), "mode_contract_tc: d in {64, 128}, k % 32 == 0, pre * L % 4 == 0");
+  COLA_REQUIRE(((uintptr_t)M % 16 == 0) && (ldm % 4 == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0),
+               "mode_contract_tc: 16-byte alignment");
+  const bool fused = (shift != 0.f) || diag || dots;
+  COLA_REQUIRE(!fused || (L == 1 && epi_x), "mode_contract_tc: shift / diag / dots need L == 1 and epi_x");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // tensor maps depend only on (pointers, shapes): Krylov loops call with the same buffers every step (two or three modes
+  // alternate), so a few recent pairs are kept
+  struct Entry { const void* in; const void* M; int64_t ldm, d, pre, L, k; CUtensorMap map_in, map_fac; bool valid; };
+  static thread_local Entry cache[8] = {};
+  static thread_local int next_slot = 0;
+  Entry* e = nullptr;
+  for (auto& c : cache)
+    if (c.valid && c.in == in && c.M == M && c.ldm == ldm && c.d == d && c.pre == pre && c.L == L && c.k == k) { e = &c; break; }
+  if (e == nullptr) {
+    e = &cache[next_slot];
+    next_slot = (next_slot + 1) % 8;
+    e->valid = false;
+    int rc = make_map_in(&e->map_in, in, pre, L, k, d);
+    if (rc) return rc;
+    rc = make_map_fac(&e->map_fac, M, ldm, d);
+    if (rc) return rc;
+    e->in = in; e->M = M; e->ldm = ldm; e->d = d; e->pre = pre; e->L = L; e->k = k; e->valid = true;
+  }
+  ModeTcArgs a;
+  a.out = out; a.epi_x = fused ? epi_x : nullptr; a.diag = diag; a.L = L; a.pre = pre; a.k = k;
+  a.n_pos_tiles = pre * L / 4; a.alpha = alpha; a.shift = shift; a.accumulate = accumulate; a.fused = fused ? 1 : 0;
+  a.dots = dots; a.dots_row = dots_row; a.gate = gate;
+  const int64_t n_tiles = a.n_pos_tiles * (k / 32);
+  int64_t grid = sm_count();
+  if (grid > n_tiles) grid = n_tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mode_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeTcCfg<64>::kSmem);
+    cudaFuncSetAttribute(mode_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ModeTcCfg<128>::kSmem);
+    attr_set = true;
+  }
+  if (d == 64) mode_tc_kernel<64><<<(unsigned)grid, kMtThreads, ModeTcCfg<64>::kSmem, st>>>(e->map_in, e->map_fac, a);
+  else mode_tc_kernel<128><<<(unsigned)grid, kMtThreads, ModeTcCfg<128>::kSmem, st>>>(e->map_in, e->map_fac, a);
+  return cuda_status("mode_contract_tc");
 }
 
 }  // extern "C"

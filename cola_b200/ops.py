@@ -789,15 +789,25 @@ class _KronCore:
         src = X
         for i, F in enumerate(self.Fs):
             pre = _prod(d_out[:i]) if i > 0 else 1
-            post = (_prod(d_in[i + 1:]) if i + 1 < D else 1) * k
+            L = _prod(d_in[i + 1:]) if i + 1 < D else 1
+            post = L * k
             last = i == D - 1
+            # a square 64- / 128-wide fp32 factor with k % 32 == 0: the per-mode tcgen05 kernel (csrc/kron_tc.cu,
+            # mode_tc_kernel; BASELINE config 4's Kronecker(128, 128, 64)); anything else: exact SIMT tiles
+            tc = self.use_tensor_cores and be.mode_contract_tc_ok(F, pre, L, k, X)
             if last:
-                be.mode_contract(F, d_out[i], d_in[i], pre, post, src, Y, epi_x=X if epi.needs_x() else None,
-                                 **epi.kw())
+                if tc:
+                    be.mode_contract_tc(F, pre, L, k, src, Y, epi_x=X if epi.needs_x() else None, **epi.kw())
+                else:
+                    be.mode_contract(F, d_out[i], d_in[i], pre, post, src, Y, epi_x=X if epi.needs_x() else None,
+                                     **epi.kw())
             else:
                 numel = pre * d_out[i] * post
                 dst = self._workspace(numel, X.dtype, X.device, i % 2)
-                be.mode_contract(F, d_out[i], d_in[i], pre, post, src, dst, gate=epi.gate)
+                if tc:
+                    be.mode_contract_tc(F, pre, L, k, src, dst, gate=epi.gate)
+                else:
+                    be.mode_contract(F, d_out[i], d_in[i], pre, post, src, dst, gate=epi.gate)
                 src = dst
 
 

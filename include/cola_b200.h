@@ -118,6 +118,17 @@ int cola_kronsum_matmat_tc_f32(int64_t n_factors, const float* const* factors, c
                                float* Y, int64_t k, float alpha, float shift, const float* diag, int accumulate,
                                double* dots, const int32_t* dots_row, const int32_t* gate, void* stream);
 
+/* One mode contraction on the tensor cores (tcgen05 3xTF32, same tiles as cola_kron_matmat_tc_f32) for a SQUARE factor of
+ * size d = 64 or 128:  out[p, a, l, r] = alpha * sum_j M[a, j] in[p, j, l, r]  with in / out (pre, d, L, k) row-major,
+ * k a multiple of 32 and pre * L a multiple of 4.  It takes the modes of a Kronecker chain the fused kernel does not
+ * (BASELINE config 4: Kronecker(128, 128, 64)); the epilogue (shift / diag / dots / accumulate, as cola_mode_contract_*)
+ * needs L == 1 (the last factor).  in and out must not alias.  cola_mode_contract_tc_supported says whether a shape is
+ * taken. */
+int cola_mode_contract_tc_supported(int64_t d, int64_t pre, int64_t L, int64_t k);
+int cola_mode_contract_tc_f32(const float* M, int64_t ldm, int64_t d, int64_t pre, int64_t L, int64_t k, const float* in,
+                              float* out, float alpha, float shift, const float* diag, const float* epi_x, int accumulate,
+                              double* dots, const int32_t* dots_row, const int32_t* gate, void* stream);
+
 /* Operators with no core (Diagonal, ScalarMul*Identity, sums of those):
  *   Y = (shift + diag[i]) * X  (+Y).   Diagonal._matmat / ScalarMul._matmat (operators.py:97-98,338-339). */
 int cola_diag_matmat_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n, int64_t k, float shift,

@@ -249,7 +249,14 @@ def reorth_update_dots(V, j0, j1, W, C1, C2, sign=-1.0, gate=None):
     return True
 
 
-_WRAPPERS = dict(col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm,
+def mode_contract_tc(M, pre, L, k, inp, out, alpha=1.0, shift=0.0, diag=None, epi_x=None, accumulate=False, dots=None,
+                     dots_row=None, gate=None):
+    d = M.shape[0]
+    mode_contract(M, d, d, pre, L * k, inp, out, alpha=alpha, shift=shift, diag=diag, epi_x=epi_x, accumulate=accumulate,
+                  dots=dots, dots_row=dots_row, gate=gate)
+
+
+_WRAPPERS = dict(mode_contract_tc=mode_contract_tc, mode_contract_tc_ok=lambda M, pre, L, k, X: False, col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm,
                  mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
                  tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,
