@@ -236,10 +236,13 @@ def mode_contract_tc(M, pre, L, k, inp, out, alpha=1.0, shift=0.0, diag=None, ep
                      dots_row=None, gate=None):
     """out[p, a, l, r] = alpha * sum_j M[a, j] inp[p, j, l, r] on the tensor cores (3xTF32); epilogue as mode_contract."""
     dt = torch.float32
-    lib().call("cola_mode_contract_tc_f32", ptr(M, dt), M.stride(0), M.shape[0], pre, L, k, ptr(inp, dt), ptr(out, dt),
-               ctypes.c_float(alpha), ctypes.c_float(shift), ptr(diag, dt) if diag is not None else None,
-               ptr(epi_x, dt) if epi_x is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
-               stream_ptr())
+
+    def p(x):   # tensors or ready-made pointers (row blocks of a BlockDiag operand)
+        return x if (x is None or isinstance(x, ctypes.c_void_p)) else ptr(x, dt)
+
+    lib().call("cola_mode_contract_tc_f32", ptr(M, dt), M.stride(0), M.shape[0], pre, L, k, p(inp), p(out),
+               ctypes.c_float(alpha), ctypes.c_float(shift), p(diag), p(epi_x), int(accumulate), ptr(dots), ptr(dots_row),
+               ptr(gate), stream_ptr())
 
 
 def reorth_dots(V, j0, j1, W, C, gate=None):

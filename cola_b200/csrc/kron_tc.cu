@@ -16,7 +16,7 @@
 // measured in scripts/umma_rate.cu: 79 cycles per 128xNx8 tf32 MMA for N <= 128 (MN-major A in shared memory).
 //
 // Two kernels: kron_fused4_tc_kernel (2-3 factors: the whole matmat in ONE persistent cooperative launch, see its
-// header) and kron_mode_tc_kernel (one launch per (32-column chunk, mode): more than 3 factors, KronSum).
+// header) and mode_tc_kernel (one mode per launch, factor size 64 or 128: longer or mixed chains, KronSum, BlockDiag).
 #include <cuda.h>
 
 #include <cstdio>
@@ -27,29 +27,10 @@
 
 namespace cola {
 
-constexpr int kTcThreads = 384;
-constexpr int kD = 64;                 // factor size handled by this path
+constexpr int kD = 64;                 // factor size of the fused path
 constexpr int kAtomBytes = 64 * 128;   // one TMA box: 64 rows (j) x 32 floats
 constexpr int kTileBytes = 4 * kAtomBytes;   // 32 KB: 128 positions x 64 j
-constexpr int kStages = 2;
 constexpr int kFacBytes = kD * kD * 4;       // 16 KB
-// shared memory map (all 1024-byte aligned for the 128B swizzle)
-constexpr int kOffFacHi = 0;
-constexpr int kOffFacLo = kOffFacHi + kFacBytes;
-constexpr int kOffStage = kOffFacLo + kFacBytes;                 // per stage: hi tile | lo tile
-constexpr int kOffBars = kOffStage + kStages * 2 * kTileBytes;
-constexpr int kSmemBytes = kOffBars + 256 + 1024;                // + alignment slack
-
-struct TcArgs {
-  float* out; const float* epi_x; const float* diag;
-  int64_t L, pre;           // in viewed as (pre, 64, L, row) with row = in_k floats
-  int64_t in_r0;            // first column of the 32-wide RHS chunk inside the source rows (TMA coordinate 0)
-  int64_t out_k, out_r0;    // row length of the destination and column offset of the chunk inside it
-  int64_t n_tiles;          // pre * L / 4
-  float alpha, shift; int accumulate; int last_mode;
-  double* dots; const int32_t* dots_row; const int32_t* gate;
-  int dbg;   // bring-up knob (COLA_KRON_DBG): 1 = skip split math, 2 = skip MMAs, 4 = skip epilogue stores
-};
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,211 +122,6 @@ __device__ __forceinline__ float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-// elementwise 3xTF32 split of `bytes` of swizzled operand data: hi in place, lo into the twin buffer
-__device__ __forceinline__ void split_hi_lo(unsigned char* hi, unsigned char* lo, int bytes, int tid, int nthreads) {
-  for (int o = tid * 16; o < bytes; o += nthreads * 16) {
-    float4 v = *reinterpret_cast<float4*>(hi + o);
-    float4 h, l;
-    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-    *reinterpret_cast<float4*>(hi + o) = h;
-    *reinterpret_cast<float4*>(lo + o) = l;
-  }
-}
-
-__global__ void __launch_bounds__(kTcThreads, 1)
-    kron_mode_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_fac,
-                        TcArgs a) {
-  if (a.gate != nullptr && *a.gate != 0) return;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  const uint32_t sbase = smem_u32(smem);
-  // barriers
-  const uint32_t bar_full0 = sbase + kOffBars;            // [stage] TMA landed
-  const uint32_t bar_ready0 = bar_full0 + 8 * kStages;     // [stage] split done (count 4: one per split warp)
-  const uint32_t bar_empty0 = bar_ready0 + 8 * kStages;    // [stage] MMAs that read the stage retired
-  const uint32_t bar_tfull0 = bar_empty0 + 8 * kStages;    // [acc]   accumulator complete
-  const uint32_t bar_tempty0 = bar_tfull0 + 8 * 2;         // [acc]   accumulator drained (count 4)
-  const uint32_t bar_fac = bar_tempty0 + 8 * 2;            // factor landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBars + 200);
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(bar_full0 + 8 * s, 1);
-      mbar_init(bar_ready0 + 8 * s, 4);
-      mbar_init(bar_empty0 + 8 * s, 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_tfull0 + 8 * s, 1);
-      mbar_init(bar_tempty0 + 8 * s, 4);
-    }
-    mbar_init(bar_fac, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  // factor: TMA (2 boxes of 32 k x 64 rows), then everybody splits it into hi/lo
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar_fac, kFacBytes);
-    tma_load_2d(sbase + kOffFacHi, &map_fac, bar_fac, 0, 0);
-    tma_load_2d(sbase + kOffFacHi + kFacBytes / 2, &map_fac, bar_fac, 32, 0);
-  }
-  mbar_wait(bar_fac, 0);
-  split_hi_lo(smem + kOffFacHi, smem + kOffFacLo, kFacBytes, threadIdx.x, kTcThreads);
-  fence_async_smem();
-  __syncthreads();
-
-  const int64_t first = blockIdx.x, step = gridDim.x;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
-      for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(bar_empty0 + 8 * s, ph ^ 1);
-        mbar_expect_tx(bar_full0 + 8 * s, kTileBytes);
-        const uint32_t dst = sbase + kOffStage + s * 2 * kTileBytes;
-        for (int at = 0; at < 4; ++at) {
-          const int64_t flat = t * 4 + at;
-          const int64_t p = flat / a.L, l = flat - p * a.L;
-          tma_load_3d(dst + at * kAtomBytes, &map_in, bar_full0 + 8 * s, (int)a.in_r0, (int)l, (int)(p * kD));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      int it = 0;
-      for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        const int acc = it & 1;
-        const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(bar_tempty0 + 8 * acc, aph ^ 1);
-        mbar_wait(bar_ready0 + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t a_hi = sbase + kOffStage + s * 2 * kTileBytes, a_lo = a_hi + kTileBytes;
-        const uint32_t b_hi = sbase + kOffFacHi, b_lo = sbase + kOffFacLo;
-        const uint32_t d = tmem_base + acc * kD;
-        uint32_t accum = 0;
-        if (!(a.dbg & 2))
-        // small terms first: A_lo*B_hi, A_hi*B_lo, then A_hi*B_hi
-#pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t A0 = (term == 0) ? a_lo : a_hi;
-          const uint32_t B0 = (term == 1) ? b_lo : b_hi;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            // A': MN-major SW128_BASE32B: rows (j) of 128 B, K groups of 4 rows 512 B apart (SBO), 8 rows per
-            // MMA step (1024 B); the four 32-position atoms along MN are 8 KB apart (LBO)
-            const uint64_t ad = make_desc(A0 + kk * 1024, kAtomBytes, 512, kLayoutSw128Base32);
-            // B': K-major, two 32-float k-chunks of 8 KB; 32 B per K step inside a chunk; 8-row groups 1 KB apart
-            const uint64_t bd = make_desc(B0 + (kk / 4) * (kFacBytes / 2) + (kk % 4) * 32, 16, 1024, kLayoutSw128);
-            umma_tf32(d, ad, bd, kIdesc, accum);
-            accum = 1;
-          }
-        }
-        umma_commit(bar_empty0 + 8 * s);     // stage may be refilled once these MMAs retire
-        umma_commit(bar_tfull0 + 8 * acc);   // accumulator ready for the epilogue
-      }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===== operand split: raw fp32 tile -> hi (in place) + lo =====
-    const int tid = threadIdx.x - 128;
-    int it = 0;
-    for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
-      const int s = it % kStages;
-      const uint32_t ph = (it / kStages) & 1;
-      mbar_wait(bar_full0 + 8 * s, ph);
-      unsigned char* hi = smem + kOffStage + s * 2 * kTileBytes;
-      if (!(a.dbg & 1)) split_hi_lo(hi, hi + kTileBytes, kTileBytes, tid, 128);
-      fence_async_smem();     // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ready0 + 8 * s);
-    }
-  } else if (warp >= 8) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int q = warp - 8;                 // TMEM lane quadrant == atom index within the tile
-    double dacc = 0.0;
-    int it = 0;
-    for (int64_t t = first; t < a.n_tiles; t += step, ++it) {
-      const int acc = it & 1;
-      const uint32_t aph = (it >> 1) & 1;
-      const int64_t flat = t * 4 + q;
-      const int64_t p = flat / a.L, l = flat - p * a.L;
-      // element (a, r) of this atom lives at base + a * row_stride + r
-      const int64_t row_stride = a.L * a.out_k;
-      const int64_t base = (p * kD * a.L + l) * a.out_k + a.out_r0 + lane;
-      mbar_wait(bar_tfull0 + 8 * acc, aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kD;
-      const float* __restrict__ xin = a.epi_x;
-      const float* __restrict__ dg = a.diag;
-      float* __restrict__ outp = a.out;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c * 16, v);
-        // operands of the fused epilogue are requested while the TMEM load is in flight (independent loads,
-        // all issued before the first use)
-        float xv[16], dv[16], ov[16];
-        if (a.last_mode) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int64_t o = base + (int64_t)(c * 16 + i) * row_stride;
-            xv[i] = xin ? xin[o] : 0.f;
-            dv[i] = dg ? dg[(p * kD + c * 16 + i) * a.L + l] : 0.f;
-            ov[i] = a.accumulate ? outp[o] : 0.f;
-          }
-        }
-        tmem_ld_wait();
-        if (c == 3) {   // accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);
-        }
-        if (a.dbg & 4) continue;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int64_t o = base + (int64_t)(c * 16 + i) * row_stride;
-          float y = a.alpha * __uint_as_float(v[i]);
-          if (a.last_mode) {
-            if (xin != nullptr) {
-              if (a.shift != 0.f) y += a.shift * xv[i];
-              if (dg != nullptr) y += dv[i] * xv[i];
-            }
-            if (a.accumulate) y += ov[i];
-            // <x, y> of the value that is stored, earlier terms of a Sum included (same contract as the SIMT and CSR
-            // epilogues: the dots are those of the whole operator)
-            if (xin != nullptr && a.dots != nullptr) dacc += (double)xv[i] * (double)y;
-          }
-          outp[o] = y;
-        }
-      }
-    }
-    if (a.dots != nullptr) {
-      double* outp = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.out_k : 0);
-      atomicAdd(outp + a.out_r0 + lane, dacc);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
-  }
-}
-
 // ---- shared by the fused kernel ------------------------------------------------------------------------------
 constexpr int kMaxFused = 3;
 constexpr int kFusedMaxPhases = 256;
@@ -662,32 +438,41 @@ __global__ void __launch_bounds__(kF4Threads, 1)
           dacc = 0.0;
           dacc_r0 = out_r0;
         }
-        float xv[32];
-        if (fused) {                                           // requested before the accumulator wait
+        // y starts as what the result is accumulated onto (earlier terms of a Sum already in Y) or zero; x (fused last
+        // mode) and those old values are requested BEFORE the accumulator wait -- read in the store loop they would queue
+        // behind every store (possible aliasing) at one exposed latency each
+        float xv[32], y[32];
+        if (fused) {
           const float* px = xin + base;
 #pragma unroll
           for (int i = 0; i < 32; ++i, px += row_stride) xv[i] = *px;
         }
+        if (accumulate) {
+          const float* po_ = outp + base;
+#pragma unroll
+          for (int i = 0; i < 32; ++i, po_ += row_stride) y[i] = *po_;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] = 0.f;
+        }
         F3_TIMED(0, mbar_wait(bar_tfull0 + 8 * acc, par));
         tc_fence_after();
-        float y[32];
-        {
-          uint32_t v[32], w[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + h * 32;
-          tmem_ld16_at<0>(taddr, v);
-          tmem_ld16_at<1>(taddr, v);
-          tmem_ld16_at<0>(taddr + 64, w);
-          tmem_ld16_at<1>(taddr + 64, w);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + h * 32;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {                 // A_hi F_hi + A_lo F_hi (columns 0-63), then A_hi F_lo (64-127)
+          uint32_t v[32];
+          tmem_ld16_at<0>(taddr + half * 64, v);
+          tmem_ld16_at<1>(taddr + half * 64, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) y[i] = alpha * (__uint_as_float(v[i]) + __uint_as_float(w[i]));
+          for (int i = 0; i < 32; ++i) y[i] += alpha * __uint_as_float(v[i]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);      // accumulator back to the MMA warp
         if (a.dbg & 4) continue;
         float* po = outp + base;
-        if (!fused && !accumulate) {
+        if (!fused) {
 #pragma unroll
           for (int i = 0; i < 32; ++i, po += row_stride) *po = y[i];
         } else {
@@ -698,14 +483,10 @@ __global__ void __launch_bounds__(kF4Threads, 1)
           float facc = 0.f;
 #pragma unroll
           for (int i = 0; i < 32; ++i, po += row_stride) {
-            float yy = y[i];
-            if (fused) {
-              float sd = a.shift;
-              if (pd != nullptr) sd += pd[i * dstride];
-              yy += sd * xv[i];
-            }
-            if (accumulate) yy += *po;
-            if (fused) facc += xv[i] * yy;                      // of the stored value: earlier terms of a Sum included
+            float sd = a.shift;
+            if (pd != nullptr) sd += pd[i * dstride];
+            const float yy = y[i] + sd * xv[i];
+            facc += xv[i] * yy;                                 // of the stored value: earlier terms of a Sum included
             *po = yy;
           }
           dacc += (double)facc;
@@ -967,34 +748,35 @@ __global__ void __launch_bounds__(kMtThreads, 1)
       for (int g = 0; g < kGroups; ++g) {
         const int a0 = hw * (KD / 2) + g * 32;                   // first output index of the group
         const int64_t base = ((p * KD + a0) * a.L + l) * a.k + cc * 32 + lane;
-        float xv[32];
-        if (fused) {                                             // requested before the accumulator wait
+        // as in the fused kernel: y starts as the values accumulated onto (or zero), x and those values are requested
+        // before the accumulator wait
+        float xv[32], y[32];
+        if (fused) {
           const float* px = xin + base;
 #pragma unroll
           for (int i = 0; i < 32; ++i, px += row_stride) xv[i] = *px;
+        }
+        if (a.accumulate) {
+          const float* po_ = outp + base;
+#pragma unroll
+          for (int i = 0; i < 32; ++i, po_ += row_stride) y[i] = *po_;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] = 0.f;
         }
         if (g == 0) {
           mbar_wait(bar_tfull0 + 8 * acc, par);
           tc_fence_after();
         }
-        float y[32];
-        {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + (KD == 64 ? hw * 32 : a0);
+#pragma unroll
+        for (int half = 0; half < (KD == 64 ? 2 : 1); ++half) {  // KD = 64: the stacked accumulator halves add up
           uint32_t v[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + (KD == 64 ? hw * 32 : a0);
-          tmem_ld16_at<0>(taddr, v);
-          tmem_ld16_at<1>(taddr, v);
-          if constexpr (KD == 64) {
-            uint32_t w[32];
-            tmem_ld16_at<0>(taddr + 64, w);
-            tmem_ld16_at<1>(taddr + 64, w);
-            tmem_ld_wait();
+          tmem_ld16_at<0>(taddr + half * 64, v);
+          tmem_ld16_at<1>(taddr + half * 64, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = a.alpha * (__uint_as_float(v[i]) + __uint_as_float(w[i]));
-          } else {
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) y[i] = a.alpha * __uint_as_float(v[i]);
-          }
+          for (int i = 0; i < 32; ++i) y[i] += a.alpha * __uint_as_float(v[i]);
         }
         if (g == kGroups - 1) {
           tc_fence_before();
@@ -1002,22 +784,18 @@ __global__ void __launch_bounds__(kMtThreads, 1)
           if (lane == 0) mbar_arrive(bar_tempty0 + 8 * acc);     // accumulator back to the MMA warp
         }
         float* po = outp + base;
-        if (!fused && !a.accumulate) {
+        if (!fused) {
 #pragma unroll
           for (int i = 0; i < 32; ++i, po += row_stride) *po = y[i];
         } else {
-          const float* pd = (fused && dg != nullptr) ? dg + (p * KD + a0) : nullptr;     // L == 1 when fused
+          const float* pd = (dg != nullptr) ? dg + (p * KD + a0) : nullptr;     // L == 1 when fused
           float facc = 0.f;                                      // fp32 over the 32 values, fp64 across (see the fused kernel)
 #pragma unroll
           for (int i = 0; i < 32; ++i, po += row_stride) {
-            float yy = y[i];
-            if (fused) {
-              float sd = a.shift;
-              if (pd != nullptr) sd += pd[i];
-              yy += sd * xv[i];
-            }
-            if (a.accumulate) yy += *po;
-            if (fused) facc += xv[i] * yy;
+            float sd = a.shift;
+            if (pd != nullptr) sd += pd[i];
+            const float yy = y[i] + sd * xv[i];
+            facc += xv[i] * yy;
             *po = yy;
           }
           dacc += (double)facc;
@@ -1089,15 +867,14 @@ int64_t cola_kron_tc_workspace_bytes(int64_t n, int64_t n_factors) {
 }
 
 int cola_kron_tc_supported(int64_t n_factors, const int64_t* dims, int64_t k) {
-  if (n_factors < 1 || n_factors > 8 || k < 32 || k % 32 != 0) return 0;
+  if (n_factors < 2 || n_factors > kMaxFused || k < 32 || k % 32 != 0) return 0;   // longer chains: per-mode kernel
   int64_t n = 1;
   for (int64_t i = 0; i < n_factors; ++i) {
     if (dims[i] != kD) return 0;
     n *= kD;
   }
   // tiles are groups of 4 atoms: pre*L must be a multiple of 4 for every mode, i.e. n/64 % 4 == 0
-  if (n_factors == 1) return 0;   // a single 64x64 dense factor: plain GEMM path
-  return ((n / kD) % 4 == 0) ? 1 : 0;
+  return ((n / kD) % 4 == 0 && k / 32 * n_factors <= kFusedMaxPhases) ? 1 : 0;
 }
 
 int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
@@ -1105,7 +882,7 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
                             int accumulate, double* dots, const int32_t* dots_row, const int32_t* gate,
                             void* stream) {
   COLA_REQUIRE(factors && ldf && X && Y, "kron_tc: null pointer");
-  COLA_REQUIRE(n_factors >= 2 && n_factors <= 8, "kron_tc: 2..8 factors of 64x64");
+  COLA_REQUIRE(n_factors >= 2 && n_factors <= kMaxFused, "kron_tc: 2..3 factors of 64x64");
   COLA_REQUIRE(k >= 32 && k % 32 == 0, "kron_tc: k must be a multiple of 32");
   COLA_REQUIRE(workspace, "kron_tc: workspace required (cola_kron_tc_workspace_bytes)");
   COLA_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0) && ((uintptr_t)workspace % 128 == 0),
@@ -1113,15 +890,7 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int64_t n = 1;
   for (int64_t i = 0; i < n_factors; ++i) n *= kD;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kron_mode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
-  }
-  float* ws0 = workspace;
-  float* ws1 = workspace + n * 32;
-  static const bool no_fused = getenv("COLA_KRON_NO_FUSED") != nullptr;   // A/B knob: one launch per (chunk, mode)
-  if (n_factors <= kMaxFused && !no_fused) {
+  {
     // ---- fused kernel: one cooperative launch for the whole matmat
     // chunk width: 64 columns when the block splits into pairs of them (measured on cfg3: 145 us vs 151 us for 32),
     // else 32; COLA_KRON_CPC overrides (1, 2, 4 blocks of 32 columns)
@@ -1213,103 +982,7 @@ int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, cons
       return cuda_status("kron_fused4_tc");
     }
   }
-  CUtensorMap fac_maps[8];
-  for (int64_t i = 0; i < n_factors; ++i) {
-    COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kron_tc: factor alignment");
-    int rc = make_map_fac(&fac_maps[i], factors[i], ldf[i]);
-    if (rc) return rc;
-  }
-  const int grid_max = sm_count();
-  // One 32-column chunk of right-hand sides at a time through ALL modes: the two chunk-sized intermediates
-  // (n*32 floats = 33.5 MB for n = 64^3) ping-pong inside L2, only X (in) and Y (out) stream through HBM.
-  for (int64_t r0 = 0; r0 < k; r0 += 32) {
-    const float* src = X;
-    int64_t src_k = k, src_r0 = r0;       // the chunk inside X is strided (row length k); intermediates are dense (32)
-    for (int64_t i = 0; i < n_factors; ++i) {
-      const bool last = (i == n_factors - 1);
-      int64_t pre = 1, L = 1;
-      for (int64_t j = 0; j < i; ++j) pre *= kD;
-      for (int64_t j = i + 1; j < n_factors; ++j) L *= kD;
-      float* dst = last ? Y : ((i % 2 == 0) ? ws0 : ws1);
-      CUtensorMap map_in;
-      int rc = make_map_in(&map_in, src, pre, L, src_k);
-      if (rc) return rc;
-      TcArgs a;
-      a.out = dst; a.epi_x = nullptr; a.diag = nullptr; a.L = L; a.pre = pre;
-      a.in_r0 = src_r0; a.out_k = last ? k : 32; a.out_r0 = last ? r0 : 0;
-      a.n_tiles = pre * L / 4; a.alpha = last ? alpha : 1.f; a.shift = 0.f; a.accumulate = 0;
-      a.last_mode = last ? 1 : 0; a.dots = nullptr; a.dots_row = dots_row; a.gate = gate;
-      static const int dbg = getenv("COLA_KRON_DBG") ? atoi(getenv("COLA_KRON_DBG")) : 0;
-      a.dbg = dbg;
-      if (last) {
-        const bool epi = (shift != 0.f) || diag || dots;
-        a.epi_x = epi ? X : nullptr; a.diag = diag; a.shift = shift; a.accumulate = accumulate; a.dots = dots;
-      }
-      const int64_t grid = a.n_tiles < grid_max ? a.n_tiles : grid_max;
-      kron_mode_tc_kernel<<<(unsigned)grid, kTcThreads, kSmemBytes, st>>>(map_in, fac_maps[i], a);
-      rc = cuda_status("kron_mode_tc");
-      if (rc) return rc;
-      src = dst; src_k = a.out_k; src_r0 = a.out_r0;
-    }
-  }
-  return COLA_OK;
-}
-
-int cola_kronsum_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
-                               float* Y, int64_t k, float alpha, float shift, const float* diag, int accumulate,
-                               double* dots, const int32_t* dots_row, const int32_t* gate, void* stream) {
-  COLA_REQUIRE(factors && ldf && X && Y, "kronsum_tc: null pointer");
-  COLA_REQUIRE(X != Y, "kronsum_tc: X and Y must not alias");
-  COLA_REQUIRE(n_factors >= 2 && n_factors <= 8, "kronsum_tc: 2..8 factors of 64x64");
-  COLA_REQUIRE(k >= 32 && k % 32 == 0, "kronsum_tc: k must be a multiple of 32");
-  COLA_REQUIRE(((uintptr_t)X % 16 == 0) && ((uintptr_t)Y % 16 == 0), "kronsum_tc: X/Y must be 16-byte aligned");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  int64_t n = 1;
-  for (int64_t i = 0; i < n_factors; ++i) n *= kD;
-  COLA_REQUIRE((n / kD) % 4 == 0, "kronsum_tc: n / 64 must be a multiple of 4");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(kron_mode_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    attr_set = true;
-  }
-  CUtensorMap fac_maps[8], in_maps[8];
-  int64_t pres[8], Ls[8];
-  for (int64_t i = 0; i < n_factors; ++i) {
-    COLA_REQUIRE(((uintptr_t)factors[i] % 16 == 0) && (ldf[i] % 4 == 0), "kronsum_tc: factor alignment");
-    int rc = make_map_fac(&fac_maps[i], factors[i], ldf[i]);
-    if (rc) return rc;
-    pres[i] = 1; Ls[i] = 1;
-    for (int64_t j = 0; j < i; ++j) pres[i] *= kD;
-    for (int64_t j = i + 1; j < n_factors; ++j) Ls[i] *= kD;
-    rc = make_map_in(&in_maps[i], X, pres[i], Ls[i], k);      // every mode contracts X itself
-    if (rc) return rc;
-  }
-  const int grid_max = sm_count();
-  const bool epi = (shift != 0.f) || diag || dots;
-  // A 32-column chunk of right-hand sides goes through ALL modes before the next one starts: its slice of X
-  // (n*32 floats) is fetched from HBM by the first mode and found in L2 by the others, its slice of Y is
-  // read-modified in L2, so the sum of D contractions moves about what one does.
-  for (int64_t r0 = 0; r0 < k; r0 += 32) {
-    for (int64_t i = 0; i < n_factors; ++i) {
-      const bool last = (i == n_factors - 1);
-      TcArgs a;
-      a.out = Y; a.L = Ls[i]; a.pre = pres[i];
-      a.in_r0 = r0; a.out_k = k; a.out_r0 = r0;
-      a.n_tiles = pres[i] * Ls[i] / 4; a.alpha = alpha;
-      a.last_mode = 1;                                         // epilogue indexing is mode-independent
-      a.accumulate = (i > 0 || accumulate) ? 1 : 0;
-      a.epi_x = (last && epi) ? X : nullptr;
-      a.shift = last ? shift : 0.f; a.diag = last ? diag : nullptr;
-      a.dots = last ? dots : nullptr; a.dots_row = dots_row; a.gate = gate;
-      static const int dbg = getenv("COLA_KRON_DBG") ? atoi(getenv("COLA_KRON_DBG")) : 0;
-      a.dbg = dbg;
-      const int64_t grid = a.n_tiles < grid_max ? a.n_tiles : grid_max;
-      kron_mode_tc_kernel<<<(unsigned)grid, kTcThreads, kSmemBytes, st>>>(in_maps[i], fac_maps[i], a);
-      int rc = cuda_status("kronsum_mode_tc");
-      if (rc) return rc;
-    }
-  }
-  return COLA_OK;
+  return fail(COLA_E_UNSUPPORTED, "kron_tc: too many column chunks for one launch (use cola_mode_contract_tc_f32 per mode)");
 }
 
 int cola_mode_contract_tc_supported(int64_t d, int64_t pre, int64_t L, int64_t k) {

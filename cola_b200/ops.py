@@ -822,37 +822,33 @@ class _KronSumCore:
         self.use_tensor_cores = True   # set False to force the exact-fp32 SIMT contractions (A/B checks)
 
     def _tc_ok(self, X):
-        """fp32, every factor 64x64, k % 32 == 0: the tcgen05 per-mode kernel (csrc/kron_tc.cu)."""
-        if X.dtype != torch.float32 or len(self.Fs) < 2 or any(tuple(f.shape) != (64, 64) for f in self.Fs):
-            return False
-        dims = (ctypes.c_int64 * len(self.Fs))(*[64] * len(self.Fs))
-        return bool(be.lib().cdll.cola_kron_tc_supported(len(self.Fs), dims, X.shape[1]))
-
-    def _apply_tc(self, X, Y, epi):
-        D = len(self.Fs)
-        facs = (ctypes.c_void_p * D)(*[f.data_ptr() for f in self.Fs])
-        ldf = (ctypes.c_int64 * D)(*[f.stride(0) for f in self.Fs])
-        be.lib().call("cola_kronsum_matmat_tc_f32", D, facs, ldf, be.ptr(X), be.ptr(Y), X.shape[1],
-                      ctypes.c_float(epi.alpha), ctypes.c_float(epi.shift),
-                      be.ptr(epi.diag) if epi.diag is not None else None, int(epi.accumulate), be.ptr(epi.dots),
-                      be.ptr(epi.dots_row), be.ptr(epi.gate), be.stream_ptr())
+        """True when every mode of this application takes the per-mode tcgen05 kernel."""
+        dims = [f.shape[0] for f in self.Fs]
+        return all(be.mode_contract_tc_ok(F, _prod(dims[:i]) if i else 1, _prod(dims[i + 1:]) if i + 1 < len(dims) else 1,
+                                          X.shape[1], X) for i, F in enumerate(self.Fs))
 
     def apply(self, X, Y, epi):
-        if self.use_tensor_cores and self._tc_ok(X):
-            return self._apply_tc(X, Y, epi)
+        """Every mode contracts X itself and accumulates into Y; the last one carries the operator epilogue.  Square 64- /
+        128-wide fp32 factors with k % 32 == 0 run on the per-mode tcgen05 kernel (csrc/kron_tc.cu, mode_tc_kernel)."""
         k = X.shape[1]
         dims = [f.shape[0] for f in self.Fs]
         D = len(dims)
         for i, F in enumerate(self.Fs):
             pre = _prod(dims[:i]) if i > 0 else 1
-            post = (_prod(dims[i + 1:]) if i + 1 < D else 1) * k
+            L = _prod(dims[i + 1:]) if i + 1 < D else 1
             acc = epi.accumulate or i > 0
+            tc = self.use_tensor_cores and be.mode_contract_tc_ok(F, pre, L, k, X)
             if i == D - 1:
                 kw = epi.kw()
                 kw["accumulate"] = acc
-                be.mode_contract(F, dims[i], dims[i], pre, post, X, Y, epi_x=X if epi.needs_x() else None, **kw)
+                if tc:
+                    be.mode_contract_tc(F, pre, L, k, X, Y, epi_x=X if epi.needs_x() else None, **kw)
+                else:
+                    be.mode_contract(F, dims[i], dims[i], pre, L * k, X, Y, epi_x=X if epi.needs_x() else None, **kw)
+            elif tc:
+                be.mode_contract_tc(F, pre, L, k, X, Y, alpha=epi.alpha, accumulate=acc, gate=epi.gate)
             else:
-                be.mode_contract(F, dims[i], dims[i], pre, post, X, Y, alpha=epi.alpha, accumulate=acc, gate=epi.gate)
+                be.mode_contract(F, dims[i], dims[i], pre, L * k, X, Y, alpha=epi.alpha, accumulate=acc, gate=epi.gate)
 
 
 class _BlockDiagCore:
@@ -870,8 +866,12 @@ class _BlockDiagCore:
             kw = epi.kw()
             if kw.get("diag") is not None:
                 kw["diag"] = be.off_ptr(epi.diag, ro)
-            be.mode_contract(M, M.shape[0], M.shape[1], c, k, be.off_ptr(X, ri * k), be.off_ptr(Y, ro * k),
-                             epi_x=be.off_ptr(X, ri * k) if epi.needs_x() else None, **kw)
+            if be.mode_contract_tc_ok(M, c, 1, k, X):          # square 64- / 128-wide fp32 blocks: tcgen05 per-mode kernel
+                be.mode_contract_tc(M, c, 1, k, be.off_ptr(X, ri * k), be.off_ptr(Y, ro * k),
+                                    epi_x=be.off_ptr(X, ri * k) if epi.needs_x() else None, **kw)
+            else:
+                be.mode_contract(M, M.shape[0], M.shape[1], c, k, be.off_ptr(X, ri * k), be.off_ptr(Y, ro * k),
+                                 epi_x=be.off_ptr(X, ri * k) if epi.needs_x() else None, **kw)
             ri += c * M.shape[1]
             ro += c * M.shape[0]
 

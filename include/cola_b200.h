@@ -97,26 +97,17 @@ int cola_mode_contract_f64(const double* M, int64_t ldm, int64_t d_out, int64_t 
 /* Kronecker matmat on the tensor cores: Y = alpha * (F_1 (x) ... (x) F_D) X (+ epilogue), every factor 64x64
  * fp32 row-major with leading dimension ldf[i], X / Y (64^D, k) row-major with k a multiple of 32.
  * tcgen05.mma kind::tf32 with 3xTF32 error compensation (fp32-grade accuracy), TMEM accumulators, TMA-staged
- * 128B-swizzled tiles; all D mode contractions run on one 32-column chunk of right-hand sides at a time so the
- * intermediates stay in L2.  Replaces Kronecker._matmat (operators.py:216-223) for the GP-kernel shapes of
- * BASELINE config 3.  `factors` / `ldf` are HOST arrays (of device pointers / of leading dimensions);
- * `workspace` is a device buffer of cola_kron_tc_workspace_bytes(n, D) bytes, 128-byte aligned.
- * cola_kron_tc_supported returns 1 when the shapes qualify (otherwise use cola_mode_contract_*). */
+ * 128B-swizzled tiles; all D mode contractions of all column chunks in ONE cooperative launch (2 <= D <= 3).  Replaces
+ * Kronecker._matmat (operators.py:216-223) for the GP-kernel shapes of BASELINE config 3.  `factors` / `ldf` are HOST
+ * arrays (of device pointers / of leading dimensions); `workspace` is a device buffer of
+ * cola_kron_tc_workspace_bytes(n, D) bytes, 128-byte aligned.  cola_kron_tc_supported returns 1 when the shapes
+ * qualify (otherwise: cola_mode_contract_tc_f32 / cola_mode_contract_* per mode). */
 int cola_kron_tc_supported(int64_t n_factors, const int64_t* dims, int64_t k);
 int64_t cola_kron_tc_workspace_bytes(int64_t n, int64_t n_factors);
 int cola_kron_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
                             float* Y, int64_t k, float* workspace, float alpha, float shift, const float* diag,
                             int accumulate, double* dots, const int32_t* dots_row, const int32_t* gate,
                             void* stream);
-
-/* Kronecker SUM on the tensor cores: Y = alpha * (F_1 (+) ... (+) F_D) X (+ epilogue), same shapes and arithmetic as
- * cola_kron_matmat_tc_f32 (64x64 fp32 factors, k a multiple of 32, 3xTF32).  Each mode contracts X itself and
- * accumulates into Y, one 32-column chunk of right-hand sides through all modes at a time (X chunk and Y chunk stay
- * in L2 between modes); the last mode carries shift / diag / dots.  Replaces KronSum._matmat (operators.py:261-268:
- * a zero-initialised accumulator, D GEMMs and 2D moveaxis copies).  No workspace.  X and Y must not alias. */
-int cola_kronsum_matmat_tc_f32(int64_t n_factors, const float* const* factors, const int64_t* ldf, const float* X,
-                               float* Y, int64_t k, float alpha, float shift, const float* diag, int accumulate,
-                               double* dots, const int32_t* dots_row, const int32_t* gate, void* stream);
 
 /* One mode contraction on the tensor cores (tcgen05 3xTF32, same tiles as cola_kron_matmat_tc_f32) for a SQUARE factor of
  * size d = 64 or 128:  out[p, a, l, r] = alpha * sum_j M[a, j] in[p, j, l, r]  with in / out (pre, d, L, k) row-major,

@@ -51,8 +51,8 @@ def kronsum_matmat():
     alg = sum(d * d for d in dims) * 4 + 2 * n * k * 4
     emit(row="KronSum matmat (operators.py:261-268)", workload="KronSum(64,64,64) fp32, 128 RHS", ms=ms,
          algorithmic_GB=alg / 1e9, achieved_GBps=alg / ms / 1e6, frac_of_hbm=alg / ms / 1e6 / HBM,
-         note="tcgen05 per-mode kernel (3xTF32), 4 chunks of 32 RHS x 3 modes = 12 launches; a chunk of X / Y stays in L2 "
-              "between modes; operand 134 MB > L2")
+         note="tcgen05 per-mode kernel (mode_tc_kernel, 3xTF32), one launch per factor: each mode reads X and accumulates "
+              "into Y (moves (3D-1) blocks of 134 MB: 1.07 GB for D = 3); operand 134 MB > L2")
     core = A.plan().terms[0][1][0]
     core.use_tensor_cores = False
     ms = time_kernel(lambda: A.matmat_into(X, Y), reps=10)

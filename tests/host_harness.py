@@ -277,7 +277,6 @@ def emulated_kernels(fused=False):
     saved_lib, saved_stream, saved_graph = be.lib, be.stream_ptr, cg.USE_CUDA_GRAPH
     saved_gate, saved_ptr, saved_off = be.require_cuda, be.ptr, be.off_ptr
     saved_tc, saved_mem, saved_probe = ops._KronCore._tc_ok, torch.cuda.mem_get_info, rng.PROBE_DEVICE
-    saved_tc_sum = ops._KronSumCore._tc_ok
     try:
         for name, fn in _WRAPPERS.items():
             setattr(be, name, fn)
@@ -287,7 +286,6 @@ def emulated_kernels(fused=False):
         fake = _CgEntryPoints()
         be.lib, be.stream_ptr, cg.USE_CUDA_GRAPH = (lambda: fake), (lambda: None), False
         ops._KronCore._tc_ok = lambda self, X: False
-        ops._KronSumCore._tc_ok = lambda self, X: False
         torch.cuda.mem_get_info = lambda device=None: (64 << 30, 64 << 30)
         rng.PROBE_DEVICE = "cpu"
         _Fused.enabled = fused
@@ -298,5 +296,4 @@ def emulated_kernels(fused=False):
         be.require_cuda, be.ptr, be.off_ptr = saved_gate, saved_ptr, saved_off
         be.lib, be.stream_ptr, cg.USE_CUDA_GRAPH = saved_lib, saved_stream, saved_graph
         ops._KronCore._tc_ok, torch.cuda.mem_get_info, rng.PROBE_DEVICE = saved_tc, saved_mem, saved_probe
-        ops._KronSumCore._tc_ok = saved_tc_sum
         _Fused.enabled = False

@@ -198,7 +198,7 @@ def test_kronsum_tensor_core_path(cb):
             ref = ref + torch.moveaxis(torch.tensordot(F.double().to(DEV), torch.moveaxis(E, i, 0), dims=1), 0, i)
         ref = ref.reshape(n, k) + (0.1 + dg.double().to(DEV))[:, None] * X.double()
         assert rel(Y, ref) < 2e-6, (D, k, rel(Y, ref))
-        assert rel(dots, (X.double() * Y.double()).sum(0)) < 1e-12
+        assert rel(dots, (X.double() * Y.double()).sum(0)) < 1e-6    # fp32 partials over 32 values, fp64 across tiles
         core.use_tensor_cores = False
         Y2 = torch.empty_like(X)
         A.matmat_into(X, Y2)
