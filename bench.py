@@ -97,7 +97,9 @@ class ClockSampler:
     def __enter__(self):
         if os.environ.get("COLA_BENCH_NO_CLOCKS"):
             return self
-        period = float(os.environ.get("COLA_BENCH_CLOCK_MS", "100")) * 1e-3
+        # 4 samples per second: on some boxes an NVML query stalls kernel LAUNCHES for milliseconds (long kernels do not
+        # notice, graph replays and copy-stream hand-offs do: cfg3 measured 1650 vs 2350-2560 it/s, e2e 417 vs 463)
+        period = float(os.environ.get("COLA_BENCH_CLOCK_MS", "250")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -421,7 +423,7 @@ def _timed(fn):
 TF32_PEAK_TFLOPS = 1166.0   # 128*256*8 MAC / 130.8 cycles * 2 * 148 SMs * 1.965 GHz (profiles/r2_umma_rate.log)
 
 
-def secondary_cfg3(ctx, cb, iters=100, reps=10):
+def secondary_cfg3(ctx, cb, iters=100, reps=25):
     """BASELINE config 3 (every rank its own 128-RHS block; rank 0 reports its own rate x world = weak scaling)."""
     dev = ctx.dev
     lib = cb.backend.lib()

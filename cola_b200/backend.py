@@ -160,6 +160,37 @@ def read_small(t):
     return pin[:nbytes].clone().view(t.dtype).reshape(t.shape)
 
 
+_PINNED_RING = {}
+
+
+def publish_async(t):
+    """Stream-ordered, DMA-free snapshot of a small device tensor (see read_small) that the host picks up LATER with
+    publish_result: the Krylov loops enqueue the next batch of iterations before they look at the control block the previous
+    batch left, so the device never idles through a host round trip.  A ring of four pinned slots per (device, stream)."""
+    require_cuda(t, "a polled tensor")
+    if not t.is_contiguous():
+        t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    key = (t.device.index, torch.cuda.current_stream().cuda_stream)
+    ring = _PINNED_RING.get(key)
+    if ring is None:
+        ring = {"slots": [(torch.empty(4096, dtype=torch.uint8).pin_memory(), torch.cuda.Event()) for _ in range(4)], "next": 0}
+        _PINNED_RING[key] = ring
+    if nbytes > 4096:
+        raise ValueError("publish_async is for control blocks (<= 4 KB)")
+    pin, ev = ring["slots"][ring["next"]]
+    ring["next"] = (ring["next"] + 1) % 4
+    lib().call("cola_publish_bytes", ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(pin.data_ptr()), nbytes, stream_ptr())
+    ev.record()
+    return (pin, ev, nbytes, t.dtype, tuple(t.shape))
+
+
+def publish_result(token):
+    pin, ev, nbytes, dtype, shape = token
+    ev.synchronize()
+    return pin[:nbytes].clone().view(dtype).reshape(shape)
+
+
 def small_ints(values, device):
     """int32 device tensor of four values, written by a kernel from its arguments (cola_store_i32x4): no pageable
     H2D memcpy, which would queue behind a large transfer on the copy engine (see read_small)."""

@@ -239,14 +239,27 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
         loop = {"graph": ws["graph"] if ws else None, "batches": 0}
 
         def drive(limit):
-            """Enqueue gated batches until the device-side rule (or the iteration cap `limit`) stops the loop."""
+            """Enqueue gated batches until the device-side rule (or the iteration cap `limit`) stops the loop.  The control
+            block is snapshotted after every batch (stream-ordered, DMA-free) and read ONE BATCH LATER: the next batch is
+            already enqueued when the host waits for a snapshot, so the device does not idle through the host round trip
+            (event wake-up, Python, launch).  Iterations enqueued past the stopping point are device-side no-ops."""
+            c = be.read_small(ctl)
+            it, done = int(c[0]), int(c[1])
+            pending = []                                         # snapshots of batches enqueued but not looked at yet
             while True:
-                c = be.read_small(ctl)
-                it, done = int(c[0]), int(c[1])
                 if done:
                     return it
-                remaining = limit - it
-                if graph_ok and loop["graph"] is None and loop["batches"] >= 1 and remaining >= 2 * CHECK_EVERY:
+                if len(pending) >= 2 or (pending and it + len(pending) * CHECK_EVERY >= limit):
+                    c = be.publish_result(pending.pop(0))
+                    it, done = int(c[0]), int(c[1])
+                    continue
+                remaining = limit - it - len(pending) * CHECK_EVERY
+                want_capture = graph_ok and loop["graph"] is None and loop["batches"] >= 1 and remaining >= 2 * CHECK_EVERY
+                if want_capture and pending:                     # capturing synchronises anyway: look at what is in flight first
+                    c = be.publish_result(pending.pop(0))
+                    it, done = int(c[0]), int(c[1])
+                    continue
+                if want_capture:
                     # Every kernel reads the iteration index and the stop flag from the device control block, so a batch
                     # of iterations is the same launch sequence each time: capture it once, replay it (launch cost -> ~0).
                     # Iterations past the stopping point are device-side no-ops, exactly as in the eager batches.
@@ -269,8 +282,9 @@ def run_batched_cg(A, b, x0, max_iters, tol, preconditioner, pbar=False):
                 if loop["graph"] is not None:
                     loop["graph"].replay()
                 else:
-                    enqueue(min(CHECK_EVERY, remaining))
+                    enqueue(max(1, min(CHECK_EVERY, remaining)))
                 loop["batches"] += 1
+                pending.append(be.publish_async(ctl))
 
         it = drive(max_iters)
         group = STOP_RULE_GROUP if _world(STOP_RULE_GROUP) > 1 else None

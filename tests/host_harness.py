@@ -261,7 +261,7 @@ _WRAPPERS = dict(mode_contract_tc=mode_contract_tc, mode_contract_tc_ok=lambda M
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
                  tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,
                  sddmm_csr=sddmm_csr, row_dots=row_dots, gram_nt=gram_nt,
-                 read_small=lambda t: t.detach().clone(),
+                 read_small=lambda t: t.detach().clone(), publish_async=lambda t: t.detach().clone(), publish_result=lambda tok: tok,
                  small_ints=lambda values, device: torch.tensor([int(v) for v in values], dtype=torch.int32))      # cola_publish_bytes: a host copy of a few device bytes
 
 
