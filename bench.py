@@ -90,9 +90,26 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, background=True):
         self.index, self.rows, self.proc, self.thread, self.stop = index, [], None, None, threading.Event()
         self.source = None
+        # background=False: no sampling thread; the timed code calls .sample() itself at points of its choosing (still
+        # inside the timed region, under load).  For launch-latency-sensitive regions (CUDA-graph replays): an NVML query
+        # from a second thread stalled those by tens of milliseconds per sample on some boxes (cfg3: 1806-2326 it/s with
+        # the thread, 2442-2480 without, same box, back to back).
+        self.background = background
+        self._nvml = None
+
+    def sample(self):
+        if self._nvml is None:
+            return
+        pynvml, h, mx = self._nvml
+        try:
+            sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+            mask = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            self.rows.append((sm, mx, [n for n, bit in self.REASONS if mask & bit]))
+        except Exception:
+            pass
 
     def __enter__(self):
         if os.environ.get("COLA_BENCH_NO_CLOCKS"):
@@ -107,6 +124,10 @@ class ClockSampler:
             phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
             h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self._nvml = (pynvml, h, mx)
+            self.source = "nvml"
+            if not self.background:
+                return self
 
             def loop():
                 while not self.stop.is_set():
@@ -437,8 +458,15 @@ def secondary_cfg3(ctx, cb, iters=100, reps=25):
         alg(A, B)
     ctx.barrier()
     l0 = lib.launch_count()
-    with ClockSampler(ctx.local) as clocks:
-        s, (x, info) = _timed(lambda: [alg(A, B) for _ in range(reps)][-1])
+    with ClockSampler(ctx.local, background=False) as clocks:    # sampled from this thread, every fifth solve (see ClockSampler)
+        def solves():
+            out = None
+            for i in range(reps):
+                out = alg(A, B)
+                if i % 5 == 2:
+                    clocks.sample()
+            return out
+        s, (x, info) = _timed(solves)
     launches = lib.launch_count() - l0
     (s,) = ctx.max_over_ranks(s)
     if ctx.rank != 0:
