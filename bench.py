@@ -41,6 +41,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in some images) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 ITERS = 50          # CG iterations per solve (step)
 GRID = 2048         # cfg2 grid side
