@@ -378,4 +378,17 @@ def test_mode_contract_tensor_core_path(cb):
     A.matmat_into(X, Y2, dots=d2)
     core.use_tensor_cores = True
     assert rel(Y1, Y2) < 5e-6 and rel(d1, d2) < 5e-6
+    # BlockDiag with 64- / 128-wide blocks: one per-mode launch per distinct block (pre = multiplicity), epilogue offsets
+    B1, B2, B3 = Fs[1], Fs[0], (torch.randn(40, 40, generator=g) / 6 + torch.eye(40)).to(DEV)
+    BD = cb.ops.BlockDiag(cb.ops.Dense(B1), cb.ops.Dense(B2), cb.ops.Dense(B3), multiplicities=[4, 8, 3])
+    nb = 4 * 64 + 8 * 128 + 3 * 40
+    dgb = torch.rand(nb, generator=g).to(DEV)
+    Ab = BD + 0.5 * cb.ops.I_like(BD) + cb.ops.Diagonal(dgb)
+    Xb = torch.randn(nb, 64, generator=g).to(DEV)
+    Yb = torch.empty_like(Xb)
+    db = torch.zeros(64, dtype=torch.float64, device=DEV)
+    Ab.matmat_into(Xb, Yb, dots=db)
+    dense = torch.block_diag(*([B1.double()] * 4 + [B2.double()] * 8 + [B3.double()] * 3)) + torch.diag(0.5 + dgb.double())
+    refb = dense @ Xb.double()
+    assert rel(Yb, refb) < 3e-6 and rel(db, (Xb.double() * refb).sum(0)) < 3e-6
 
