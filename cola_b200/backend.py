@@ -243,6 +243,18 @@ def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shi
                stream_ptr())
 
 
+def csr_spmm_tiled(T, vals, shape, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False, dots=None, dots_row=None,
+                   gate=None):
+    """Staged SpMM from the tile-local form `T` (cola_b200.csr_tiles.CsrTiles); `vals` = T.values(data)."""
+    k = X.shape[1]
+    dt = vals.dtype
+    lib().call(f"cola_csr_spmm_tiled_{sfx(dt)}", ptr(T.rec, torch.int32), ptr(T.rp, torch.int32), ptr(T.idx, torch.int32),
+               ptr(vals), shape[0], T.n_tiles, T.n_tiles2d, T.rows2d, T.stride, T.strip_rows, T.strips, T.cap_rows, T.cap_nz,
+               ptr(X, dt), k, ptr(Y, dt), k, scalar(dt, alpha), scalar(dt, shift),
+               ptr(diag, dt) if diag is not None else None, int(accumulate), ptr(dots), ptr(dots_row), ptr(gate),
+               stream_ptr())
+
+
 def mode_contract(M, d_out, d_in, pre, post, inp, out, alpha=1.0, shift=0.0, diag=None, epi_x=None, accumulate=False,
                   dots=None, dots_row=None, gate=None):
     """inp/out/diag/epi_x are ctypes pointers or tensors (tensors are converted)."""

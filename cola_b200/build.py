@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libcola_b200.so")
-SOURCES = ["vec_kernels.cu", "csr_spmm.cu", "mode_contract.cu", "reorth.cu", "kron_tc.cu", "tridiag_eig.cu", "param_grad.cu"]
+SOURCES = ["vec_kernels.cu", "csr_spmm.cu", "csr_tiled.cu", "mode_contract.cu", "reorth.cu", "kron_tc.cu", "tridiag_eig.cu", "param_grad.cu"]
 HEADERS = ["common.cuh", "sweep.cuh", os.path.join("..", "..", "include", "cola_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]

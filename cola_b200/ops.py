@@ -690,12 +690,34 @@ class _CsrCore:
     COLUMN-BLOCKED: the pattern is cut once into vertical strips whose slice of X (SPMV_BLOCK_BYTES) stays resident in
     L2, and the strips are applied one after the other, each accumulating into Y; the CSR arrays still stream through
     once in total, Y is re-read per strip.  Row sums are then taken strip by strip (fp rounding order only)."""
+    TILE_STAGE_BYTES = int(os.environ.get("COLA_SPMM_TILE_KB", "100")) << 10    # X rows one ring stage of the staged kernel holds (0: off)
+    TILE_STRIP_ROWS = int(os.environ.get("COLA_SPMM_TILE_R", "0"))               # 0: from the stage size
     SPMV_BLOCK_BYTES = int(os.environ.get("COLA_SPMV_BLOCK_MB", "45")) << 20   # measured on cfg5 (2^24 nodes, fp64): 32 MB 2.53 ms, 45 MB 2.18 ms, 68 MB 2.89 ms; plain 3.99; cuSPARSE 2.97
 
     def __init__(self, S):
         self.S = S
         self.shape = tuple(S.shape)
         self._strips = {}
+        self._tiled = {}
+
+    def _tiles(self, X, Y):
+        """The tile-local form for the staged kernel (csrc/csr_tiled.cu), or None: rows of X of 128 B .. 4 KB, contiguous
+        blocks, a pattern whose tiles gather long column runs (stencil / banded: BASELINE config 2)."""
+        row_bytes = X.shape[1] * X.element_size()
+        if (self.TILE_STAGE_BYTES <= 0 or row_bytes % 16 or not 128 <= row_bytes <= 4096 or not X.is_contiguous()
+                or not Y.is_contiguous() or self.S.nnz == 0):
+            return None
+        if row_bytes not in self._tiled:
+            from .csr_tiles import CsrTiles, STRIPS
+            cap_rows = self.TILE_STAGE_BYTES // row_bytes
+            R = self.TILE_STRIP_ROWS
+            if R <= 0:                               # staged rows ~ 1.35 x the tile's own rows on a 5-point stencil
+                R = 8
+                while R * 2 * STRIPS * 1.35 <= cap_rows and R < 64:
+                    R *= 2
+            T = CsrTiles(self.S, R, cap_rows, row_bytes)
+            self._tiled[row_bytes] = T if T.worthwhile() else None
+        return self._tiled[row_bytes]
 
     def _column_strips(self, k, itemsize):
         """None (plain kernel), or [(indptr, indices, data, nnz)] per vertical strip, built on first use."""
@@ -729,6 +751,9 @@ class _CsrCore:
         S = self.S
         strips = self._column_strips(X.shape[1], X.element_size()) if X.shape[1] <= 4 else None
         if strips is None:
+            T = self._tiles(X, Y)
+            if T is not None:
+                return be.csr_spmm_tiled(T, T.values(S.data), S.shape, X, Y, **epi.kw())
             return be.csr_spmm(S.indptr, S.indices, S.data, S.shape, S.nnz, S.max_row_nnz, X, Y, **epi.kw())
         last = len(strips) - 1
         for b, (indptr, indices, data, nnz) in enumerate(strips):

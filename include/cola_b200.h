@@ -76,6 +76,27 @@ int cola_csr_spmm_f64(const int32_t* rowptr, const int32_t* colidx, const double
                       double shift, const double* diag, int accumulate, double* dots, const int32_t* dots_row,
                       const int32_t* gate, void* stream);
 
+/* Staged CSR SpMM for wide X blocks on patterns with long column runs (stencil / banded matrices; same replacement as
+ * cola_csr_spmm_*: Sparse._matmat, cola/ops/operators.py:77-78, + cg.py:157-158 through `dots`).  The pattern comes in
+ * the tile-local form cola_b200/csr_tiles.py builds once: a tile = `strips` strips of `strip_rows` consecutive rows,
+ * `stride` rows apart for the first n_tiles2d tiles (rows [0, rows2d)), consecutive rows after; rec = 32 int32 per tile
+ * [nz_begin, nz_padded (multiple of 4), n_runs (-1: gather from global), n_distinct, 0 x4, (col0, slot0<<16|len) x12];
+ * rp = 2*RT+4 int32 per tile (RT = strip_rows*strips): local row pointers [0,RT], n_runs again at [RT+3], the slot
+ * of each row's own X row at [RT+4, 2RT+4); idx = per non-zero the slot of its X row among the tile's staged
+ * rows (the column for irregular tiles); vals in the same padded order.  cap_rows / cap_nz = largest n_distinct /
+ * nz_padded of any tile (ring-stage size).  X and Y contiguous (ldx == k), k*sizeof(T) a multiple of 16.
+ * COLA_E_UNSUPPORTED when two ring stages do not fit shared memory. */
+int cola_csr_spmm_tiled_f32(const int32_t* rec, const int32_t* rp, const int32_t* idx, const float* vals, int64_t n_rows,
+                            int64_t n_tiles, int64_t n_tiles2d, int64_t rows2d, int64_t stride, int64_t strip_rows,
+                            int64_t strips, int64_t cap_rows, int64_t cap_nz, const float* X, int64_t k, float* Y, int64_t ldy,
+                            float alpha, float shift, const float* diag, int accumulate, double* dots,
+                            const int32_t* dots_row, const int32_t* gate, void* stream);
+int cola_csr_spmm_tiled_f64(const int32_t* rec, const int32_t* rp, const int32_t* idx, const double* vals, int64_t n_rows,
+                            int64_t n_tiles, int64_t n_tiles2d, int64_t rows2d, int64_t stride, int64_t strip_rows,
+                            int64_t strips, int64_t cap_rows, int64_t cap_nz, const double* X, int64_t k, double* Y,
+                            int64_t ldy, double alpha, double shift, const double* diag, int accumulate, double* dots,
+                            const int32_t* dots_row, const int32_t* gate, void* stream);
+
 /* Batched mode contraction  out[p,a,q] = alpha * sum_j M[a,j] in[p,j,q].
  * M is (d_out, d_in) row-major with leading dimension ldm.  `in` is (pre, d_in, post) contiguous,
  * `out` (pre, d_out, post) contiguous; they must not alias.

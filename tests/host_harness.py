@@ -92,6 +92,55 @@ def csr_spmm(rowptr, colidx, vals, shape, nnz, max_row_nnz, X, Y, alpha=1.0, shi
         _epilogue(KX, X, Y, alpha, shift, diag, accumulate, dots, dots_row)
 
 
+def csr_spmm_tiled(T, vals, shape, X, Y, alpha=1.0, shift=0.0, diag=None, accumulate=False, dots=None, dots_row=None,
+                   gate=None):
+    """What csrc/csr_tiled.cu computes, tile by tile FROM THE TILE-LOCAL FORM (records, runs, slots, local row pointers):
+    a wrong record shows up here as a wrong product."""
+    if not _open(gate):
+        return
+    n, k = shape[0], X.shape[1]
+    KX = torch.full((n, k), float("nan"), dtype=torch.float64)
+    RT = T.rows_per_tile
+    lr_all = torch.arange(RT)
+    for t in range(T.n_tiles):
+        rec = T.rec[t].tolist()
+        nzb, nr, nd = rec[0], rec[2], rec[3]
+        if nr >= 0:
+            runs = [(rec[8 + 2 * r], rec[9 + 2 * r] >> 16, rec[9 + 2 * r] & 0xFFFF) for r in range(nr)]
+            staged = torch.zeros((max(nd, 1), k), dtype=torch.float64)
+            for col0, slot0, ln in runs:
+                staged[slot0:slot0 + ln] = X[col0:col0 + ln].double()
+            assert sum(r[2] for r in runs) == nd and nd <= T.cap_rows
+            src = staged
+        else:
+            src = X.double()
+        rp = T.rp[t, :RT + 1].long()
+        assert int(T.rp[t, RT + 3]) == nr
+        cnt = rp[1:] - rp[:-1]
+        nnz_t = int(rp[RT])
+        assert nnz_t <= rec[1] <= T.cap_nz and rec[1] % 4 == 0 and nzb % 4 == 0
+        lrow_e = torch.repeat_interleave(lr_all, cnt)
+        e = slice(nzb, nzb + nnz_t)
+        sel = T.idx[e].long()
+        if nr >= 0:
+            assert k * X.element_size() == T.row_bytes and bool((sel % T.row_bytes == 0).all())
+            sel = sel // T.row_bytes
+        contrib = vals[e].double()[:, None] * src[sel]
+        Yt = torch.zeros((RT, k), dtype=torch.float64).index_add_(0, lrow_e, contrib)
+        rows = torch.tensor([T.row_of(t, lr) for lr in range(RT)])
+        ok = rows < n
+        assert int(cnt[~ok].sum()) == 0
+        if nr >= 0 and shape[0] == shape[1]:           # every row's own X row is staged (the fused epilogue reads it there)
+            assert torch.equal(staged[(T.rp[t, RT + 4:2 * RT + 4].long() // T.row_bytes)[ok]], X[rows[ok]].double())
+        KX[rows[ok]] = Yt[ok]
+    assert not bool(torch.isnan(KX).any()), "a row belongs to no tile"
+    KX = KX.to(X.dtype)
+    if shift == 0.0 and diag is None and dots is None:
+        Y.copy_(alpha * KX + Y if accumulate else alpha * KX)
+    else:
+        _epilogue(KX, X, Y, alpha, shift, diag, accumulate, dots, dots_row)
+
+
 def mode_contract(M, d_out, d_in, pre, post, inp, out, alpha=1.0, shift=0.0, diag=None, epi_x=None, accumulate=False,
                   dots=None, dots_row=None, gate=None):
     if not _open(gate):
@@ -256,7 +305,7 @@ def mode_contract_tc(M, pre, L, k, inp, out, alpha=1.0, shift=0.0, diag=None, ep
                   dots=dots, dots_row=dots_row, gate=gate)
 
 
-_WRAPPERS = dict(mode_contract_tc=mode_contract_tc, mode_contract_tc_ok=lambda M, pre, L, k, X: False, col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm,
+_WRAPPERS = dict(mode_contract_tc=mode_contract_tc, mode_contract_tc_ok=lambda M, pre, L, k, X: False, col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm, csr_spmm_tiled=csr_spmm_tiled,
                  mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
                  tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,

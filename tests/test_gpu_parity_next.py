@@ -392,3 +392,91 @@ def test_mode_contract_tensor_core_path(cb):
     refb = dense @ Xb.double()
     assert rel(Yb, refb) < 3e-6 and rel(db, (Xb.double() * refb).sum(0)) < 3e-6
 
+
+
+def _banded(n, offsets, dt, g):
+    """COO of a banded matrix with the given diagonals (random values, dominant main diagonal)."""
+    rows, cols, vals = [], [], []
+    for off in offsets:
+        r = torch.arange(max(0, -off), min(n, n - off))
+        rows.append(r)
+        cols.append(r + off)
+        vals.append(torch.full((r.numel(), ), 8.0, dtype=dt) if off == 0 else -torch.rand(r.numel(), dtype=dt, generator=g))
+    return torch.cat(vals), torch.cat(rows), torch.cat(cols)
+
+
+def test_spmm_staged_tiles(cb, monkeypatch):
+    """Wide blocks on stencil / banded patterns take the staged kernel (csrc/csr_tiled.cu: the X rows a tile of 8 strips
+    gathers arrive in shared memory once, as bulk-copied runs; cola_b200/csr_tiles.py builds the tile-local form).  Same
+    result as the register-gather kernel and as a dense fp64 product: 2-D tiles with a ragged tail, boundary strips, the
+    fused epilogue and accumulate, irregular tiles (gather from global) inside the same launch, in-place value updates,
+    and a CG solve (BASELINE config 2's operator at test size)."""
+    from cola_b200.csr_tiles import CsrTiles
+    ops = cb.ops
+    be = cb.backend
+    g = torch.Generator().manual_seed(11)
+    for dt, tol, ks in [(torch.float64, 1e-13, (16, 32, 64)), (torch.float32, 3e-6, (32, 64))]:
+        for n, offsets in [(96 * 100, (-96, -1, 0, 1, 96)), (64 * 130 + 5, (-64, -1, 0, 1, 64)), (9000, (-128, -2, -1, 0, 1, 2, 128))]:
+            vals, rows, cols = _banded(n, offsets, dt, g)
+            Ad = torch.zeros(n, n, dtype=torch.float64)
+            Ad[rows, cols] = vals.double()
+            dg = torch.rand(n, dtype=dt, generator=g)
+            for k in ks:
+                X = torch.randn(n, k, dtype=dt, generator=g).to(DEV)
+                outs = []
+                for stage in (0, 100 << 10):
+                    monkeypatch.setattr(ops._CsrCore, "TILE_STAGE_BYTES", stage)
+                    S = ops.Sparse(vals.to(DEV), rows.to(DEV), cols.to(DEV), (n, n))
+                    A = S + 0.25 * ops.I_like(S) + ops.Diagonal(dg.to(DEV))
+                    core = A.plan().terms[-1][1][0]
+                    Y = torch.empty_like(X)
+                    dots = torch.zeros(k, dtype=torch.float64, device=DEV)
+                    A.matmat_into(X, Y, dots=dots)
+                    T = core._tiles(X, Y)
+                    assert (T is not None) == (stage > 0), (n, k, stage)
+                    if T is not None:
+                        assert T.n_tiles2d > 0 and T.n_tiles > T.n_tiles2d       # strips a far diagonal apart + a consecutive-row tail
+                    ref = (Ad + torch.diag(0.25 + dg.double())) @ X.double().cpu()
+                    assert rel(Y, ref) < tol, (dt, n, k, stage, rel(Y, ref))
+                    assert rel(dots, (X.double().cpu() * ref).sum(0)) < max(tol, 1e-6 if stage else tol)
+                    S2 = ops.Sparse(vals.to(DEV), rows.to(DEV), cols.to(DEV), (n, n))
+                    assert rel((S + 2.0 * S2) @ X, 3.0 * (Ad @ X.double().cpu())) < tol     # second term accumulates into Y
+                    outs.append(Y)
+                assert rel(outs[0], outs[1]) < tol
+    # irregular tiles: a pattern without runs forced through the staged kernel (every tile gathers from global memory),
+    # and a banded pattern whose staged rows exceed a deliberately small stage (mixed regular / irregular tiles)
+    n = 3000
+    r = torch.randint(0, n, (9 * n, ), generator=g)
+    c = torch.randint(0, n, (9 * n, ), generator=g)
+    key = torch.unique(r * n + c)
+    r, c = key // n, key % n
+    v = torch.randn(r.numel(), dtype=torch.float64, generator=g)
+    vb, rb, cbnd = _banded(n, (-64, -1, 0, 1, 64), torch.float64, g)
+    for (vv, rr, cc), R, cap, all_irregular in (((v, r, c), 16, 64, True), ((vb, rb, cbnd), 16, 170, False)):
+        S = ops.Sparse(vv.to(DEV), rr.to(DEV), cc.to(DEV), (n, n))
+        T = CsrTiles(S, R, cap, 16 * 8)
+        assert (T.n_regular == 0) if all_irregular else (0 < T.n_regular < T.n_tiles), (T.n_regular, T.n_tiles)
+        X = torch.randn(n, 16, dtype=torch.float64, generator=g).to(DEV)
+        Y = torch.empty_like(X)
+        dots = torch.zeros(16, dtype=torch.float64, device=DEV)
+        be.csr_spmm_tiled(T, T.values(S.data), S.shape, X, Y, alpha=2.0, shift=0.5, dots=dots)
+        Ad = torch.zeros(n, n, dtype=torch.float64)
+        Ad[rr, cc] = vv
+        ref = 2.0 * (Ad @ X.cpu()) + 0.5 * X.cpu()
+        assert rel(Y, ref) < 1e-13 and rel(dots, (X.cpu() * ref).sum(0)) < 1e-6
+    # values written in place are picked up (the padded copy is refreshed), and a CG solve runs on the staged kernel
+    monkeypatch.setattr(ops._CsrCore, "TILE_STAGE_BYTES", 100 << 10)
+    data, rows, cols, shape = pb.laplacian_2d_coo(96, torch.float64)
+    S = ops.Sparse(data.to(DEV), rows.to(DEV), cols.to(DEV), shape)
+    X = torch.randn(shape[0], 16, dtype=torch.float64, generator=g).to(DEV)
+    Y1 = S @ X
+    S.data.mul_(3.0)
+    assert rel(S @ X, 3.0 * Y1) < 1e-14
+    S.data.div_(3.0)
+    A = cb.PSD(S + 0.05 * ops.I_like(S))
+    assert A.plan().terms[-1][1][0]._tiles(X, Y1) is not None
+    sol, info = cb.linalg.cg(A, X, tol=1e-10, max_iters=2000)
+    Ad = torch.zeros(shape, dtype=torch.float64)
+    Ad[rows, cols] = data
+    Ad += 0.05 * torch.eye(shape[0], dtype=torch.float64)
+    assert rel(Ad @ sol.cpu(), X.cpu()) < 1e-8

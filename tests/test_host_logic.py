@@ -216,6 +216,12 @@ def test_spmv_column_strips(emu, monkeypatch):
     gn.test_spmv_column_strips(emu, monkeypatch)
 
 
+def test_spmm_staged_tiles(emu, monkeypatch):
+    """The tile-local CSR form (cola_b200/csr_tiles.py) and its dispatch, with the kernel replaced by an emulation that
+    computes FROM the records, runs, slots and local row pointers."""
+    gn.test_spmm_staged_tiles(emu, monkeypatch)
+
+
 def test_native_api_refuses_parameters_that_require_grad(emu):
     """The kernels do not record autograd: a leaf that requires grad raises while recording is on (instead of handing
     back a result without grad_fn), and is accepted under torch.no_grad()."""
