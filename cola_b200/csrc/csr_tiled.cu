@@ -16,18 +16,17 @@
 
 namespace cola {
 
-constexpr int kTlMaxConsumers = 768;             // consumer threads (a launch parameter) + one producer warp <= 800
 constexpr int kTlRec = 32;                       // record words per tile (cola_b200/csr_tiles.py)
 
 template <typename T>
 struct TiledArgs {
   const int32_t* rec; const int32_t* rp; const int32_t* idx; const T* vals;
-  int64_t n_rows, n_tiles, n_tiles2d, rows2d, stride, tiles_per_blk;
+  int64_t n_rows, n_tiles, n_tiles2d, rows2d, stride, tiles_per_blk, n_blk;
   int strip_rows, strips, rp_stride, cap_rows, cap_nz, n_stages;
   const T* X; int64_t k; T* Y; int64_t ldy;
   T alpha, shift; const T* diag; int accumulate;
   double* dots; const int32_t* dots_row; int64_t k_full; const int32_t* gate;
-  int lanes;                                     // threads per row: k * sizeof(T) / 16
+  int lanes;                                     // threads per row: k * sizeof(T) / 16 / (chunks per thread)
   int consumers;                                 // consumer threads (whole warps); the producer is the warp after them
   int stage_bytes, off_idx, off_val, off_rp;     // ring stage layout (bytes)
 };
@@ -67,19 +66,23 @@ __device__ __forceinline__ void tl_bulk_load(uint32_t dst, const void* src, uint
 // per-thread view of the tile being consumed
 template <typename T>
 struct TlRows {
-  const unsigned char* sx;       // staged X rows, already offset to this thread's 16-byte chunk
+  const unsigned char* sx;       // staged X rows, already offset to this thread's first 16-byte chunk
   const int32_t* rp; const int32_t* sidx; const T* sval;
   const T* Xc; T* Yc;
   int64_t row0, stride;
   int RT, R, g, groups, s0, r0, ds, dr;
 };
 
-// Rows g, g + groups, ... of one tile.  REGULAR: sidx / the own-row table hold BYTE offsets of staged rows (slot * row
-// bytes, from csr_tiles.py); else sidx holds columns and the rows are gathered from global memory.
-template <typename T, bool EPI, bool DOTS, bool REGULAR>
+// Rows g, g + groups, ... of one tile.  A thread owns CH 16-byte chunks of its row, `lanes` chunks apart (neighbouring
+// lanes read neighbouring chunks: no bank conflicts, whole sectors per store), so the per-non-zero overhead (value,
+// offset, address) is paid once per CH * 16 bytes.  REGULAR: sidx / the own-row table hold BYTE offsets of staged rows
+// (slot * row bytes, from csr_tiles.py); else sidx holds columns and the rows are gathered from global memory.
+template <typename T, bool EPI, bool DOTS, bool REGULAR, int CH>
 __device__ __forceinline__ void tl_tile_rows(const TiledArgs<T>& a, const TlRows<T>& w, T* facc) {
   constexpr int VEC = 16 / (int)sizeof(T);
   const int32_t* self_off = w.rp + w.RT + 4;
+  const int cstep = a.lanes * 16;                 // bytes between a thread's chunks
+  const int cstep_e = a.lanes * VEC;              // ... in elements
   int s = w.s0, r = w.r0;
   for (int lr = w.g; lr < w.RT; lr += w.groups) {
     const int64_t row = w.row0 + s * w.stride + r;
@@ -87,51 +90,81 @@ __device__ __forceinline__ void tl_tile_rows(const TiledArgs<T>& a, const TlRows
     if (r >= w.R) { r -= w.R; ++s; }
     if (row >= a.n_rows) continue;
     const int32_t e0 = w.rp[lr], cnt = w.rp[lr + 1] - e0;
-    Vec<T, VEC> xo, yo;
+    Vec<T, VEC> xo[CH];
     T sd = a.shift;
     if constexpr (EPI) {                                                  // own row: the epilogue's operand
-      if constexpr (REGULAR) xo = *reinterpret_cast<const Vec<T, VEC>*>(w.sx + self_off[lr]);
-      else xo = ldg<T, VEC>(w.Xc + row * a.k);
+      if constexpr (REGULAR) {
+        const unsigned char* px = w.sx + self_off[lr];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) xo[c] = *reinterpret_cast<const Vec<T, VEC>*>(px + c * cstep);
+      } else {
+#pragma unroll
+        for (int c = 0; c < CH; ++c) xo[c] = ldg<T, VEC>(w.Xc + row * a.k + c * cstep_e);
+      }
       if (a.diag) sd += a.diag[row];
     }
     T* yp = w.Yc + row * a.ldy;
-    if (a.accumulate) yo = ldg<T, VEC>(yp);
     const int32_t* pi = w.sidx + e0;
     const T* pv = w.sval + e0;
-    T acc[VEC];
+    T acc[CH][VEC];
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) acc[q] = (T)0;
-#pragma unroll 4
-    for (int32_t j = 0; j < cnt; ++j) {
-      const T wv = pv[j];
-      Vec<T, VEC> x;
-      if constexpr (REGULAR) x = *reinterpret_cast<const Vec<T, VEC>*>(w.sx + pi[j]);
-      else x = ldg<T, VEC>(w.Xc + (int64_t)pi[j] * a.k);
+    for (int c = 0; c < CH; ++c)
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) acc[q] += wv * x.v[q];
+      for (int q = 0; q < VEC; ++q) acc[c][q] = (T)0;
+#pragma unroll 2
+      for (int32_t j = 0; j < cnt; ++j) {
+        const T wv = pv[j];
+        Vec<T, VEC> x[CH];
+        if constexpr (REGULAR) {
+          const unsigned char* px = w.sx + pi[j];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) x[c] = *reinterpret_cast<const Vec<T, VEC>*>(px + c * cstep);
+        } else {
+          const T* px = w.Xc + (int64_t)pi[j] * a.k;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) x[c] = ldg<T, VEC>(px + c * cstep_e);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[c][q] += wv * x[c].v[q];
+      }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      Vec<T, VEC> y;
+      if constexpr (EPI) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) y.v[q] = a.alpha * acc[c][q] + sd * xo[c].v[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) y.v[q] = a.alpha * acc[c][q];
+      }
+      if (a.accumulate) {
+        const Vec<T, VEC> yo = ldg<T, VEC>(yp + c * cstep_e);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) y.v[q] += yo.v[q];
+      }
+      if constexpr (EPI && DOTS) {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) facc[c * VEC + q] += xo[c].v[q] * y.v[q];
+      }
+      stg_stream<T, VEC>(yp + c * cstep_e, y);
     }
-    Vec<T, VEC> y;
-    if constexpr (EPI) {
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) y.v[q] = a.alpha * acc[q] + sd * xo.v[q];
-    } else {
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) y.v[q] = a.alpha * acc[q];
-    }
-    if (a.accumulate) {
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) y.v[q] += yo.v[q];
-    }
-    if constexpr (EPI && DOTS) {
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) facc[q] += xo.v[q] * y.v[q];
-    }
-    stg_stream<T, VEC>(yp, y);
   }
 }
 
-template <typename T, bool EPI, bool DOTS>
-__global__ void __launch_bounds__(800, 1) csr_spmm_tiled_kernel(TiledArgs<T> a) {
+// position u of a CTA's tile sequence -> tile.  The 2-D tiles run block-fastest: consecutive tiles of a CTA are vertical
+// neighbours (same strip columns, next block of strips), so the halo strip a tile reads above / below itself is the
+// previous / next tile's own strip: still in L2 (measured: X read 1.25x -> ~1.05x from DRAM).
+template <typename T>
+__device__ __forceinline__ int64_t tl_tile_of(const TiledArgs<T>& a, int64_t u) {
+  if (u >= a.n_tiles2d || a.n_blk == 0) return u;
+  const int64_t c = u / a.n_blk, b = u - c * a.n_blk;
+  return b * a.tiles_per_blk + c;
+}
+
+template <typename T, bool EPI, bool DOTS, int CH>
+__global__ void __launch_bounds__(CH == 2 ? 544 : 768) __maxnreg__(CH == 2 ? 96 : 80) csr_spmm_tiled_kernel(TiledArgs<T> a) {
   if (a.gate != nullptr && *a.gate != 0) return;
   constexpr int VEC = 16 / (int)sizeof(T);
   extern __shared__ __align__(128) unsigned char tl_smem[];
@@ -148,31 +181,32 @@ __global__ void __launch_bounds__(800, 1) csr_spmm_tiled_kernel(TiledArgs<T> a) 
   }
   double* s_dots = reinterpret_cast<double*>(tl_smem + (size_t)a.n_stages * a.stage_bytes + 16 * a.n_stages + 64);
   if (DOTS) {
-    for (int i = threadIdx.x; i < a.lanes * VEC; i += blockDim.x) s_dots[i] = 0.0;
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) s_dots[i] = 0.0;
   }
   __syncthreads();
 
-  // this CTA's tiles: one contiguous chunk (neighbouring tiles share halo rows: L2 locality, contiguous records)
+  // this CTA's tiles: one contiguous chunk of the tile sequence
   const int64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
-  const int64_t t_begin = (int64_t)blockIdx.x * per;
-  const int64_t t_end = t_begin + per < a.n_tiles ? t_begin + per : a.n_tiles;
+  const int64_t u_begin = (int64_t)blockIdx.x * per;
+  const int64_t u_end = u_begin + per < a.n_tiles ? u_begin + per : a.n_tiles;
   const uint32_t row_bytes = (uint32_t)(a.k * (int64_t)sizeof(T));
 
   if (warp == a.consumers / 32) {
-    // ===== producer warp: lane j copies run j; lanes 12 / 13 / 14 the slots, values and row pointers =====
-    int32_t v = (t_begin < t_end) ? a.rec[t_begin * kTlRec + lane] : 0;
-    int it = 0;
-    for (int64_t t = t_begin; t < t_end; ++t, ++it) {
+    // ===== producer warp: lane j copies run j; lanes 12 / 13 / 14 the offsets, values and row pointers =====
+    int32_t v = (u_begin < u_end) ? a.rec[tl_tile_of(a, u_begin) * kTlRec + lane] : 0;
+    int s = 0;
+    uint32_t parity = 1;
+    for (int64_t u = u_begin; u < u_end; ++u) {
+      const int64_t t = tl_tile_of(a, u);
       const int32_t cur = v;
-      if (t + 1 < t_end) v = a.rec[(t + 1) * kTlRec + lane];        // next record while this tile's copies are issued
-      const int s = it % a.n_stages;
+      if (u + 1 < u_end) v = a.rec[tl_tile_of(a, u + 1) * kTlRec + lane];   // next record while this tile's copies are issued
       const uint32_t full = bar0 + 8 * s, empty = bar0 + 8 * (a.n_stages + s);
       const int32_t nz_begin = __shfl_sync(0xffffffffu, cur, 0), nz_pad = __shfl_sync(0xffffffffu, cur, 1);
       const int32_t n_runs = __shfl_sync(0xffffffffu, cur, 2), n_dist = __shfl_sync(0xffffffffu, cur, 3);
       const int32_t col0 = __shfl_sync(0xffffffffu, cur, (8 + 2 * lane) & 31);
       const int32_t sl = __shfl_sync(0xffffffffu, cur, (9 + 2 * lane) & 31);
       if (lane == 0) {
-        while (!tl_mbar_try(empty, ((it / a.n_stages) & 1) ^ 1)) __nanosleep(100);   // (a spinning warp costs its scheduler issue slots)
+        while (!tl_mbar_try(empty, parity)) __nanosleep(100);   // (a spinning warp costs its scheduler issue slots)
       }
       __syncwarp();
       const uint32_t stage = sbase + (uint32_t)s * (uint32_t)a.stage_bytes;
@@ -191,9 +225,10 @@ __global__ void __launch_bounds__(800, 1) csr_spmm_tiled_kernel(TiledArgs<T> a) 
       } else if (lane == 14) {
         tl_bulk_load(stage + a.off_rp, a.rp + t * a.rp_stride, (uint32_t)a.rp_stride * 4u, full);
       }
+      if (++s == a.n_stages) { s = 0; parity ^= 1; }
     }
   } else {
-    // ===== consumers: `lanes` threads per row, one 16-byte column chunk each =====
+    // ===== consumers: `lanes` threads per row, CH 16-byte column chunks each =====
     const int tid = threadIdx.x;
     const int g = tid / a.lanes, l = tid - g * a.lanes;
     const int groups = a.consumers / a.lanes;
@@ -203,12 +238,16 @@ __global__ void __launch_bounds__(800, 1) csr_spmm_tiled_kernel(TiledArgs<T> a) 
     w.s0 = g / a.strip_rows; w.r0 = g - w.s0 * a.strip_rows;          // local row g + i * groups as (strip, row in strip),
     w.ds = groups / a.strip_rows; w.dr = groups - w.ds * a.strip_rows;  // advanced without a division per row
     w.Xc = a.X + (size_t)l * VEC; w.Yc = a.Y + (size_t)l * VEC;
-    double dacc[VEC];
+    T facc[CH * VEC];                                                  // <x, y> partials: fp32 over a few tiles, then fp64
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) dacc[q] = 0.0;
-    int it = 0, s = 0;
+    for (int q = 0; q < CH * VEC; ++q) facc[q] = (T)0;
+    double dacc[CH * VEC];
+#pragma unroll
+    for (int q = 0; q < CH * VEC; ++q) dacc[q] = 0.0;
+    int s = 0, since_fold = 0;
     uint32_t parity = 0;
-    for (int64_t t = t_begin; t < t_end; ++t, ++it) {
+    for (int64_t u = u_begin; u < u_end; ++u) {
+      const int64_t t = tl_tile_of(a, u);
       tl_mbar_wait(bar0 + 8 * s, parity);
       const unsigned char* stage = tl_smem + (size_t)s * a.stage_bytes;
       w.sx = stage + l * 16;
@@ -223,33 +262,34 @@ __global__ void __launch_bounds__(800, 1) csr_spmm_tiled_kernel(TiledArgs<T> a) 
         w.row0 = a.rows2d + (t - a.n_tiles2d) * w.RT;
         w.stride = a.strip_rows;
       }
-      T facc[VEC];
-#pragma unroll
-      for (int q = 0; q < VEC; ++q) facc[q] = (T)0;
       if (col_ok) {
-        if (w.rp[w.RT + 3] >= 0) tl_tile_rows<T, EPI, DOTS, true>(a, w, facc);
-        else tl_tile_rows<T, EPI, DOTS, false>(a, w, facc);
-      }
-      if constexpr (DOTS) {
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) dacc[q] += (double)facc[q];
+        if (w.rp[w.RT + 3] >= 0) tl_tile_rows<T, EPI, DOTS, true, CH>(a, w, facc);
+        else tl_tile_rows<T, EPI, DOTS, false, CH>(a, w, facc);
       }
       __syncwarp();
       if (lane == 0) tl_mbar_arrive(bar0 + 8 * (a.n_stages + s));   // this warp no longer reads the stage
       if (++s == a.n_stages) { s = 0; parity ^= 1; }
+      if constexpr (DOTS) {
+        if (++since_fold == 8 || u + 1 == u_end) {                  // fp32 partials of <= 8 tiles, folded in fp64 registers
+          since_fold = 0;
+#pragma unroll
+          for (int q = 0; q < CH * VEC; ++q) { dacc[q] += (double)facc[q]; facc[q] = (T)0; }
+        }
+      }
     }
-    if constexpr (DOTS) {
+    if constexpr (DOTS) {                                           // once per CTA (shared fp64 atomics are CAS loops)
       if (col_ok) {
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) atomicAdd(s_dots + l * VEC + q, dacc[q]);
+        for (int c = 0; c < CH; ++c)
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) atomicAdd(s_dots + (c * a.lanes + l) * VEC + q, dacc[c * VEC + q]);
       }
     }
   }
   if constexpr (DOTS) {
     __syncthreads();
     double* out = a.dots + (a.dots_row ? (int64_t)(*a.dots_row) * a.k_full : 0);
-    for (int i = threadIdx.x; i < a.lanes * VEC; i += blockDim.x)
-      if (i < a.k) atomicAdd(out + i, s_dots[i]);
+    for (int i = threadIdx.x; i < a.k; i += blockDim.x) atomicAdd(out + i, s_dots[i]);
   }
 }
 
@@ -270,13 +310,22 @@ static int csr_spmm_tiled(const int32_t* rec, const int32_t* rp, const int32_t* 
   TiledArgs<T> a;
   a.rec = rec; a.rp = rp; a.idx = idx; a.vals = vals; a.n_rows = n_rows; a.n_tiles = n_tiles; a.n_tiles2d = n_tiles2d;
   a.rows2d = rows2d; a.stride = stride; a.tiles_per_blk = n_tiles2d > 0 ? stride / strip_rows : 1;
+  a.n_blk = n_tiles2d > 0 ? n_tiles2d / a.tiles_per_blk : 1;
+  if (const char* e = getenv("COLA_SPMM_TILE_ORDER")) { if (atoi(e) == 0) a.n_blk = 0; }
   a.strip_rows = (int)strip_rows; a.strips = (int)strips; a.rp_stride = (int)(2 * strip_rows * strips + 4);
   a.cap_rows = (int)cap_rows; a.cap_nz = (int)cap_nz;
   a.X = X; a.k = k; a.Y = Y; a.ldy = ldy; a.alpha = alpha; a.shift = shift; a.diag = diag; a.accumulate = accumulate;
   a.dots = dots; a.dots_row = dots_row; a.k_full = k; a.gate = gate;
-  a.lanes = (int)(k / VEC);
-  a.consumers = 768;
-  if (const char* e = getenv("COLA_SPMM_TILE_WARPS")) { const int v = atoi(e); if (v >= 1 && v <= kTlMaxConsumers / 32) a.consumers = 32 * v; }
+  const int chunks = (int)(k / VEC);
+  // chunks per thread: 2 halves the per-non-zero overhead (value, offset, address) per byte; measured on cfg2 (fp32, k = 64):
+  // 1 chunk x 23 warps 0.482 ms, 2 x 16 0.411 ms, 4 x 8..15 >= 0.60 ms
+  int ch = chunks % 2 == 0 ? 2 : 1;
+  if (const char* e = getenv("COLA_SPMM_TILE_CH")) { const int v = atoi(e); if ((v == 1 || v == 2) && chunks % v == 0) ch = v; }
+  a.lanes = chunks / ch;
+  const int max_consumers = ch == 2 ? 512 : 736;   // + the producer warp (registers are per SM sub-partition: 5 warps x 96, 6 x 80)
+  a.consumers = max_consumers;
+  if (const char* e = getenv("COLA_SPMM_TILE_WARPS")) { const int v = atoi(e); if (v >= 1 && 32 * v <= max_consumers) a.consumers = 32 * v; }
+  COLA_REQUIRE(a.lanes <= max_consumers, "csr_spmm_tiled: row too wide");
   while (a.consumers < a.lanes) a.consumers += 32;
   const int64_t row_bytes = k * (int64_t)sizeof(T);
   auto up = [](int64_t x, int64_t m) { return (x + m - 1) / m * m; };
@@ -287,7 +336,7 @@ static int csr_spmm_tiled(const int32_t* rec, const int32_t* rp, const int32_t* 
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const int64_t extra = 16 * 8 + 64 + (int64_t)a.lanes * VEC * 8 + 128;
+  const int64_t extra = 16 * 8 + 64 + k * 8 + 128;
   int n_stages = (int)(((int64_t)smem_max - extra) / a.stage_bytes);
   if (n_stages > 6) n_stages = 6;
   if (n_stages < 2) return fail(COLA_E_UNSUPPORTED, "csr_spmm_tiled: a ring of two stages does not fit shared memory");
@@ -296,19 +345,24 @@ static int csr_spmm_tiled(const int32_t* rec, const int32_t* rp, const int32_t* 
   const bool epi = (shift != (T)0) || diag || dots;
   int64_t grid = sm_count();
   if (grid > n_tiles) grid = n_tiles;
-#define COLA_TILED_LAUNCH(EPIV, DOTSV)                                                              \
+#define COLA_TILED_LAUNCH(EPIV, DOTSV, CHV)                                                      \
   do {                                                                                              \
-    auto kern = csr_spmm_tiled_kernel<T, EPIV, DOTSV>;                                              \
+    auto kern = csr_spmm_tiled_kernel<T, EPIV, DOTSV, CHV>;                                    \
     static int attr_smem = 0;                                                                       \
     if ((int)smem > attr_smem) {                                                                    \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
       attr_smem = (int)smem;                                                                        \
     }                                                                                               \
-    kern<<<(unsigned)grid, a.consumers + 32, smem, st>>>(a);                                              \
+    kern<<<(unsigned)grid, a.consumers + 32, smem, st>>>(a);                                        \
   } while (0)
-  if (dots) COLA_TILED_LAUNCH(true, true);
-  else if (epi) COLA_TILED_LAUNCH(true, false);
-  else COLA_TILED_LAUNCH(false, false);
+#define COLA_TILED_EPI(CHV)                                  \
+  do {                                                       \
+    if (dots) COLA_TILED_LAUNCH(true, true, CHV);            \
+    else if (epi) COLA_TILED_LAUNCH(true, false, CHV);       \
+    else COLA_TILED_LAUNCH(false, false, CHV);               \
+  } while (0)
+  if (ch == 2) COLA_TILED_EPI(2);
+  else COLA_TILED_EPI(1);
   return cuda_status("csr_spmm_tiled");
 }
 

@@ -54,14 +54,16 @@ by = A.nnz * 8 + 4 * (n + 1) + 2 * n * k * 4
 ms = time_kernel(lambda: be.csr_spmm(A.indptr, A.indices, A.data, shape, A.nnz, A.max_row_nnz, p, ap, dots=pap), reps=20)
 print(f"register-gather spmm+dots: {ms:.4f} ms  {by/ms*1e-6:.0f} GB/s algorithmic")
 want = ap.clone()
-for R, cap in ((32, 400), (16, 200), (8, 100)):
+for R, cap in ((32, 400), (16, 200)):
     torch.cuda.synchronize()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); T = CsrTiles(A, R, cap, k * A.data.element_size()); vals = T.values(A.data); t1.record(); torch.cuda.synchronize()
-    for warps in (8, 16, 20, 24):
+    for ch, warps, order in ((1, 16, 0), (1, 23, 0), (2, 8, 0), (2, 12, 0), (2, 16, 0), (2, 16, 1), (4, 8, 0), (4, 15, 0)):
+        os.environ["COLA_SPMM_TILE_NB"] = str(order)
         os.environ["COLA_SPMM_TILE_WARPS"] = str(warps)
+        os.environ["COLA_SPMM_TILE_CH"] = str(ch)
         ap.zero_()
         ms = time_kernel(lambda: be.csr_spmm_tiled(T, vals, shape, p, ap, dots=pap), reps=20)
-        print(f"staged R={R} cap={cap} warps={warps} (cap_rows {T.cap_rows} cap_nz {T.cap_nz} regular {T.n_regular}/{T.n_tiles}, build {t0.elapsed_time(t1):.0f} ms): "
+        print(f"staged R={R} cap={cap} ch={ch} warps={warps} batched={order} (cap_rows {T.cap_rows} cap_nz {T.cap_nz} regular {T.n_regular}/{T.n_tiles}, build {t0.elapsed_time(t1):.0f} ms): "
               f"{ms:.4f} ms  {by/ms*1e-6:.0f} GB/s algorithmic, max diff vs register-gather {float((ap-want).abs().max()):.2e}")
     del T, vals
