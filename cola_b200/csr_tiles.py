@@ -168,6 +168,11 @@ class CsrTiles:
             self._vals, self._vals_token = v, token
         return self._vals
 
+    def stage_bytes(self, itemsize):
+        """Bytes of one ring stage as csrc/csr_tiled.cu lays it out: X rows | offsets | values | row pointers, 128-byte aligned."""
+        up = lambda x: -(-x // 128) * 128
+        return up(self.cap_rows * self.row_bytes) + up(self.cap_nz * 4) + up(self.cap_nz * itemsize) + up(self.rp_stride * 4)
+
     def worthwhile(self):
         """The staged kernel pays when almost every tile is regular and its runs are long (stencil / banded patterns)."""
         return self.n_tiles > 0 and self.n_regular >= 0.9 * self.n_tiles and self.mean_run >= 8.0

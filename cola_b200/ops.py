@@ -690,8 +690,9 @@ class _CsrCore:
     COLUMN-BLOCKED: the pattern is cut once into vertical strips whose slice of X (SPMV_BLOCK_BYTES) stays resident in
     L2, and the strips are applied one after the other, each accumulating into Y; the CSR arrays still stream through
     once in total, Y is re-read per strip.  Row sums are then taken strip by strip (fp rounding order only)."""
-    TILE_STAGE_BYTES = int(os.environ.get("COLA_SPMM_TILE_KB", "100")) << 10    # X rows one ring stage of the staged kernel holds (0: off)
+    TILE_STAGE_BYTES = int(os.environ.get("COLA_SPMM_TILE_KB", "106")) << 10    # X rows one ring stage of the staged kernel holds (0: off)
     TILE_STRIP_ROWS = int(os.environ.get("COLA_SPMM_TILE_R", "0"))               # 0: from the stage size
+    TILE_SMEM_BYTES = 227 << 10                                                  # opt-in shared memory of one sm_100 CTA
     SPMV_BLOCK_BYTES = int(os.environ.get("COLA_SPMV_BLOCK_MB", "45")) << 20   # measured on cfg5 (2^24 nodes, fp64): 32 MB 2.53 ms, 45 MB 2.18 ms, 68 MB 2.89 ms; plain 3.99; cuSPARSE 2.97
 
     def __init__(self, S):
@@ -709,14 +710,23 @@ class _CsrCore:
             return None
         if row_bytes not in self._tiled:
             from .csr_tiles import CsrTiles, STRIPS
-            cap_rows = self.TILE_STAGE_BYTES // row_bytes
+            # one ring stage holds, per tile row: ~1.33 staged rows of X (5-point stencil halo), its non-zeros' offsets
+            # and values, two row-pointer words; if the halo turns out wider, halve the strips once or twice
+            nz_row = 1.05 * self.S.nnz / max(self.S.shape[0], 1) * (4 + X.element_size()) + 8
             R = self.TILE_STRIP_ROWS
-            if R <= 0:                               # staged rows ~ 1.35 x the tile's own rows on a 5-point stencil
+            if R <= 0:
                 R = 8
-                while R * 2 * STRIPS * 1.35 <= cap_rows and R < 64:
+                while 2 * R * STRIPS * (1.33 * row_bytes + nz_row) <= self.TILE_STAGE_BYTES and R < 64:
                     R *= 2
-            T = CsrTiles(self.S, R, cap_rows, row_bytes)
-            self._tiled[row_bytes] = T if T.worthwhile() else None
+            found = None
+            while found is None and R >= 8:
+                cap_rows = int(self.TILE_STAGE_BYTES - R * STRIPS * nz_row) // row_bytes
+                T = CsrTiles(self.S, R, cap_rows, row_bytes)
+                fits = 2 * T.stage_bytes(X.element_size()) + X.shape[1] * 8 + 1024 <= self.TILE_SMEM_BYTES   # a ring of two stages
+                if T.worthwhile() and fits:
+                    found = T
+                R //= 2
+            self._tiled[row_bytes] = found
         return self._tiled[row_bytes]
 
     def _column_strips(self, k, itemsize):

@@ -424,7 +424,7 @@ def test_spmm_staged_tiles(cb, monkeypatch):
             for k in ks:
                 X = torch.randn(n, k, dtype=dt, generator=g).to(DEV)
                 outs = []
-                for stage in (0, 100 << 10):
+                for stage in (0, 106 << 10):
                     monkeypatch.setattr(ops._CsrCore, "TILE_STAGE_BYTES", stage)
                     S = ops.Sparse(vals.to(DEV), rows.to(DEV), cols.to(DEV), (n, n))
                     A = S + 0.25 * ops.I_like(S) + ops.Diagonal(dg.to(DEV))
@@ -465,7 +465,7 @@ def test_spmm_staged_tiles(cb, monkeypatch):
         ref = 2.0 * (Ad @ X.cpu()) + 0.5 * X.cpu()
         assert rel(Y, ref) < 1e-13 and rel(dots, (X.cpu() * ref).sum(0)) < 1e-6
     # values written in place are picked up (the padded copy is refreshed), and a CG solve runs on the staged kernel
-    monkeypatch.setattr(ops._CsrCore, "TILE_STAGE_BYTES", 100 << 10)
+    monkeypatch.setattr(ops._CsrCore, "TILE_STAGE_BYTES", 106 << 10)
     data, rows, cols, shape = pb.laplacian_2d_coo(96, torch.float64)
     S = ops.Sparse(data.to(DEV), rows.to(DEV), cols.to(DEV), shape)
     X = torch.randn(shape[0], 16, dtype=torch.float64, generator=g).to(DEV)
