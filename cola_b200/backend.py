@@ -343,6 +343,22 @@ def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
                stream_ptr())
 
 
+def mgs_chain(W, Q, n_links, H, wnorm2=None, gate=None):
+    """All MGS links of one Arnoldi step in one cooperative launch: Q (m+1, n, b) basis, H (>= n_links, b) fp64 rows
+    (zero on entry), W (n, b).  Returns False when the library declines (block too wide / launch refused): the caller
+    then runs the mgs_link chain."""
+    n, b = W.shape
+    rc = getattr(lib().cdll, f"cola_mgs_chain_{sfx(W.dtype)}")(
+        ptr(W), ptr(Q, W.dtype), Q.stride(0), n_links, ptr(H, torch.float64), H.stride(0),
+        ptr(wnorm2, torch.float64) if wnorm2 is not None else None, n, b, ptr(gate), stream_ptr())
+    if rc == -2:
+        return False
+    if rc != 0:
+        msg = lib().cdll.cola_last_error()
+        raise RuntimeError(f"cola_mgs_chain failed with status {rc}: {msg.decode() if msg else ''}")
+    return True
+
+
 # ---- parameter gradients (csrc/param_grad.cu) ------------------------------------------------------------
 def sddmm_csr(rowptr, colidx, n_rows, G, V, alpha, out):
     """out[e] = alpha * <G[row(e), :], V[colidx[e], :]> over the CSR pattern; G, V (n, k) contiguous."""

@@ -65,6 +65,46 @@ __device__ __forceinline__ Vec<T, N> ldg_stream(const T* p) {
   }
   return r;
 }
+// L2-only load (ld.global.cg): data another SM, or an earlier pass of this kernel, may have rewritten
+template <typename T, int N>
+__device__ __forceinline__ Vec<T, N> ldg_cg(const T* p) {
+  Vec<T, N> r;
+  if constexpr (sizeof(T) * N == 16) {
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    r = *reinterpret_cast<Vec<T, N>*>(&t);
+  } else if constexpr (sizeof(T) * N == 8) {
+    float2 t = __ldcg(reinterpret_cast<const float2*>(p));
+    r = *reinterpret_cast<Vec<T, N>*>(&t);
+  } else if constexpr (sizeof(T) * N == 4) {
+    float t = __ldcg(reinterpret_cast<const float*>(p));
+    r = *reinterpret_cast<Vec<T, N>*>(&t);
+  } else {
+    r = *reinterpret_cast<const Vec<T, N>*>(p);
+  }
+  return r;
+}
+// 16-byte accesses carrying an L2 eviction policy (createpolicy): lines a kernel re-reads pass after pass are marked
+// evict_last so that streamed operands do not push them out of L2
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+template <typename T, int N>
+__device__ __forceinline__ Vec<T, N> ldg_hint(const T* p, uint64_t pol) {
+  static_assert(sizeof(T) * N == 16, "16-byte vectors only");
+  uint4 t;
+  asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p), "l"(pol));
+  return *reinterpret_cast<Vec<T, N>*>(&t);
+}
+template <typename T, int N>
+__device__ __forceinline__ void stg_hint(T* p, const Vec<T, N>& x, uint64_t pol) {
+  static_assert(sizeof(T) * N == 16, "16-byte vectors only");
+  const uint4 t = *reinterpret_cast<const uint4*>(&x);
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(p), "r"(t.x), "r"(t.y), "r"(t.z), "r"(t.w), "l"(pol) : "memory");
+}
 template <typename T, int N>
 __device__ __forceinline__ void stg_stream(T* p, const Vec<T, N>& x) {
   if constexpr (sizeof(T) * N == 16) {

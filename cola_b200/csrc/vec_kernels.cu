@@ -1,8 +1,11 @@
 // Vector sweeps of the Krylov loops: column dots / scalings, CG x-r-p updates and control block,
 // Lanczos three-term step, Arnoldi MGS links, core-less (diagonal) matmat.  All are instances of
 // sweep_kernel (sweep.cuh): one HBM pass over each operand, fp64 per-column reductions.
+#include <cooperative_groups.h>
+
 #include "sweep.cuh"
 
+namespace cg = cooperative_groups;
 namespace cola {
 
 thread_local char g_err[512] = "";
@@ -477,6 +480,107 @@ int mgs_link(T* W, const T* Qprev, const double* hprev, const T* Qcur, double* h
   return rc;
 }
 
+// ---- Arnoldi MGS chain: all links of one step in ONE cooperative launch (arnoldi.py:304-316) ----------------
+// for j = 0 .. n_links-1:  h_j = <q_j, w>;  w -= h_j q_j     and finally  wnorm2 += <w, w>
+// in exact modified-Gram-Schmidt order, like n_links + 1 mgs_link launches (pass j subtracts h_{j-1} q_{j-1} and
+// accumulates <q_j, w> in the same sweep), with a grid-wide sync where a launch boundary was.  A thread owns the same
+// elements of w in every pass, so w needs no sync of its own and stays in L2 (ld.global.cg / plain stores; the streaming
+// hint is kept for the last use of q_{j-1}); q_j is read from DRAM once (its second use, one pass later, is an L2 hit
+// when w and one basis block fit).  The link chain re-read q_{j-1} from DRAM and paid a launch + drain per link.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kSweepThreads)
+    mgs_chain_kernel(T* W, const T* Q, int64_t q_stride, int n_links, double* H, int64_t ldh, double* wnorm2, int64_t n,
+                     int64_t k, int64_t ld, int lanes, int rows_per_pass, int64_t colmask, const int32_t* gate) {
+  if (!gate_open(gate)) return;                     // uniform over the grid: nobody reaches a grid sync
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double red[kSweepThreads * VEC];
+  const int tid = threadIdx.x;
+  const int r = tid / lanes, l = tid - r * lanes;
+  const int64_t c0 = (int64_t)l * VEC;
+  const bool active = (r < rows_per_pass) && (c0 < k);
+  const int64_t stride = (int64_t)gridDim.x * rows_per_pass;
+  constexpr bool HINT = sizeof(T) * VEC == 16;       // w is the operand every pass re-reads: evict_last in L2
+  uint64_t pol = 0;
+  if constexpr (HINT) pol = l2_policy_evict_last();
+  auto ldw = [&](const T* p) {
+    if constexpr (HINT) return ldg_hint<T, VEC>(p, pol);
+    else return ldg_cg<T, VEC>(p);
+  };
+  for (int j = 0; j <= n_links; ++j) {
+    const T* qp = j > 0 ? Q + (int64_t)(j - 1) * q_stride : nullptr;
+    const T* qc = j < n_links ? Q + (int64_t)j * q_stride : nullptr;
+    T hp[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) hp[v] = qp ? (T)__ldcg(H + (int64_t)(j - 1) * ldh + ((c0 + v) & colmask)) : (T)0;
+    double acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.0;
+    if (active) {
+      auto one = [&](int64_t o, Vec<T, VEC> w, const Vec<T, VEC>& xp, const Vec<T, VEC>& xc) {
+        if (qp) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) w.v[v] = w.v[v] - hp[v] * xp.v[v];
+          if constexpr (HINT) stg_hint<T, VEC>(W + o, w, pol);
+          else stg<T, VEC>(W + o, w);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += (double)(qc ? xc.v[v] : w.v[v]) * (double)w.v[v];
+      };
+      int64_t row = (int64_t)blockIdx.x * rows_per_pass + r;
+      for (; row + stride < n; row += 2 * stride) {          // two rows in flight per thread
+        const int64_t oa = row * ld + c0, ob = (row + stride) * ld + c0;
+        Vec<T, VEC> wa = ldw(W + oa), wb = ldw(W + ob), pa, pb, ca, cb;
+        if (qp) { pa = ldg_stream<T, VEC>(qp + oa); pb = ldg_stream<T, VEC>(qp + ob); }
+        if (qc) { ca = ldg_stream<T, VEC>(qc + oa); cb = ldg_stream<T, VEC>(qc + ob); }
+        one(oa, wa, pa, ca);
+        one(ob, wb, pb, cb);
+      }
+      if (row < n) {
+        const int64_t oa = row * ld + c0;
+        Vec<T, VEC> wa = ldw(W + oa), pa, ca;
+        if (qp) pa = ldg_stream<T, VEC>(qp + oa);
+        if (qc) ca = ldg_stream<T, VEC>(qc + oa);
+        one(oa, wa, pa, ca);
+      }
+    }
+    double* out = qc ? H + (int64_t)j * ldh : wnorm2;
+    if (out != nullptr) block_col_reduce<VEC>(red, acc, active, tid, r, l, lanes, rows_per_pass, c0, k, colmask, out);
+    if (j < n_links) grid.sync();                   // h_j complete (fp64 atomics at L2) before anyone subtracts it
+  }
+}
+
+template <typename T>
+int mgs_chain(T* W, const T* Q, int64_t q_stride, int64_t n_links, double* H, int64_t ldh, double* wnorm2, int64_t n,
+              int64_t b, const int32_t* gate, cudaStream_t st) {
+  COLA_REQUIRE(W && Q && H, "mgs_chain: null pointer");
+  COLA_REQUIRE(n_links >= 1 && n_links < (1 << 20) && ldh >= b, "mgs_chain: bad link count / ldh");
+  if (n <= 0 || b <= 0) return COLA_OK;
+  Shape s = shape_of<T>(n, b, b, W, Q);
+  if (s.vec > 1 && q_stride % s.vec != 0) s = Shape{n, b, b, 1, (int64_t)-1};
+  if (s.k > (int64_t)kSweepThreads * s.vec) return fail(COLA_E_UNSUPPORTED, "mgs_chain: block wider than one sweep slab");
+  int rc = COLA_OK;
+  COLA_DISPATCH_VEC(T, s.vec, ({
+    RowMap m = row_map(s.k, VEC, kSweepThreads);
+    auto kern = mgs_chain_kernel<T, VEC>;
+    static int per_sm = 0;
+    if (per_sm == 0) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kSweepThreads, 0);
+    if (per_sm < 1) return fail(COLA_E_UNSUPPORTED, "mgs_chain: kernel does not fit an SM");
+    int64_t tiles = (s.n + m.rows_per_pass - 1) / m.rows_per_pass;
+    int64_t grid = (int64_t)sm_count() * (per_sm > 4 ? 4 : per_sm);   // co-resident by construction (grid-wide sync)
+    if (grid > tiles) grid = tiles;
+    int nl = (int)n_links;
+    int64_t qs = q_stride, ldh_ = ldh, n_ = s.n, k_ = s.k, ld_ = s.ld, cm = s.colmask;
+    void* args[] = {&W, &Q, &qs, &nl, &H, &ldh_, &wnorm2, &n_, &k_, &ld_, &m.lanes, &m.rows_per_pass, &cm, &gate};
+    cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(kSweepThreads), args, 0, st);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail(COLA_E_UNSUPPORTED, "mgs_chain: cooperative launch refused");
+    }
+    rc = cuda_status("mgs_chain");
+  }));
+  return rc;
+}
+
 }  // namespace cola
 
 // ======================================================================================================
@@ -564,6 +668,10 @@ int cola_device_info(int* sms, int* major, int* minor) {
   int cola_mgs_link_##SFX(T* W, const T* Qprev, const double* hprev, const T* Qcur, double* hcur, double* wnorm2,    \
                           int64_t n, int64_t b, const int32_t* gate, void* s) {                                       \
     return mgs_link<T>(W, Qprev, hprev, Qcur, hcur, wnorm2, n, b, gate, ST(s));                                       \
+  }                                                                                                        \
+  int cola_mgs_chain_##SFX(T* W, const T* Q, int64_t q_stride, int64_t n_links, double* H, int64_t ldh, double* wnorm2, \
+                           int64_t n, int64_t b, const int32_t* gate, void* s) {                                        \
+    return mgs_chain<T>(W, Q, q_stride, n_links, H, ldh, wnorm2, n, b, gate, ST(s));                                    \
   }
 
 COLA_VEC_API(f32, float)

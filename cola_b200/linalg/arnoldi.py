@@ -2,9 +2,10 @@
 289-335).  `arnoldi(A, start_vector, max_iters, tol, use_householder, pbar, key) -> (Q, H, info)`.
 
 The reference's Python `for_loop` over basis vectors (arnoldi.py:304-311: one dot, one store, one axpy per j, each
-a separate eager op with its own temporaries) becomes a chain of `mgs_link` launches: link j subtracts
-h_{j-1} q_{j-1} from w and accumulates h_j = <q_j, w> in the same pass, so w and each q_j cross HBM once per
-link, in exact MGS order (the factorisation matches the reference to rounding, not just to CGS2 accuracy).
+a separate eager op with its own temporaries) becomes ONE cooperative launch per step (`mgs_chain`: pass j subtracts
+h_{j-1} q_{j-1} from w and accumulates h_j = <q_j, w> in the same sweep, grid-wide sync between passes, w resident in
+L2, each q_j read from DRAM once), in exact MGS order (the factorisation matches the reference to rounding, not just
+to CGS2 accuracy).  Blocks the chain kernel declines run the same passes as separate `mgs_link` launches.
 The basis is stored (m+1, n, b), the matmat operand layout.
 """
 import time
@@ -16,6 +17,8 @@ from .. import backend as be
 from .. import rng
 from ..ops import Dense, LinearOperator, Stiefel, lazify
 from .lanczos import BatchedDense
+
+USE_CHAIN = True     # False: one mgs_link launch per link (A/B checks)
 
 
 def arnoldi_fact(A: LinearOperator, rhs, max_iters, tol, pbar=False):
@@ -48,11 +51,12 @@ def arnoldi_fact(A: LinearOperator, rhs, max_iters, tol, pbar=False):
         w = Q[idx + 1]
         A.matmat_into(Q[idx], w)
         h = H64[idx]
-        # MGS chain (arnoldi.py:304-311)
-        be.mgs_link(w, None, None, Q[0], h[0])
-        for j in range(1, idx + 1):
-            be.mgs_link(w, Q[j - 1], h[j - 1], Q[j], h[j])
-        be.mgs_link(w, Q[idx], h[idx], None, None, wnorm2=nrm_sq[idx + 1])
+        # MGS chain (arnoldi.py:304-311): one cooperative launch per step; link by link where the library declines
+        if not (USE_CHAIN and be.mgs_chain(w, Q, idx + 1, h, wnorm2=nrm_sq[idx + 1])):
+            be.mgs_link(w, None, None, Q[0], h[0])
+            for j in range(1, idx + 1):
+                be.mgs_link(w, Q[j - 1], h[j - 1], Q[j], h[j])
+            be.mgs_link(w, Q[idx], h[idx], None, None, wnorm2=nrm_sq[idx + 1])
         be.col_scale(w, w, nrm_sq[idx + 1], take_sqrt=True, mode=3, a=tol / 2.)   # w /= clip(norm, tol/2)
         norm_host = np.sqrt(be.read_small(nrm_sq[idx + 1]).numpy())                         # poll for the stop rule
         if idx == 0:

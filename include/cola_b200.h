@@ -272,6 +272,17 @@ int cola_mgs_link_f32(float* W, const float* Qprev, const double* hprev, const f
 int cola_mgs_link_f64(double* W, const double* Qprev, const double* hprev, const double* Qcur, double* hcur,
                       double* wnorm2, int64_t n, int64_t b, const int32_t* gate, void* stream);
 
+/* The whole MGS chain of one Arnoldi step (arnoldi.py:304-316) in one cooperative launch:
+ *   for j in [0, n_links):  H[j*ldh + c] += sum_i Q_j[i,c] * W[i,c];  W -= (T)H[j*ldh + c] * Q_j     (Q_j = Q + j*q_stride)
+ *   then wnorm2[c] += sum_i W[i,c]^2 (may be NULL)
+ * in exact modified-Gram-Schmidt order (same arithmetic as n_links + 1 cola_mgs_link_* launches), grid-wide syncs
+ * instead of launch boundaries, W kept in L2, each Q_j read from DRAM once.  H rows must be zero on entry.
+ * COLA_E_UNSUPPORTED for blocks wider than 256 16-byte vectors or when a cooperative launch is refused: use the links. */
+int cola_mgs_chain_f32(float* W, const float* Q, int64_t q_stride, int64_t n_links, double* H, int64_t ldh,
+                       double* wnorm2, int64_t n, int64_t b, const int32_t* gate, void* stream);
+int cola_mgs_chain_f64(double* W, const double* Q, int64_t q_stride, int64_t n_links, double* H, int64_t ldh,
+                       double* wnorm2, int64_t n, int64_t b, const int32_t* gate, void* stream);
+
 /* ---- parameter gradients of the backward passes ---------------------------------------------
  * cg_bwd (cola/linalg/inverse/cg.py:72-86) and slq_bwd (cola/linalg/tbd/slq.py:10-31) end in
  * xnp.vjp_derivs(fun = theta -> A(theta) @ V, primals = theta, duals = G) (cola/backends/torch_fns.py:244-260), which

@@ -206,6 +206,16 @@ def mgs_link(W, Qprev, hprev, Qcur, hcur, wnorm2=None, gate=None):
         wnorm2.reshape(-1)[:b] += (W.double() ** 2).sum(0)
 
 
+def mgs_chain(W, Q, n_links, H, wnorm2=None, gate=None):
+    if not _open(gate):
+        return True
+    mgs_link(W, None, None, Q[0], H[0])
+    for j in range(1, n_links):
+        mgs_link(W, Q[j - 1], H[j - 1], Q[j], H[j])
+    mgs_link(W, Q[n_links - 1], H[n_links - 1], None, None, wnorm2=wnorm2)
+    return True
+
+
 def sddmm_csr(rowptr, colidx, n_rows, G, V, alpha, out):
     counts = (rowptr[1:] - rowptr[:-1]).to(torch.int64)
     rows = torch.repeat_interleave(torch.arange(n_rows), counts)
@@ -305,7 +315,7 @@ def mode_contract_tc(M, pre, L, k, inp, out, alpha=1.0, shift=0.0, diag=None, ep
                   dots=dots, dots_row=dots_row, gate=gate)
 
 
-_WRAPPERS = dict(mode_contract_tc=mode_contract_tc, mode_contract_tc_ok=lambda M, pre, L, k, X: False, col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm, csr_spmm_tiled=csr_spmm_tiled,
+_WRAPPERS = dict(mode_contract_tc=mode_contract_tc, mode_contract_tc_ok=lambda M, pre, L, k, X: False, col_dots=col_dots, col_scale=col_scale, axpby=axpby, diag_matmat=diag_matmat, csr_spmm=csr_spmm, csr_spmm_tiled=csr_spmm_tiled, mgs_chain=mgs_chain,
                  mode_contract=mode_contract, reorth_dots=reorth_dots, reorth_update=reorth_update,
                  reorth_update_dots=reorth_update_dots, lanczos_three_term=lanczos_three_term,
                  tridiag_eig_first_row=tridiag_eig_first_row, mgs_link=mgs_link,
