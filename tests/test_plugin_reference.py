@@ -267,7 +267,7 @@ def test_reference_api_over_host_loops_on_emulated_kernels(installed):
         cg_lib.call = lambda name, *a: (launched.append(name), cg_call(name, *a))[1]
         got = run()
     # the B200 host loops really ran (not the reference's): their kernels were "launched"
-    assert {"mode_contract", "csr_spmm", "reorth_update", "mgs_link", "tridiag_eig_first_row", "cola_cg_update_xp_f64",
+    assert {"mode_contract", "csr_spmm", "reorth_update", "mgs_chain", "tridiag_eig_first_row", "cola_cg_update_xp_f64",
             "cola_cg_advance_f64"} <= set(launched)
     for name, r in ref.items():
         gval = got[name]
