@@ -259,7 +259,7 @@ def test_reference_api_over_host_loops_on_emulated_kernels(installed):
     launched = []
     import cola_b200.backend as be
     with emulated_kernels():
-        for name in ("mode_contract", "csr_spmm", "reorth_update", "mgs_link", "tridiag_eig_first_row"):
+        for name in ("mode_contract", "csr_spmm", "reorth_update", "mgs_chain", "tridiag_eig_first_row"):
             fn = getattr(be, name)
             setattr(be, name, (lambda f, n: (lambda *a, **k: (launched.append(n), f(*a, **k))[1]))(fn, name))
         cg_lib = be.lib()
