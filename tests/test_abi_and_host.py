@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     assert L.cdll.cola_version() >= 1
     for family in ("csr_spmm", "mode_contract", "diag_matmat", "col_dots", "col_scale", "axpby", "cg_update_r",
                    "cg_update_xp", "cg_tol", "cg_advance", "reorth_dots", "reorth_update", "lanczos_three_term",
-                   "mgs_link"):
+                   "mgs_link", "mgs_chain", "csr_spmm_tiled"):
         for sfx in ("f32", "f64"):
             assert f"cola_{family}_{sfx}" in decls
 

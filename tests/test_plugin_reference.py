@@ -301,7 +301,7 @@ def test_reference_own_suite_over_host_loops(tmp_path):
     assert " passed" in tail and "failed" not in tail and int(tail.split(" passed")[0].split()[-1]) >= 290, tail
     calls = json.load(open(stats))
     # the fast path was really taken: every loop family launched its kernels
-    for name in ("cola_cg_*", "mode_contract", "lanczos_three_term", "reorth_update", "mgs_link", "tridiag_eig_first_row",
+    for name in ("cola_cg_*", "mode_contract", "lanczos_three_term", "reorth_update", "mgs_chain", "tridiag_eig_first_row",
                  "diag_matmat", "col_scale"):
         assert calls.get(name, 0) > 0, (name, calls)
 
