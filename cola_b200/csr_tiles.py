@@ -42,6 +42,18 @@ def far_diagonal(indices, row_indices, nnz, square):
     return 0
 
 
+def banded_like(indices, row_indices, nnz):
+    """Cheap screen before the tile form is built (sorts and uniques over every non-zero): do a handful of diagonals
+    hold almost all entries?  Sampled; stencil and banded matrices pass, graphs without structure do not."""
+    if nnz == 0:
+        return False
+    step = max(1, nnz // (1 << 20))
+    off = indices[::step].to(torch.int64) - row_indices[::step].to(torch.int64)
+    _, counts = torch.unique(off, return_counts=True)
+    top = torch.sort(counts, descending=True).values[:32]
+    return int(top.sum()) * 10 >= 9 * off.numel()
+
+
 class CsrTiles:
     """See the module docstring.  `strip_rows` = largest R wanted (R becomes the largest divisor of D below it when the
     pattern has a far diagonal D), `cap_rows` = staged rows of X a tile may hold (shared-memory budget of one ring stage), `row_bytes` = bytes of one row of X (k * itemsize: the

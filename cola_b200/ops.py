@@ -709,7 +709,10 @@ class _CsrCore:
                 or not Y.is_contiguous() or self.S.nnz == 0):
             return None
         if row_bytes not in self._tiled:
-            from .csr_tiles import CsrTiles, STRIPS
+            from .csr_tiles import CsrTiles, STRIPS, banded_like
+            if not banded_like(self.S.indices, self.S.row_indices, self.S.nnz):
+                self._tiled[row_bytes] = None
+                return None
             # one ring stage holds, per tile row: ~1.33 staged rows of X (5-point stencil halo), its non-zeros' offsets
             # and values, two row-pointer words; if the halo turns out wider, halve the strips once or twice
             nz_row = 1.05 * self.S.nnz / max(self.S.shape[0], 1) * (4 + X.element_size()) + 8

@@ -464,6 +464,13 @@ def test_spmm_staged_tiles(cb, monkeypatch):
         Ad[rr, cc] = vv
         ref = 2.0 * (Ad @ X.cpu()) + 0.5 * X.cpu()
         assert rel(Y, ref) < 1e-13 and rel(dots, (X.cpu() * ref).sum(0)) < 1e-6
+    # a pattern without diagonals is screened out before the tile form is built (the build sorts every non-zero)
+    S = ops.Sparse(v.to(DEV), r.to(DEV), c.to(DEV), (n, n))
+    Xr = torch.randn(n, 16, dtype=torch.float64, generator=g).to(DEV)
+    import cola_b200.csr_tiles as ct
+    with monkeypatch.context() as mp:
+        mp.setattr(ct, "CsrTiles", lambda *a, **k: (_ for _ in ()).throw(AssertionError("tile form built for a random pattern")))
+        assert S.plan().terms[-1][1][0]._tiles(Xr, torch.empty_like(Xr)) is None
     # values written in place are picked up (the padded copy is refreshed), and a CG solve runs on the staged kernel
     monkeypatch.setattr(ops._CsrCore, "TILE_STAGE_BYTES", 106 << 10)
     data, rows, cols, shape = pb.laplacian_2d_coo(96, torch.float64)
