@@ -16,6 +16,9 @@
 
 namespace cola {
 
+#ifndef TL_UNROLL
+#define TL_UNROLL 2      // non-zeros of a row in flight (measured on cfg2: see profiles/r2_cg_cfg2_summary.md)
+#endif
 constexpr int kTlRec = 32;                       // record words per tile (cola_b200/csr_tiles.py)
 
 template <typename T>

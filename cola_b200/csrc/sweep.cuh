@@ -6,7 +6,13 @@
 // always owns the same columns), are tree-reduced across the block's rows in shared memory and leave the
 // SM as one fp64 atomicAdd per column per block.  HBM-bound by construction: bytes = sum of operand sizes.
 #pragma once
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cola {
 
@@ -18,7 +24,7 @@ constexpr int kSweepThreads = 256;
 template <int VEC>
 __device__ __forceinline__ void block_col_reduce(double* red, const double (&acc)[VEC], bool active, int tid, int r,
                                                  int l, int lanes, int rows, int64_t c0, int64_t k, int64_t colmask,
-                                                 double* out) {
+                                                 double* out, int cluster = 1) {
   __syncthreads();
 #pragma unroll
   for (int v = 0; v < VEC; ++v) red[tid * VEC + v] = active ? acc[v] : 0.0;
@@ -31,6 +37,23 @@ __device__ __forceinline__ void block_col_reduce(double* red, const double (&acc
       for (int v = 0; v < VEC; ++v) red[(r * lanes + l) * VEC + v] += red[((r + s) * lanes + l) * VEC + v];
     }
     __syncthreads();
+  }
+  if (cluster > 1) {
+    // the CTAs of a thread-block cluster fold their column sums through distributed shared memory and leave as ONE
+    // atomic per column per cluster: same-address fp64 atomics serialise at L2 (~40 ns each: 1184 CTAs x 128 columns cost
+    // a 45 us tail on a 60 us sweep), so an 8-CTA cluster cuts that tail 8x
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();                                            // every CTA's row 0 of `red` is final
+    if (cl.block_rank() == 0 && r == 0 && c0 < k) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        double sum = red[l * VEC + v];
+        for (unsigned j = 1; j < cl.num_blocks(); ++j) sum += cl.map_shared_rank(red, j)[l * VEC + v];
+        atomicAdd(out + ((c0 + v) & colmask), sum);
+      }
+    }
+    cl.sync();                                            // nobody's shared memory goes away (or is reused) under the reader
+    return;
   }
   if (r == 0 && c0 < k) {
 #pragma unroll
@@ -50,7 +73,7 @@ __device__ __forceinline__ void block_col_reduce(double* red, const double (&acc
 // column 0 for per-column scalars and reductions.
 template <typename T, int VEC, typename Op>
 __global__ void __launch_bounds__(kSweepThreads)
-    sweep_kernel(int64_t n, int64_t k, int lanes, int rows_per_pass, int64_t colmask, Op op) {
+    sweep_kernel(int64_t n, int64_t k, int lanes, int rows_per_pass, int64_t colmask, Op op, int cluster) {
   constexpr int NACC = Op::NACC;
   if (!op.enabled()) return;
   const int tid = threadIdx.x;
@@ -88,7 +111,7 @@ __global__ void __launch_bounds__(kSweepThreads)
     for (int a = 0; a < NACC; ++a) {
       double* out = op.out(a);
       if (out == nullptr) continue;  // uniform across the grid
-      block_col_reduce<VEC>(red, acc[a], active, tid, r, l, lanes, rows_per_pass, c0, k, colmask, out);
+      block_col_reduce<VEC>(red, acc[a], active, tid, r, l, lanes, rows_per_pass, c0, k, colmask, out, cluster);
     }
   }
 }
@@ -104,11 +127,37 @@ int launch_sweep(int64_t n, int64_t k, int64_t colmask, cudaStream_t st, MakeOp 
     RowMap m = row_map(kk, VEC, kSweepThreads);
     int64_t tiles = (n + m.rows_per_pass - 1) / m.rows_per_pass;
     int64_t tiles2 = (tiles + 1) / 2;
-    int64_t grid = (int64_t)sm_count() * 8;  // 8 x 256 threads = full occupancy, whole waves
+    static const int per_sm = [] { const char* e = getenv("COLA_SWEEP_CTAS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? v : 8; }();
+    int64_t grid = (int64_t)sm_count() * per_sm;  // 8 x 256 threads = full occupancy, whole waves
     if (grid > tiles2) grid = tiles2 > 0 ? tiles2 : 1;
     auto op = make(c);
-    sweep_kernel<T, VEC, decltype(op)><<<(unsigned)grid, kSweepThreads, 0, st>>>(n, kk, m.lanes, m.rows_per_pass,
-                                                                                  colmask, op);
+    using OpT = decltype(op);
+    // kernels with column reductions run as clusters of 8 CTAs (one fp64 atomic per column per cluster, see
+    // block_col_reduce); `out(a)` is uniform over the grid, so every CTA of a cluster takes the same path
+    static const int want_cluster = [] { const char* e = getenv("COLA_SWEEP_CLUSTER"); const int v = e ? atoi(e) : 8; return (v == 1 || v == 2 || v == 4 || v == 8) ? v : 8; }();
+    int cluster = (OpT::NACC > 0 && grid >= 2 * want_cluster) ? want_cluster : 1;
+    if (cluster > 1) {
+      grid = (grid + cluster - 1) / cluster * cluster;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)grid);
+      cfg.blockDim = dim3(kSweepThreads);
+      cfg.dynamicSmemBytes = 0;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)cluster;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_kernel<T, VEC, OpT>, n, kk, m.lanes, m.rows_per_pass, colmask, op, cluster);
+      if (e != cudaSuccess) {          // (not expected on sm_100: fall back to the plain launch)
+        cudaGetLastError();
+        cluster = 1;
+      }
+    }
+    if (cluster == 1)
+      sweep_kernel<T, VEC, OpT><<<(unsigned)grid, kSweepThreads, 0, st>>>(n, kk, m.lanes, m.rows_per_pass, colmask, op, 1);
     int rc = cuda_status(name);
     if (rc) return rc;
   }

@@ -1,11 +1,8 @@
 // Vector sweeps of the Krylov loops: column dots / scalings, CG x-r-p updates and control block,
 // Lanczos three-term step, Arnoldi MGS links, core-less (diagonal) matmat.  All are instances of
 // sweep_kernel (sweep.cuh): one HBM pass over each operand, fp64 per-column reductions.
-#include <cooperative_groups.h>
-
 #include "sweep.cuh"
 
-namespace cg = cooperative_groups;
 namespace cola {
 
 thread_local char g_err[512] = "";

@@ -3,6 +3,9 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import cola_b200 as cb
+if os.environ.get("COLA_LIB"):
+    import cola_b200.backend as _be
+    _be.LIB_PATH = os.path.abspath(os.environ["COLA_LIB"])
 from cola_b200 import backend as be
 from cola_b200.csr_tiles import CsrTiles
 from bench import laplacian_coo, time_kernel
