@@ -487,7 +487,7 @@ int mgs_link(T* W, const T* Qprev, const double* hprev, const T* Qcur, double* h
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kSweepThreads)
     mgs_chain_kernel(T* W, const T* Q, int64_t q_stride, int n_links, double* H, int64_t ldh, double* wnorm2, int64_t n,
-                     int64_t k, int64_t ld, int lanes, int rows_per_pass, int64_t colmask, const int32_t* gate) {
+                     int64_t k, int64_t ld, int lanes, int rows_per_pass, int64_t colmask, const int32_t* gate, int cluster) {
   if (!gate_open(gate)) return;                     // uniform over the grid: nobody reaches a grid sync
   cg::grid_group grid = cg::this_grid();
   __shared__ double red[kSweepThreads * VEC];
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(kSweepThreads)
       }
     }
     double* out = qc ? H + (int64_t)j * ldh : wnorm2;
-    if (out != nullptr) block_col_reduce<VEC>(red, acc, active, tid, r, l, lanes, rows_per_pass, c0, k, colmask, out);
+    if (out != nullptr) block_col_reduce<VEC>(red, acc, active, tid, r, l, lanes, rows_per_pass, c0, k, colmask, out, cluster);
     if (j < n_links) grid.sync();                   // h_j complete (fp64 atomics at L2) before anyone subtracts it
   }
 }
@@ -567,8 +567,32 @@ int mgs_chain(T* W, const T* Q, int64_t q_stride, int64_t n_links, double* H, in
     if (grid > tiles) grid = tiles;
     int nl = (int)n_links;
     int64_t qs = q_stride, ldh_ = ldh, n_ = s.n, k_ = s.k, ld_ = s.ld, cm = s.colmask;
-    void* args[] = {&W, &Q, &qs, &nl, &H, &ldh_, &wnorm2, &n_, &k_, &ld_, &m.lanes, &m.rows_per_pass, &cm, &gate};
-    cudaError_t e = cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(kSweepThreads), args, 0, st);
+    // clusters of 8 CTAs fold their column sums before the atomics (see block_col_reduce): every pass ends in
+    // grid x b same-address atomics, which is what a short pass waits for
+    int cluster = (grid >= 16 && grid * s.k >= 48 * 1024) ? 8 : 1;   // same threshold as launch_sweep
+    cudaError_t e = cudaErrorUnknown;
+    if (cluster > 1) {
+      const int64_t gridc = grid / cluster * cluster;           // (rounding down keeps the grid co-resident)
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)gridc);
+      cfg.blockDim = dim3(kSweepThreads);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = (unsigned)cluster;
+      attr[1].val.clusterDim.y = 1;
+      attr[1].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 2;
+      e = cudaLaunchKernelEx(&cfg, kern, W, Q, qs, nl, H, ldh_, wnorm2, n_, k_, ld_, m.lanes, m.rows_per_pass, cm, gate, cluster);
+      if (e != cudaSuccess) { cudaGetLastError(); cluster = 1; }
+    }
+    if (cluster == 1) {
+      void* args[] = {&W, &Q, &qs, &nl, &H, &ldh_, &wnorm2, &n_, &k_, &ld_, &m.lanes, &m.rows_per_pass, &cm, &gate, &cluster};
+      e = cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)grid), dim3(kSweepThreads), args, 0, st);
+    }
     if (e != cudaSuccess) {
       cudaGetLastError();
       return fail(COLA_E_UNSUPPORTED, "mgs_chain: cooperative launch refused");

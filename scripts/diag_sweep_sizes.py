@@ -7,8 +7,8 @@ from cola_b200 import backend as be
 dev = torch.device("cuda:0")
 dt, sx = torch.float32, "f32"
 lib, st = be.lib(), be.stream_ptr
-k = 128
-for logn in (16, 17, 18, 19, 20, 21):
+k = int(os.environ.get("K", 128))
+for logn in [int(v) for v in os.environ.get("LOGN", "16,17,18,19,20,21").split(",")]:
     n = 1 << logn
     r = torch.randn(n, k, device=dev); ap = torch.randn(n, k, device=dev); x = torch.zeros(n, k, device=dev); p = torch.randn(n, k, device=dev)
     gamma = torch.ones((1000, k), dtype=torch.float64, device=dev); pap = torch.ones((1000, k), dtype=torch.float64, device=dev)
