@@ -762,3 +762,35 @@ def test_vector_sweeps_fold_and_ragged(cb):
             O = torch.empty_like(X)
             be.col_scale(X, O, sq, take_sqrt=True, mode=2)
             assert rel(O, X / torch.sqrt(sq).to(dt)) < (1e-6 if dt == torch.float32 else 1e-14)
+
+
+def test_vector_sweeps_cluster_reduction(cb):
+    """Sweeps that would end in many same-address fp64 atomics (grid x columns >= 48K) run as 8-CTA thread-block
+    clusters whose column sums are folded through distributed shared memory first (csrc/sweep.cuh).  Same sums as the
+    plain launch (up to the fp64 summation order) and as a double-precision torch reduction: the cluster path, the
+    plain path just below the threshold, a grid that is not a multiple of the cluster size before rounding, several
+    column slabs (k > 1024), and a gated launch (every CTA of every cluster leaves before the first cluster sync)."""
+    be = cb.backend
+    for dt in (torch.float32, torch.float64):
+        for n, k in [(40000, 128), (40000, 256), (9001, 512), (300000, 32), (3000, 1500), (1 << 18, 64)]:
+            torch.manual_seed(n + k)
+            X = torch.randn(n, k, dtype=dt, device=DEV)
+            Y = torch.randn(n, k, dtype=dt, device=DEV)
+            d = torch.zeros(k, dtype=torch.float64, device=DEV)
+            be.col_dots(X, Y, d)
+            assert rel(d, (X.double() * Y.double()).sum(0)) < 1e-12, (dt, n, k)
+            d2 = torch.zeros(k, dtype=torch.float64, device=DEV)
+            be.col_dots(X, Y, d2)
+            assert rel(d, d2) < 1e-14                            # run to run: only the order of the fp64 atomics moves
+    # a CG solve whose sweeps take the cluster path (128 columns), against a dense solve
+    n, k = 20000, 128
+    g = torch.Generator().manual_seed(3)
+    dg = (1.0 + torch.rand(n, dtype=torch.float64, generator=g)).to(DEV)
+    lo = (0.3 * torch.rand(n - 1, dtype=torch.float64, generator=g)).to(DEV)
+    A = cb.PSD(cb.ops.Tridiagonal(lo, dg, lo))
+    B = torch.randn(n, k, dtype=torch.float64, generator=g).to(DEV)
+    x, info = cb.linalg.cg(A, B, tol=1e-11, max_iters=500)
+    R = dg[:, None] * x
+    R[1:] += lo[:, None] * x[:-1]
+    R[:-1] += lo[:, None] * x[1:]
+    assert rel(R, B) < 1e-9
