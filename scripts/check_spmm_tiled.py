@@ -43,6 +43,8 @@ for g, k, dt, R, cap in ((96, 16, torch.float64, 32, 400), (160, 32, torch.float
         bad += not ok
         print(f"g={g} k={k} {str(dt)[6:]} R={R} tiles={T.n_tiles} 2d={T.n_tiles2d} regular={T.n_regular} cap_rows={T.cap_rows} {mode}: err {err:.2e} dots {derr:.1e} {'ok' if ok else 'FAIL'}")
 print("FAILURES", bad)
+if os.environ.get("CHECK_ONLY"):
+    sys.exit(1 if bad else 0)
 
 g = int(os.environ.get("GRID", 2048)); k = int(os.environ.get("K", 64))
 data, rows, cols, shape = laplacian_coo(g, torch.float32, dev)
