@@ -102,7 +102,8 @@ def arnoldi_eigs(A: LinearOperator, start_vector=None, max_iters=100, tol=1e-7, 
     Q, H, info = arnoldi(A=A, start_vector=start_vector, max_iters=max_iters, tol=tol,
                          use_householder=use_householder, pbar=pbar, key=key)
     Qd, Hd = Q.to_dense()[:, :-1], H.to_dense()[:-1]
-    eigvals, vs = torch.linalg.eig(Hd)                          # (m x m): not a hot spot
+    eigvals, vs = torch.linalg.eig(Hd.cpu())                    # (m x m) library call, on the host (CUDA eig is a hybrid that goes there anyway)
+    eigvals, vs = eigvals.to(Hd.device), vs.to(Hd.device)
     # complex Ritz vectors: the product Q @ vs is a small-k dense contraction, done on real/imag parts
     Qc = Qd.contiguous()
     re = Dense(Qc) @ vs.real.contiguous()

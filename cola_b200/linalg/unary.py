@@ -46,7 +46,10 @@ class ArnoldiUnary(LinearOperator):
             b = blk.shape[1]
             Q, H, _, info = arnoldi_fact(self.A, blk, max_iters=m, tol=tol)     # Q (m+1, n, b), H (b, m+1, m)
             self.info.update(info)
-            eigvals, P = torch.linalg.eig(H[:, :-1])             # (b, m, m): tiny, library call
+            # (b, m, m): tiny, library call -- on the host: torch's CUDA eig is MAGMA's hybrid geev (it round-trips through
+            # the host anyway and costs 30-40 ms for 16 matrices of 30 x 30; LAPACK on the copies: ~2 ms)
+            eigvals, P = torch.linalg.eig(H[:, :-1].cpu())
+            eigvals, P = eigvals.to(V.device), P.to(V.device)
             nrm = torch.zeros(b, dtype=torch.float64, device=V.device)
             be.col_dots(blk, blk, nrm)
             norms = torch.sqrt(nrm).to(self.dtype)
