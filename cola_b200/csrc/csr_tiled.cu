@@ -3,13 +3,17 @@
 // csr_spmm.cu, from the tile-local form of the pattern built by cola_b200/csr_tiles.py:
 //   * a tile is S strips of R consecutive rows, `stride` rows apart (the pattern's dominant far diagonal), so the rows
 //     of X gathered across that diagonal belong to the neighbouring strips of the SAME tile;
-//   * the distinct rows of X a tile touches arrive in shared memory ONCE, as a few contiguous runs, by bulk copies
-//     (cp.async.bulk, one per run, issued by a producer warp two tiles ahead into a ring); the non-zeros address them by
-//     slot, so the row loop reads shared memory only: no register gather, no L1 lottery;
+//   * the distinct rows of X a tile touches (its own rows included: the fused epilogue's operand) arrive in shared memory
+//     ONCE, as a few contiguous runs, by bulk copies (cp.async.bulk, one per run, issued by a producer warp into a ring of
+//     stages with full / empty mbarriers); the non-zeros address them by byte offset, so the row loop reads shared memory
+//     only: no register gather, no L1 lottery;
 //   * L2 -> SM traffic for a 5-point stencil drops from 3 rows of X per output row (register-gather kernel: 3.2 GB per
-//     cfg2 SpMM at the ~8 TB/s the L2 fabric delivers) to 1.3.
+//     cfg2 SpMM at the ~8 TB/s the L2 fabric delivered it) to 1.3, and the tiles of a CTA run block-fastest (vertical
+//     neighbours back to back) so the halo strips are L2 hits: X crosses DRAM 1.05 times;
+//   * <x, y> partials stay in registers (fp32 over <= 8 tiles, then fp64) and meet in shared memory once per CTA.
 // Tiles the record marks irregular (too many runs / too many distinct rows) gather from global memory in the same loop.
-// X must be contiguous (ldx == k) and k * sizeof(T) a multiple of 16.
+// X must be contiguous (ldx == k) and k * sizeof(T) a multiple of 16.  cfg2 (fp32, k = 64): 0.41 ms = 5.7 TB/s of
+// algorithmic bytes (register-gather kernel: 0.58 ms); bring-up table in profiles/r2_cg_cfg2_summary.md.
 #include <cstdlib>
 
 #include "sweep.cuh"
