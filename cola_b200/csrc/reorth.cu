@@ -111,6 +111,83 @@ __global__ void __launch_bounds__(kDotsThreads) reorth_dots_kernel(RoArgs<T> a) 
   }
 }
 
+// ---- reorth_dots for ONE column (a single Lanczos start vector: BASELINE config 5) -------------------------------
+// The column is swept as 16-byte vectors.  A thread keeps its kD1Rows vectors of W in registers for a whole chunk and
+// walks the basis: per basis vector kD1Rows independent 16-byte loads (two basis vectors in flight), one partial sum, one
+// warp reduction, one add into the warp's own row of shared accumulators (no shared atomics: fp64 ones are CAS loops).
+// The general kernel above gives a warp whole basis vectors in 4 KB pieces and reduces after every piece: 5.0-5.6 TB/s
+// on this shape where the update sweep over the same bytes reaches 7.0.
+constexpr int kD1Threads = 256;
+constexpr int kD1Rows = 8;            // 16-byte vectors of W per thread
+
+template <typename T>
+__global__ void __launch_bounds__(kD1Threads, 2) reorth_dots1_kernel(RoArgs<T> a) {
+  if (a.gate != nullptr && *a.gate != 0) return;
+  constexpr int VEC = 16 / (int)sizeof(T);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int64_t nj = a.j1 - a.j0;
+  double* csm = reinterpret_cast<double*>(smem_raw);                 // [warp][nj]
+  const int tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+  constexpr int kWarps = kD1Threads / 32;
+  for (int64_t i = tid; i < nj * kWarps; i += kD1Threads) csm[i] = 0.0;
+  __syncthreads();
+  double* mine = csm + (int64_t)warp * nj;
+  const int64_t nv = a.n;                                             // 16-byte vectors per column
+  const int64_t chunk = (int64_t)kD1Threads * kD1Rows;
+  const int64_t n_chunks = (nv + chunk - 1) / chunk;
+  for (int64_t ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+    const int64_t base = ch * chunk + tid;
+    Vec<T, VEC> w[kD1Rows];
+    bool ok[kD1Rows];
+#pragma unroll
+    for (int i = 0; i < kD1Rows; ++i) {
+      const int64_t r = base + (int64_t)i * kD1Threads;
+      ok[i] = r < nv;
+      if (ok[i]) w[i] = ldg_stream<T, VEC>(a.Wc + r * VEC);
+      else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) w[i].v[v] = (T)0;
+      }
+    }
+    auto dot_one = [&](const T* vj) {
+      Vec<T, VEC> x[kD1Rows];
+#pragma unroll
+      for (int i = 0; i < kD1Rows; ++i) {
+        if (ok[i]) x[i] = ldg_stream<T, VEC>(vj + (base + (int64_t)i * kD1Threads) * VEC);
+        else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) x[i].v[v] = (T)0;
+        }
+      }
+      T acc = (T)0;
+#pragma unroll
+      for (int i = 0; i < kD1Rows; ++i)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc += x[i].v[v] * w[i].v[v];
+      return (double)acc;
+    };
+    int64_t jj = 0;
+    for (; jj + 1 < nj; jj += 2) {                                     // two basis vectors in flight
+      const T* v0 = a.V + (a.j0 + jj) * a.vstride;
+      double s0 = dot_one(v0), s1 = dot_one(v0 + a.vstride);
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) { mine[jj] += s0; mine[jj + 1] += s1; }
+    }
+    if (jj < nj) {
+      double s0 = warp_sum(dot_one(a.V + (a.j0 + jj) * a.vstride));
+      if (lane == 0) mine[jj] += s0;
+    }
+  }
+  __syncthreads();
+  for (int64_t j = tid; j < nj; j += kD1Threads) {
+    double s = 0.0;
+#pragma unroll
+    for (int wp = 0; wp < kWarps; ++wp) s += csm[(int64_t)wp * nj + j];
+    if (s != 0.0) atomicAdd(a.C + a.j0 + j, s);
+  }
+}
+
 constexpr int kUpdThreads = 256;
 
 template <typename T, int VEC>
@@ -468,6 +545,19 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
     n /= maxv;
     b = maxv;
   }
+  static const bool dots1 = [] { const char* e = getenv("COLA_REORTH_DOTS1"); return !(e && atoi(e) == 0); }();
+  if (fold && dots1 && (j1 - j0) * (kD1Threads / 32) * 8 <= 96 * 1024) {
+    RoArgs<T> a{};
+    a.V = V; a.vstride = vstride; a.j0 = j0; a.j1 = j1; a.Wc = W; a.n = n; a.b = b; a.C = C; a.gate = gate; a.fold = fold;
+    const size_t smem = (size_t)((j1 - j0) * (kD1Threads / 32) * 8);
+    const int64_t chunk = (int64_t)kD1Threads * kD1Rows;
+    int64_t grid = (int64_t)sm_count() * 2;
+    if (grid > (n + chunk - 1) / chunk) grid = (n + chunk - 1) / chunk;
+    auto kern = reorth_dots1_kernel<T>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)grid, kD1Threads, smem, st>>>(a);
+    return cuda_status("reorth_dots");
+  }
   // vector path: b*sizeof(T) a multiple of 16 B and rows 16 B aligned
   int vec = 1;
   {
@@ -490,6 +580,7 @@ int reorth_dots(const T* V, int64_t vstride, int64_t j0, int64_t j1, const T* W,
   int64_t w_rows = (32 * 1024) / (b * (int64_t)sizeof(T));
   if (w_rows < 32 / Lr) w_rows = 32 / Lr;
   if (w_rows > 1024) w_rows = 1024;
+  if (const char* e = getenv("COLA_REORTH_WROWS")) { const int64_t v = atoll(e); if (v >= 32 && v <= 16384) w_rows = v; }   // A/B knob
   const int64_t w_bytes = w_rows * b * (int64_t)sizeof(T);
   int64_t max_nj = (budget - w_bytes) / (b * 8);
   COLA_REQUIRE(max_nj >= 1, "reorth_dots: probe block too wide for shared memory");
