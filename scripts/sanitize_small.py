@@ -17,3 +17,11 @@ A = cb.ops.Tridiagonal(torch.rand(n - 1, device=dev, dtype=torch.float64), 4 + t
 Q, H, info = cb.linalg.arnoldi(A, torch.randn(n, 4, device=dev, dtype=torch.float64), max_iters=6, tol=1e-12)
 print("arnoldi ok", info["iterations"])
 torch.cuda.synchronize()
+# single-column reorth_dots (own kernel): ragged last chunk, odd and even basis sizes
+for n, nj, dt in ((100000, 5, torch.float64), (4100, 2, torch.float32), (2048 * 8 + 8, 1, torch.float64)):
+    V = torch.randn(nj + 1, n, 1, dtype=dt, device=dev); W = torch.randn(n, 1, dtype=dt, device=dev)
+    C = torch.zeros(nj + 1, 1, dtype=torch.float64, device=dev)
+    be.reorth_dots(V, 1, nj + 1, W, C)
+    ref = V[1:, :, 0].double() @ W[:, 0].double()
+    print("reorth_dots1", n, nj, float((C[1:, 0] - ref).abs().max() / ref.abs().max()))
+torch.cuda.synchronize()
