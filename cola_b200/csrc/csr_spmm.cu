@@ -30,6 +30,7 @@ struct CsrArgs {
   int lanes, groups, rows_per_tile, cap;
   int need_x;
   int l2_prefetch, row_bytes;
+  int l2_hints;   // SpMV: evict_last on the X gathers, evict-first on row pointers and Y (COLA_SPMV_L2_HINTS=0: off)
 };
 
 // One staged non-zero: element offset of its X row (col * ldx, computed ONCE per non-zero while staging
@@ -417,9 +418,26 @@ __global__ void __launch_bounds__(kCsrThreads, MINB) csr_spmm_pipe_kernel(CsrArg
 // combined with sub-warp shuffles.  With ~32 registers the SM holds 2048 threads = 256 independent rows in
 // flight, which is what hides the rowptr -> colidx -> X dependent-load chain.
 // ---------------------------------------------------------------------------------------------------
+// gather load that asks L2 to keep the line (evict_last): the slice of X a column strip gathers from is the only reusable
+// data of the sweep; everything else (CSR arrays, row pointers, Y) streams through with evict-first hints
+template <typename T>
+__device__ __forceinline__ T ldg_keep(const T* p, uint64_t pol) {
+  if constexpr (sizeof(T) == 8) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return (T)v;
+  } else {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    return (T)v;
+  }
+}
+
 template <typename T, int KMAX, int SUB, bool EPI, bool DOTS>
 __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
   if (a.gate != nullptr && *a.gate != 0) return;
+  uint64_t keep = 0;
+  if (a.l2_hints) keep = l2_policy_evict_last();
   const int tid = threadIdx.x;
   const int sub = tid % SUB;
   const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + tid) / SUB;
@@ -430,7 +448,7 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
 #pragma unroll
   for (int c = 0; c < KMAX; ++c) dacc[c] = 0.0;
   for (int64_t row = grp; row < a.n_rows; row += n_grp) {
-    const int32_t s = a.rowptr[row], e = a.rowptr[row + 1];
+    const int32_t s = a.l2_hints ? __ldcs(a.rowptr + row) : a.rowptr[row], e = a.l2_hints ? __ldcs(a.rowptr + row + 1) : a.rowptr[row + 1];
     if (!EPI && a.accumulate && s == e) continue;   // a vertical strip without entries in this row: Y stays as it is
     T acc[KMAX];
 #pragma unroll
@@ -442,8 +460,7 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
       const T* xr = a.X + col * a.ldx;
 #pragma unroll
       for (int c = 0; c < KMAX; ++c)
-        if (c < k) acc[c] += w * __ldg(xr + c);   // read-only path: 32-byte sector fills for the random gather
-                                                  // (an L2 evict_last policy on these loads changed nothing: 3.90 ms both ways)
+        if (c < k) acc[c] += w * (a.l2_hints ? ldg_keep<T>(xr + c, keep) : __ldg(xr + c));   // read-only path: 32-byte sector fills
     }
 #pragma unroll
     for (int c = 0; c < KMAX; ++c)
@@ -458,12 +475,13 @@ __global__ void __launch_bounds__(256) csr_spmv_kernel(CsrArgs<T> a) {
             const T xo = a.X[row * a.ldx + c];
             if (a.shift != (T)0) t += a.shift * xo;
             if (a.diag) t += d * xo;
-            if (a.accumulate) t += a.Y[row * a.ldy + c];
+            if (a.accumulate) t += a.l2_hints ? __ldcs(a.Y + row * a.ldy + c) : a.Y[row * a.ldy + c];
             if constexpr (DOTS) dacc[c] += (double)xo * (double)t;
           } else if (a.accumulate) {
-            t += a.Y[row * a.ldy + c];
+            t += a.l2_hints ? __ldcs(a.Y + row * a.ldy + c) : a.Y[row * a.ldy + c];
           }
-          a.Y[row * a.ldy + c] = t;
+          if (a.l2_hints) __stcs(a.Y + row * a.ldy + c, t);
+          else a.Y[row * a.ldy + c] = t;
         }
       }
     }
@@ -533,6 +551,8 @@ int csr_spmm(const int32_t* rowptr, const int32_t* colidx, const T* vals, int64_
     int64_t n_tiles = (n_rows + a.rows_per_tile - 1) / a.rows_per_tile;
     if (k <= 4) {   // SpMV-like: sub-warp-per-row kernel, no staging
       a.k = k;
+      static const int l2_hints = [] { const char* e = getenv("COLA_SPMV_L2_HINTS"); return (e && atoi(e) == 0) ? 0 : 1; }();
+      a.l2_hints = (k <= 2) ? l2_hints : 0;   // cfg5 graph, 45 MB column strips: k = 1 2.26 -> 2.13 ms, k = 2 4.00 -> 3.86, k = 4 7.09 -> 7.44 (off there)
       const double avg_nnz = n_rows > 0 ? (double)nnz / (double)n_rows : 1.0;
       int subw = avg_nnz >= 24 ? 8 : (avg_nnz >= 6 ? 4 : 2);   // measured on the cfg5 graph (17 nnz/row): 4 beats 8 by 4 %
       if (const char* e = getenv("COLA_SPMV_SUB")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8 || v == 16) subw = v; }
