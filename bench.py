@@ -117,9 +117,11 @@ class ClockSampler:
     def __enter__(self):
         if os.environ.get("COLA_BENCH_NO_CLOCKS"):
             return self
-        # 4 samples per second: on some boxes an NVML query stalls kernel LAUNCHES for milliseconds (long kernels do not
+        # 2-3 samples per second: on some boxes an NVML query stalls kernel LAUNCHES for milliseconds (long kernels do not
         # notice, graph replays and copy-stream hand-offs do: cfg3 measured 1650 vs 2350-2560 it/s, e2e 417 vs 463)
-        period = float(os.environ.get("COLA_BENCH_CLOCK_MS", "250")) * 1e-3
+        # (one outlier line of the round, 491 instead of 528-542 it/s with e2e 512 on the same box, had 5 samples in a 1.0 s region:
+        # 2-3 samples per second are enough for a median)
+        period = float(os.environ.get("COLA_BENCH_CLOCK_MS", "400")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -133,6 +135,7 @@ class ClockSampler:
                 return self
 
             def loop():
+                self.stop.wait(min(0.12, period))     # first sample inside the region (under load), not at its start
                 while not self.stop.is_set():
                     try:
                         sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
