@@ -127,8 +127,12 @@ int launch_sweep(int64_t n, int64_t k, int64_t colmask, cudaStream_t st, MakeOp 
     RowMap m = row_map(kk, VEC, kSweepThreads);
     int64_t tiles = (n + m.rows_per_pass - 1) / m.rows_per_pass;
     int64_t tiles2 = (tiles + 1) / 2;
-    static const int per_sm = [] { const char* e = getenv("COLA_SWEEP_CTAS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? v : 8; }();
-    int64_t grid = (int64_t)sm_count() * per_sm;  // 8 x 256 threads = full occupancy, whole waves
+    // resident CTAs per SM: 8 x 256 threads = full occupancy for the pure streams; 4 for sweeps that end in column reductions
+    // (half the cluster syncs and atomics at the end; measured with the cluster reduction on, profiles/r2_sweep_cluster_reduce.log:
+    // update_r 64 MB blocks 37.8 -> 29.5 us, 128 MB 76.8 -> 72.6, 1 GB 517 -> 513; col_dots 53.6 -> 47.9 on 128 MB; axpby loses 2 %)
+    static const int per_sm_env = [] { const char* e = getenv("COLA_SWEEP_CTAS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 8) ? v : 0; }();
+    const int per_sm = per_sm_env ? per_sm_env : (decltype(make(c))::NACC > 0 ? 4 : 8);
+    int64_t grid = (int64_t)sm_count() * per_sm;  // whole waves of resident CTAs
     if (grid > tiles2) grid = tiles2 > 0 ? tiles2 : 1;
     auto op = make(c);
     using OpT = decltype(op);
