@@ -135,7 +135,7 @@ class ClockSampler:
                 return self
 
             def loop():
-                self.stop.wait(min(0.12, period))     # first sample inside the region (under load), not at its start
+                self.stop.wait(min(0.03, period))     # first sample inside the region (under load), not at its very start
                 while not self.stop.is_set():
                     try:
                         sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
@@ -180,6 +180,8 @@ class ClockSampler:
                 self.proc.kill()
         elif self.thread is not None:
             self.thread.join(timeout=1)
+        if not self.rows and self._nvml is not None:
+            self.sample()                              # a region shorter than the first wait: one sample as it ends
 
     def summary(self):
         if not self.rows:
