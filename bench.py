@@ -29,6 +29,7 @@ CPU oracle's trace on the same operator and right-hand sides.  `cpu_baseline` = 
 `--impl reference` times the unmodified reference's CPU path alone on the same `config` (rank 0 only).
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -115,13 +116,18 @@ class ClockSampler:
             pass
 
     def __enter__(self):
+        # every timed region of this file sits inside one of these: no cyclic garbage collection in it (what timeit does too):
+        # a collection pauses the enqueueing thread for tens of milliseconds, longer than the 30 ms of work a CG batch queues
+        gc.collect()
+        self._gc_was_on = gc.isenabled()
+        gc.disable()
         if os.environ.get("COLA_BENCH_NO_CLOCKS"):
             return self
-        # 2-3 samples per second: on some boxes an NVML query stalls kernel LAUNCHES for milliseconds (long kernels do not
+        # a sample every 0.6 s (the first 30 ms in): on some boxes an NVML query stalls kernel LAUNCHES for milliseconds (long kernels do not
         # notice, graph replays and copy-stream hand-offs do: cfg3 measured 1650 vs 2350-2560 it/s, e2e 417 vs 463)
-        # (one outlier line of the round, 491 instead of 528-542 it/s with e2e 512 on the same box, had 5 samples in a 1.0 s region:
-        # 2-3 samples per second are enough for a median)
-        period = float(os.environ.get("COLA_BENCH_CLOCK_MS", "400")) * 1e-3
+        # (six back-to-back cfg2 runs on one box: 3 samples in the 0.93 s region 534 / 540 / 520 / 537 / 490 / 496 it/s with e2e a
+        # steady 515-516 (no sampler there); 2 samples: 538 / 526 / 537 / 536 / 539 / 530; none: 534 / 511 / 536)
+        period = float(os.environ.get("COLA_BENCH_CLOCK_MS", "600")) * 1e-3
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -170,6 +176,8 @@ class ClockSampler:
                 pass
 
     def __exit__(self, *exc):
+        if getattr(self, "_gc_was_on", False):
+            gc.enable()
         self.stop.set()
         if self.proc is not None:
             time.sleep(0.15)
@@ -355,15 +363,19 @@ def run_ours(args):
     except Exception:
         pass
     ctx.barrier()
+    gc.collect()
+    gc.disable()                                                # as in the resident region (ClockSampler.__enter__)
     t0 = time.perf_counter()
     try:
         e2e_iters = e2e_double_buffered(alg, A, B_host, x_host, dev, args.steps)
         e2e_s = time.perf_counter() - t0
+        gc.enable()
         # the copies ran on side streams: check that what arrived on the host is the solution
         err = float((x_host.to(dev) - x_ref).norm() / x_ref.norm())
         if not err < 1e-3:
             raise RuntimeError(f"double-buffered e2e returned a different solution (relative error {err:.2e})")
     except Exception as exc:                                   # measure the plain serial form instead
+        gc.enable()
         e2e_mode = f"serial (double-buffered path failed: {type(exc).__name__}: {exc})"[:200]
         torch.cuda.synchronize()
         t0 = time.perf_counter()
