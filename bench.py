@@ -485,12 +485,12 @@ def secondary_cfg3(ctx, cb, iters=100, reps=25):
         alg(A, B)
     ctx.barrier()
     l0 = lib.launch_count()
-    with ClockSampler(ctx.local, background=False) as clocks:    # sampled from this thread, every fifth solve (see ClockSampler)
+    with ClockSampler(ctx.local, background=False) as clocks:    # sampled from this thread, twice (see ClockSampler)
         def solves():
             out = None
             for i in range(reps):
                 out = alg(A, B)
-                if i % 5 == 2:
+                if i in (reps // 3, (2 * reps) // 3):    # two samples under load (an NVML query costs up to ~25 ms on some boxes)
                     clocks.sample()
             return out
         s, (x, info) = _timed(solves)
